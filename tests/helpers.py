@@ -1,0 +1,36 @@
+"""Shared helpers for the parity tests (test infrastructure)."""
+import os
+
+import numpy as np
+import torch
+
+from oracle import vsrd_oracle as oracle
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+RENDER_CASES = ["box_f32", "residual_f32", "residual_f64", "late_f32", "late_f64"]
+
+
+def load_golden(name):
+    data = np.load(os.path.join(GOLDEN_DIR, f"render_{name}.npz"))
+    return {k: torch.from_numpy(data[k]) for k in data.files}
+
+
+def scene_from_golden(g, dtype=None, requires_grad=False, device="cpu"):
+    def leaf(key):
+        if key not in g:
+            return None
+        t = g[key].to(device=device, dtype=dtype or g[key].dtype).clone()
+        return t.requires_grad_(requires_grad)
+
+    return oracle.Scene(
+        locations=leaf("locations"), rotations=leaf("rotations"), half_extents=leaf("half_extents"),
+        mlp_weights=leaf("mlp_weights"), temperature=float(g["temperature"]))
+
+
+def render_kwargs(g):
+    return dict(num_samples=int(g["num_samples"]), distance_range=[0.0, 100.0],
+                sdf_std_deviation=float(g["std_deviation"]), cosine_ratio=float(g["cosine_ratio"]))
+
+
+def rel_l2(a, b):
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
