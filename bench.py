@@ -1,0 +1,476 @@
+#!/usr/bin/env python
+"""Throughput of the VSRD silhouette-renderer hot path (BASELINE.json metric: ray-samples/s fwd+bwd).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+One "step" = one optimisation step's renderer work on one synthetic KITTI-360-shaped target frame
+(configs[1]: 376x1408, 17 views, 8 instances, 1000 rays, 100+100 samples, residual field on):
+ray gather -> coarse pass -> importance resampling -> fine pass + silhouette/eikonal loss ->
+backward to the gradients of (locations, rotations, half extents, residual-MLP weights).
+Unit of work: ray-samples = R * ((S-1) + (2S-1)) per step.
+
+  value       device-resident inputs, raw kernel sequence replayed as a CUDA graph, CUDA-event timed,
+              L2 flushed between steps, max over ranks.
+  e2e         same metric through the public drop-in API (vsrd.models + vsrd.rendering closures as
+              scripts/main.py composes them, autograd backward, Adam step) with the step's inputs
+              coming from pinned host memory and the loss read back to the host every step.
+  roofline    dominant kernel (field backward) against the FP32-FMA peak.
+  cpu_baseline  oracle port (the reference's PyTorch algorithm) on the host cores, bounded sample.
+
+`--impl reference` times that CPU port alone (rank 0 only under torchrun).
+Multi-GPU: frame-parallel, one frame per rank, no collective on the data path (weak scaling).
+"""
+from __future__ import annotations
+
+import argparse
+import functools
+import json
+import math
+import os
+import statistics
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+F_MLP = 2 * (16 * 49 + 3 * 16 * 17 + 17)       # 3234 contraction flop per MLP value pass
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--rays", type=int, default=1000)
+    ap.add_argument("--samples", type=int, default=100)
+    ap.add_argument("--instances", type=int, default=8)
+    ap.add_argument("--views", type=int, default=17)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--cpu-sample-rays", type=int, default=250)
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# Mid-schedule operating point (step 1500 of 3000, residual field on): scripts/main.py:420-431
+def schedule_at(frac=0.5):
+    anneal = lambda hi, lo: (math.cos(math.pi * frac) + 1.0) / 2.0 * (hi - lo) + lo
+    return dict(temperature=anneal(1.0, 0.1), std_deviation=anneal(1.0, 0.1), cosine_ratio=frac)
+
+
+def workload_name(args):
+    return (f"configs[1]: synthetic KITTI-360 frame 376x1408, V={args.views}, N={args.instances}, "
+            f"R={args.rays} rays/step, S={args.samples}+{args.samples} samples/ray, residual MLP 48-16x4-1")
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference arm (oracle port) -- also used for cpu_baseline
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(args, steps, warmup, num_rays):
+    """Times the oracle (oracle/vsrd_oracle.py: the reference's PyTorch algorithm) on the host cores:
+    detector decode + hypernetwork + two-pass renderer + BCE/eikonal + backward to the leaf parameters."""
+    from oracle import vsrd_oracle as oracle
+    from vsrd_b200 import synthetic
+
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    frame = synthetic.make_frame(args.instances, args.views, seed=0)
+    gen = torch.Generator().manual_seed(0)
+    inv_proj, cam = frame.inverse_projections()
+    raw_loc, raw_dim, raw_ori = synthetic.perturbed_raw_parameters(frame, seed=0)
+    leaves = [t.clone().requires_grad_(True) for t in (raw_loc, raw_dim, raw_ori)]
+    emb = torch.rand(256, generator=gen).repeat(args.instances, 1).requires_grad_(True)
+    torch.manual_seed(0)
+    hyper = oracle.HyperNetwork()
+    sched = schedule_at()
+    h, w = frame.image_size
+    times = []
+    for it in range(warmup + steps):
+        pix = frame.draw_pixel_indices(num_rays, gen)
+        view = pix // (h * w)
+        v, u = (pix // w) % h, pix % w
+        d = torch.einsum("rmn,rn->rm", inv_proj[view], torch.stack([u, v, torch.ones_like(u)], -1).float())
+        d = torch.nn.functional.normalize(d, dim=-1)
+        o = cam[view]
+        targets = torch.rand(num_rays, args.instances, generator=gen)
+        t0 = time.perf_counter()
+        loc, dim, rot = oracle.decode_box_parameters(*leaves)
+        scene = oracle.Scene(loc, rot, dim, hyper(emb), sched["temperature"])
+        loss, _ = oracle.render_loss(scene, o, d, targets, num_samples=args.samples, distance_range=[0.0, 100.0],
+                                     sdf_std_deviation=sched["std_deviation"], cosine_ratio=sched["cosine_ratio"])
+        loss.backward()
+        float(loss)
+        dt = time.perf_counter() - t0
+        for p in [*leaves, emb, *hyper.parameters()]:
+            p.grad = None
+        if it >= warmup:
+            times.append(dt)
+    per_step = sum(times) / len(times)
+    units = num_rays * (3 * args.samples - 2)
+    return dict(value=units / per_step, ms_per_step=per_step * 1e3, cores=threads,
+                sample=f"{num_rays} of {args.rays} rays/step, same frame shape, {warmup} warm-up + {steps} timed steps")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    res = cpu_reference_run(args, max(1, args.steps), max(1, args.warmup), args.cpu_sample_rays)
+    line = {
+        "impl": "reference", "metric": "ray_samples_per_sec_fwd_bwd", "value": res["value"], "unit": "ray-samples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "note": "CPU oracle port of the reference's PyTorch renderer; "
+                   "each step is a bounded sample of the workload (see cpu_baseline.sample)"},
+        "cpu_baseline": {"value": res["value"], "unit": "ray-samples/s", "cores": res["cores"], "kind": "port",
+                         "sample": res["sample"]},
+        "e2e": {"value": res["value"], "unit": "ray-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake_slowdown": 0x80}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+        return False
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "note": "NVML unavailable"}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# native arm
+# ------------------------------------------------------------------------------------------------
+def build_frame_inputs(args, rank, device, steps_total):
+    """Synthetic frame, per-step ray batches and silhouette targets (rendered from the GT boxes)."""
+    from vsrd_b200 import functional as F
+    from vsrd_b200 import ops, synthetic
+
+    frame = synthetic.make_frame(args.instances, args.views, seed=rank)
+    gen = torch.Generator().manual_seed(100 + rank)
+    inv_proj, cam = frame.inverse_projections()
+    pool = torch.stack([frame.draw_pixel_indices(args.rays, gen) for _ in range(steps_total)])   # [T,R] int64
+    h, w = frame.image_size
+    # targets: hard-ish silhouettes of the ground-truth boxes through the same renderer
+    targets = []
+    gt = [t.to(device) for t in (frame.gt_locations, frame.gt_rotations, frame.gt_half_extents)]
+    for k in range(steps_total):
+        o, d = ops.gather_rays(inv_proj.to(device), cam.to(device), pool[k].to(device), h, w)
+        with torch.no_grad():
+            lab, *_ = F.two_pass_render(*gt, None, o, d, num_samples=args.samples, temperature=0.1,
+                                        std_deviation=0.1, cosine_ratio=1.0, seed=k)
+        targets.append(lab.clamp(0.0, 1.0).cpu())
+    return frame, inv_proj, cam, pool, torch.stack(targets)
+
+
+def make_models(args, frame, rank, device):
+    import vsrd
+    from vsrd_b200 import synthetic
+
+    torch.manual_seed(rank)
+    detector = vsrd.models.BoxParameters3D(batch_size=1, num_instances=args.instances)
+    hyper = vsrd.models.HyperDistanceField(in_channels=48, out_channels_list=[16, 16, 16, 16],
+                                           hyper_in_channels=256, hyper_out_channels_list=[256, 256, 256, 256])
+    encoder = vsrd.models.SinusoidalEncoder(num_frequencies=8)
+    raw_loc, raw_dim, raw_ori = synthetic.perturbed_raw_parameters(frame, seed=rank)
+    with torch.no_grad():
+        detector.locations.copy_(raw_loc[None])
+        detector.dimensions.copy_(raw_dim[None])
+        detector.orientations.copy_(raw_ori[None])
+    return detector.to(device), hyper.to(device), encoder.to(device)
+
+
+def main_style_step(vsrd, model_tuple, config, rays_o, rays_d, targets, sched, num_instances):
+    """The renderer part of one scripts/main.py step, written against the drop-in API exactly as the
+    script composes it (closures of main.py:433-523, 530-578, 629-687)."""
+    import torch.nn as nn
+    detector, hyper, encoder = model_tuple
+
+    class _NS:
+        pass
+    models = _NS()   # what main.py calls `models` (attribute access)
+    models.positional_encoder, models.hyper_distance_field, models.detector = encoder, hyper, detector
+    world = detector()
+    weights = hyper(world["embeddings"])
+
+    def residual_distance_field(distance_field):
+        def wrapper(positions):
+            x, y, z = torch.unbind(positions, dim=-1)
+            positions = torch.stack([torch.abs(x), y, z], dim=-1) / max(config.volume_rendering.distance_range)
+            return torch.sigmoid(distance_field(models.positional_encoder(positions)) - 1.0)
+        return wrapper
+
+    def residual_composition(distance_field, residual_distance_field):
+        def wrapper(positions):
+            return distance_field(positions) + residual_distance_field(positions)
+        return wrapper
+
+    def instance_field(distance_field, instance_label):
+        def wrapper(positions):
+            distances = distance_field(positions)
+            labels = nn.functional.one_hot(instance_label, num_instances)
+            return distances, labels.expand(*distances.shape[:-1], -1)
+        return wrapper
+
+    def soft_union(distance_fields, temperature):
+        def wrapper(positions):
+            distances, labels = map(torch.stack, zip(*[f(positions) for f in distance_fields]))
+            w = nn.functional.softmin(distances / temperature, dim=0)
+            return torch.sum(distances * w, dim=0), torch.sum(labels * w, dim=0)
+        return wrapper
+
+    field = soft_union(
+        distance_fields=[
+            vsrd.rendering.sdfs.translation(
+                vsrd.rendering.sdfs.rotation(
+                    instance_field(
+                        distance_field=residual_composition(
+                            distance_field=vsrd.rendering.sdfs.box(dimension),
+                            residual_distance_field=residual_distance_field(
+                                distance_field=functools.partial(hyper.distance_field, w_i)),
+                        ),
+                        instance_label=i,
+                    ),
+                    orientation),
+                location)
+            for i, (location, dimension, orientation, w_i) in enumerate(zip(
+                world["locations"][0], world["dimensions"][0], world["orientations"][0], weights[0]))
+        ],
+        temperature=sched["temperature"],
+    )
+    render = vsrd.rendering.hierarchical_volumetric_rendering
+    kwargs = dict(distance_field=field, ray_positions=rays_o, ray_directions=rays_d,
+                  distance_range=config.volume_rendering.distance_range, num_samples=config.volume_rendering.num_fine_samples,
+                  sdf_std_deviation=sched["std_deviation"], cosine_ratio=sched["cosine_ratio"])
+    with torch.no_grad():
+        *_, sampled_distances, sampled_weights = render(**kwargs)
+    labels, gradients, _, _ = render(**kwargs, sampled_distances=sampled_distances, sampled_weights=sampled_weights)
+    silhouette = nn.functional.binary_cross_entropy(labels.clamp(1.0e-6, 1.0 - 1.0e-6), targets, reduction="none").mean()
+    eikonal = nn.functional.mse_loss(torch.norm(gradients, dim=-1), gradients.new_ones(*gradients.shape[:-1]))
+    return silhouette + 0.01 * eikonal
+
+
+def run_native(args):
+    import vsrd
+    from vsrd_b200 import _lib, ops
+    from vsrd_b200.engine import SilhouetteStep
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py: no CUDA device; the native arm has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+    _lib.load()
+
+    K, W = args.steps, max(args.warmup, 3)
+    total = K + W
+    frame, inv_proj, cam, pool, targets = build_frame_inputs(args, rank, device, total)
+    detector, hyper, encoder = make_models(args, frame, rank, device)
+    sched = schedule_at()
+    units = args.rays * (3 * args.samples - 2)
+
+    # ---------------- device-resident leg ("value") ----------------
+    with torch.no_grad():
+        world_out = detector()
+        mlp_w = hyper(world_out["embeddings"])[0]
+    step = SilhouetteStep(inv_projection=inv_proj, camera_positions=cam, image_size=frame.image_size,
+                          num_rays=args.rays, num_samples=args.samples, device=device)
+    step.set_parameters(world_out["locations"][0], world_out["orientations"][0], world_out["dimensions"][0], mlp_w)
+    step.set_schedule(**sched)
+    pool_dev, targets_dev = pool.to(device), targets.to(device)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)   # > 126 MB L2
+    step.set_batch(pool_dev[0], targets_dev[0])
+    use_graph = not args.no_graph
+    if use_graph:
+        step.capture()
+    runner = step.run if use_graph else step.run_eager
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    for k in range(W):
+        step.set_batch(pool_dev[k], targets_dev[k])
+        runner()
+    barrier()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    with ClockSampler(local_rank) as clocks:
+        for k in range(K):
+            step.set_batch(pool_dev[W + k], targets_dev[W + k])
+            flush.zero_()                                  # evict L2 between timed steps (outside the events)
+            starts[k].record()
+            runner()
+            ends[k].record()
+        barrier()
+    dev_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
+    loss_value = float(step.out["loss_parts"].sum())
+    if not math.isfinite(loss_value):
+        raise RuntimeError("bench.py: non-finite loss from the device-resident leg")
+
+    # per-kernel breakdown (eager, event per launch) for the roofline of the dominant kernel
+    per_kernel = {}
+    reps = 10
+    for k in range(reps):
+        step.set_batch(pool_dev[(W + k) % total], targets_dev[(W + k) % total])
+        flush.zero_()
+        step.timers = []
+        step.run_eager()
+        torch.cuda.synchronize()
+        for (n0, e0), (n1, e1) in zip(step.timers[:-1], step.timers[1:]):
+            per_kernel.setdefault(n1, []).append(e0.elapsed_time(e1))
+    step.timers = None
+    per_kernel = {k: statistics.median(v) for k, v in per_kernel.items()}
+
+    # ---------------- end-to-end leg through the public API ----------------
+    config = vsrd.utils.Dict.apply(dict(volume_rendering=dict(distance_range=[0.0, 100.0], num_fine_samples=args.samples)))
+    params = [
+        dict(params=[detector.locations], lr=1e-2), dict(params=[detector.dimensions], lr=1e-2),
+        dict(params=[detector.orientations], lr=1e-2), dict(params=[detector.embeddings], lr=1e-3),
+        dict(params=list(hyper.parameters()), lr=1e-4),
+    ]
+    optimizer = torch.optim.Adam(params, lr=1e-2)
+    pool_pin, targets_pin = pool.pin_memory(), targets.pin_memory()
+    inv_proj_dev, cam_dev = inv_proj.to(device), cam.to(device)
+    h, w = frame.image_size
+
+    def e2e_step(k):
+        pix = pool_pin[k].to(device, non_blocking=True)                  # H2D: ray selection of this step
+        tgt = targets_pin[k].to(device, non_blocking=True)               # H2D: silhouette targets
+        rays_o, rays_d = ops.gather_rays(inv_proj_dev, cam_dev, pix, h, w)
+        optimizer.zero_grad(set_to_none=True)
+        loss = main_style_step(vsrd, (detector, hyper, encoder), config, rays_o, rays_d, tgt, sched, args.instances)
+        loss.backward()
+        optimizer.step()
+        return float(loss)                                               # D2H: the step's loss
+
+    for k in range(W):
+        e2e_step(k)
+    barrier()
+    e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e_start.record()
+    for k in range(K):
+        last = e2e_step(W + k)
+    e_end.record()
+    barrier()
+    e2e_ms = e_start.elapsed_time(e_end)
+    if not math.isfinite(last):
+        raise RuntimeError("bench.py: non-finite loss from the end-to-end leg")
+
+    # ---------------- reduce over ranks ----------------
+    t = torch.tensor([dev_ms, e2e_ms], device=device, dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        sm_max = float(peaks.get("sm_max_mhz", 1965.0))
+        sms = torch.cuda.get_device_properties(device).multi_processor_count
+        fma_peak_tflops = sms * 128 * 2 * sm_max * 1e6 / 1e12
+        m_fine = 2 * args.samples - 1
+        bwd_ms = per_kernel.get("field_backward", float("nan"))
+        # algorithmic contraction flops of the backward field kernel: 4F per (fine sample, instance)
+        # (reverse-over-reverse beyond the 2F forward; the kernel's own 2F recompute earns no credit)
+        bwd_flops = 4 * F_MLP * args.instances * args.rays * m_fine
+        achieved = bwd_flops / (bwd_ms * 1e-3) / 1e12 if bwd_ms == bwd_ms and bwd_ms > 0 else None
+        hbm_bytes = 80 * args.instances * args.rays * m_fine   # 80*N B per fine ray-sample (3-kernel split)
+        line = {
+            "metric": "ray_samples_per_sec_fwd_bwd",
+            "value": world * units * K / (dev_ms * 1e-3),
+            "unit": "ray-samples/s",
+            "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": dev_ms / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args), "l2": "flushed (256 MiB memset) between timed steps",
+                       "schedule": sched, "graph": use_graph, "parallelism": f"frame-parallel x{world}, no collective"},
+            "e2e": {"value": world * units * K / (e2e_ms * 1e-3), "unit": "ray-samples/s",
+                    "ms_per_step": e2e_ms / K,
+                    "h2d_bytes_per_step": int(pool[0].numel() * 8 + targets[0].numel() * 4),
+                    "d2h_bytes_per_step": 4,
+                    "api": "vsrd.models + vsrd.rendering.hierarchical_volumetric_rendering (main.py closures) + autograd + Adam"},
+            "gpu_launches": SilhouetteStep.KERNELS_PER_STEP * K,
+            "roofline": {"bound": "fp32_fma", "kernel": "field_backward_kernel<residual>", "achieved": achieved,
+                         "peak": fma_peak_tflops, "unit": "TFLOP/s",
+                         "frac": (achieved / fma_peak_tflops) if achieved else None, "traffic": None,
+                         "peak_source": f"{sms} SMs x 128 lanes x 2 x sm_max_mhz {sm_max:.0f} (MEASURED_PEAKS.json clock)",
+                         "kernel_ms": bwd_ms, "algorithmic_flops_per_launch": bwd_flops,
+                         "algorithmic_hbm_bytes_per_step": hbm_bytes,
+                         "hbm_peak_gbs": peaks.get("hbm_gbs")},
+            "kernel_ms": per_kernel,
+            "clocks": clocks.summary(),
+            "loss": loss_value,
+        }
+        if world == 1 and not args.skip_cpu_baseline:
+            res = cpu_reference_run(args, steps=3, warmup=1, num_rays=args.cpu_sample_rays)
+            line["cpu_baseline"] = {"value": res["value"], "unit": "ray-samples/s", "cores": res["cores"],
+                                    "kind": "port", "sample": res["sample"], "ms_per_step": res["ms_per_step"]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_native(a)

@@ -1,0 +1,137 @@
+/* vsrd_b200 — C ABI of the B200-native VSRD silhouette-renderer hot path.
+ *
+ * The reference (skmhrk1209/VSRD) is pure Python/PyTorch and has no FFI layer of its own
+ * (SURVEY.md §8b).  Each entry point below replaces the named reference function; the Python
+ * host layer (vsrd_b200/, vsrd/) binds them with ctypes and re-exposes the reference's own
+ * call signatures on top.  INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to contiguous fp32 (or int64 where stated) unless the
+ *     parameter name starts with `host_`;
+ *   - all calls are asynchronous on `stream` (a cudaStream_t passed as void*), perform no host
+ *     synchronisation and are CUDA-graph capturable;
+ *   - buffers are borrowed for the duration of the call; outputs are caller-allocated;
+ *   - return value: 0 on success, non-zero on error; vsrd_last_error() returns a thread-local,
+ *     human-readable message for the last failure on the calling thread;
+ *   - layouts are RAY-MAJOR: distances[R][M+1], per-sample outputs [R][M][...];
+ *     the reference's sample-major tensors ([M, R, ...]) are permuted views of these.
+ *
+ * Symbols: R = rays, S = num_samples, M = intervals per ray (S-1 in pass 1, 2S-1 in pass 2),
+ *          N = instances, NW = 1617 residual-MLP weights per instance (48-16-16-16-16-1).
+ */
+#ifndef VSRD_B200_H_
+#define VSRD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VSRD_MLP_WEIGHTS 1617
+#define VSRD_GRAD_STRIDE 1632   /* 1617 weights + 15 pose gradients (t, half extents, R), padded */
+#define VSRD_MAX_INSTANCES 32
+#define VSRD_MAX_INTERVALS 512
+
+/* Decoded per-frame parameters: what scripts/main.py:530-618 closes over when it composes
+ * soft_union(translation(rotation(instance_field(box [+ residual])))). */
+typedef struct VsrdScene {
+    int32_t num_instances;        /* N <= VSRD_MAX_INSTANCES */
+    int32_t _pad;
+    const float* locations;       /* [N,3]   world_outputs.locations                         */
+    const float* rotations;       /* [N,3,3] world_outputs.orientations, p = (x - t) @ R      */
+    const float* half_extents;    /* [N,3]   world_outputs.dimensions                         */
+    const float* mlp_weights;     /* [N,NW]  hyper_distance_field(embeddings) or NULL (warm-up)*/
+    float temperature;            /* sdf_union_temperature (main.py:422-426)                  */
+    float scale;                  /* max(distance_range) (main.py:441)                        */
+} VsrdScene;
+
+typedef struct VsrdRays {
+    int32_t num_rays;             /* R */
+    int32_t num_intervals;        /* M <= VSRD_MAX_INTERVALS; distances hold M+1 entries per ray */
+    const float* origins;         /* [R,3]   ray_positions                                    */
+    const float* directions;      /* [R,3]   ray_directions                                   */
+    const float* distances;       /* [R,M+1] sampled_distances, ascending                     */
+} VsrdRays;
+
+/* Arguments of hierarchical_volumetric_rendering (vsrd/rendering/renderers.py:177-188). */
+typedef struct VsrdRenderParams {
+    float std_deviation;          /* sdf_std_deviation */
+    float cosine_ratio;
+    float epsilon;                /* 1e-6 */
+    float _pad;
+} VsrdRenderParams;
+
+/* Optional in-kernel loss (scripts/main.py:653-687, 855): loss = sil_w * mean BCE(clamp(labels), targets)
+ * + eik_w * mean((|grad| - 1)^2).  targets == NULL disables it. */
+typedef struct VsrdLoss {
+    const float* targets;         /* [R,N] soft-mask targets in label order, or NULL            */
+    float silhouette_weight;
+    float eikonal_weight;         /* 0 during warm-up                                           */
+} VsrdLoss;
+
+int vsrd_version(void);
+const char* vsrd_last_error(void);
+
+/* Number of thread blocks per instance the backward field kernel uses for (N,R,M); the caller
+ * provides `partials` with N * that * VSRD_GRAD_STRIDE floats. */
+int vsrd_backward_blocks_per_instance(int num_instances, int num_rays, int num_intervals);
+
+/* ---- a1: vsrd.rendering.ray_casting (vsrd/rendering/utils.py:5-18) ----------------------
+ * inv_projection[V][9] = inv(E)[:3,:3] @ inv(K) (row-major); out directions[V][H][W][3]. */
+int vsrd_ray_directions(const float* inv_projection, int num_views, int height, int width,
+                        float* directions, void* stream);
+
+/* Rays for `num_rays` flat pixel indices into [V,H,W] (scripts/main.py:632-633 gathers them from
+ * the [V,H,W,3] tensors; here they are generated on the fly).  camera_positions[V][3]. */
+int vsrd_gather_rays(const float* inv_projection, const float* camera_positions, const int64_t* pixel_indices,
+                     int num_rays, int num_views, int height, int width,
+                     float* origins, float* directions, void* stream);
+
+/* ---- a9: quadrature_sampler (vsrd/rendering/samplers.py:5-8) ----------------------------
+ * bins[S+1]; jitter[R][S] in [0,1) or NULL to draw from the counter-based generator (seed).
+ * out distances[R][S]. */
+int vsrd_place_coarse(const float* bins, const float* jitter, uint64_t seed, int num_rays, int num_samples,
+                      float* distances, void* stream);
+
+/* ---- a10: inverse_transform_sampler + concat + sort (samplers.py:11-36, renderers.py:196-210)
+ * coarse_distances[R][S], coarse_weights[R][S-1]; sorted_uniforms[R][S] or NULL (generator);
+ * out distances[R][2S], ascending. */
+int vsrd_place_fine(const float* coarse_distances, const float* coarse_weights, const float* sorted_uniforms,
+                    uint64_t seed, int num_rays, int num_samples, float* distances, void* stream);
+
+/* ---- a5-a8: per-(sample, instance) field: box SDF + residual MLP, value and spatial gradient.
+ * out field[N][R*M] as float4 (d_i, dd_i/dx, dd_i/dy, dd_i/dz). */
+int vsrd_field_forward(const VsrdScene* scene, const VsrdRays* rays, float* field, void* stream);
+
+/* ---- a8 (soft union) + a11 (renderers.py:218-263): union, SDF->opacity, front-to-back compositing.
+ * out labels[R][N], gradients[R][M][3] (un-normalised union gradient), weights[R][M].
+ * If loss->targets != NULL also accumulates loss_out[0] += BCE sum / (R*N) * w, loss_out[1] += eikonal
+ * mean * w (loss_out must be zeroed by the caller); loss/loss_out may be NULL. */
+int vsrd_composite_forward(const VsrdScene* scene, const VsrdRays* rays, const VsrdRenderParams* params,
+                           const float* field, float* labels, float* gradients, float* weights,
+                           const VsrdLoss* loss, float* loss_out, void* stream);
+
+/* ---- backward of the above (replaces the autograd double-backward replay, a16).
+ * Upstream gradients grad_labels[R][N], grad_gradients[R][M][3], grad_weights[R][M]; each may be
+ * NULL.  If loss->targets != NULL the loss gradients are generated in-kernel from `labels`
+ * (the forward output) instead and added to the explicit ones.
+ * out adjoint[N][R*M] as float4: adjoints of (d_i, grad d_i). */
+int vsrd_composite_backward(const VsrdScene* scene, const VsrdRays* rays, const VsrdRenderParams* params,
+                            const float* field, const float* grad_labels, const float* grad_gradients,
+                            const float* grad_weights, const VsrdLoss* loss, const float* labels,
+                            float* adjoint, void* stream);
+
+/* Reduces adjoint[N][R*M] into parameter gradients (recomputing the per-sample forward):
+ * grad_locations[N][3], grad_rotations[N][9], grad_half_extents[N][3], grad_mlp_weights[N][NW]
+ * (NULL when scene->mlp_weights is NULL).  `partials` is scratch, see
+ * vsrd_backward_blocks_per_instance(). Outputs are overwritten (not accumulated). */
+int vsrd_field_backward(const VsrdScene* scene, const VsrdRays* rays, const float* adjoint, float* partials,
+                        float* grad_locations, float* grad_rotations, float* grad_half_extents,
+                        float* grad_mlp_weights, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* VSRD_B200_H_ */

@@ -1,0 +1,78 @@
+"""CPU-side checks of the C-ABI boundary: the library builds/loads without a GPU and exports every
+symbol include/vsrd_b200.h declares; the ctypes structs match the header's layout."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "vsrd_b200.h")
+
+
+def _declared_functions():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(vsrd_[a-z_0-9]+)\s*\(", text)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from vsrd_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        from vsrd_b200 import build
+        build.build()
+    return _lib.load()
+
+
+def test_header_declares_expected_entry_points():
+    names = _declared_functions()
+    assert "vsrd_field_forward" in names and "vsrd_field_backward" in names
+    assert "vsrd_composite_forward" in names and "vsrd_composite_backward" in names
+    assert len(names) >= 11
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from vsrd_b200 import _lib
+    for name in _declared_functions():
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
+    assert sorted(_lib.SIGNATURES) == _declared_functions()
+
+
+def test_version_and_error_string_callable_without_gpu(lib):
+    assert lib.vsrd_version() == 1
+    assert isinstance(lib.vsrd_last_error(), bytes)
+
+
+def test_struct_layout_matches_header():
+    from vsrd_b200 import _lib
+    # VsrdScene: 2 x int32, 4 pointers, 2 floats -> 48 bytes on LP64; VsrdRays: 2 x int32 + 3 pointers
+    assert ctypes.sizeof(_lib.VsrdScene) == 48
+    assert ctypes.sizeof(_lib.VsrdRays) == 32
+    assert ctypes.sizeof(_lib.VsrdRenderParams) == 16
+    assert ctypes.sizeof(_lib.VsrdLoss) == 16
+    text = open(HEADER).read()
+    assert f"#define VSRD_MLP_WEIGHTS {_lib.MLP_WEIGHTS}" in text
+    assert f"#define VSRD_GRAD_STRIDE {_lib.GRAD_STRIDE}" in text
+    assert f"#define VSRD_MAX_INSTANCES {_lib.MAX_INSTANCES}" in text
+    assert f"#define VSRD_MAX_INTERVALS {_lib.MAX_INTERVALS}" in text
+
+
+def test_argument_errors_are_reported_without_gpu(lib):
+    """Validation happens before any CUDA call, so the error convention is testable on CPU."""
+    from vsrd_b200 import _lib
+    scene = _lib.VsrdScene(0, 0, None, None, None, None, 1.0, 100.0)
+    rays = _lib.VsrdRays(1, 1, None, None, None)
+    status = lib.vsrd_field_forward(ctypes.byref(scene), ctypes.byref(rays), None, None)
+    assert status != 0
+    assert b"num_instances" in lib.vsrd_last_error()
+    with pytest.raises(RuntimeError, match="num_instances"):
+        _lib.check(status)
+
+
+def test_ops_refuse_cpu_tensors():
+    import torch
+    from vsrd_b200 import ops
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        ops.SceneArgs(torch.zeros(2, 3), torch.zeros(2, 3, 3), torch.zeros(2, 3), None, 1.0)

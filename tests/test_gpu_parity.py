@@ -1,0 +1,260 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the committed goldens.
+
+Tolerances (BASELINE.json north_star): rendered silhouettes within 1e-4 abs; parameter gradients
+within 1e-3 rel.  Gradients are compared (a) against the fp32 oracle outright and (b) against the
+fp64 oracle with the fp32 reference's own error alongside (SURVEY.md §7 hard part 4: the fp32
+reference is itself 3e-4..4e-2 from fp64 on these losses)."""
+import pytest
+import torch
+
+from oracle import vsrd_oracle as oracle
+from tests.helpers import load_golden, rel_l2, render_kwargs, scene_from_golden
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _cuda(g, *keys):
+    return [g[k].to(DEV, torch.float32) for k in keys]
+
+
+def _scene_tensors(g, requires_grad=False):
+    loc, rot, dim = _cuda(g, "locations", "rotations", "half_extents")
+    w = g["mlp_weights"].to(DEV, torch.float32) if "mlp_weights" in g else None
+    ts = [loc, rot, dim] + ([w] if w is not None else [])
+    for t in ts:
+        t.requires_grad_(requires_grad)
+    return loc, rot, dim, w
+
+
+def _ray_major(t):
+    """[M(+1), R, 1] sample-major golden -> [R, M(+1)]"""
+    return t.squeeze(-1).t().contiguous()
+
+
+@pytest.fixture(scope="module")
+def F():
+    from vsrd_b200 import functional
+    return functional
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from vsrd_b200 import ops
+    return ops
+
+
+# ------------------------------------------------------------------------------------------------
+# field kernel alone
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("residual", [False, True])
+def test_field_forward_matches_fp64_autograd(ops, residual):
+    g = load_golden("residual_f32")
+    gen = torch.Generator().manual_seed(0)
+    n_pts = 4099
+    loc64 = g["locations"].double()
+    pick = torch.randint(0, loc64.shape[0], (n_pts,), generator=gen)
+    x = (loc64[pick] + (torch.rand(n_pts, 3, generator=gen, dtype=torch.float64) * 2 - 1)
+         * torch.tensor([3.0, 2.0, 5.0], dtype=torch.float64)).float()
+    # express the points as rays: origin 0, direction x/|x|, one interval whose midpoint is |x|
+    norm = x.norm(dim=-1, keepdim=True)
+    dirs = x / norm
+    dist = torch.cat([norm - 0.25, norm + 0.25], dim=-1)
+    pos = dirs * ((dist[:, :1] + dist[:, 1:]) / 2.0)          # what the kernel reconstructs (fp32)
+    loc, rot, dim, w = _scene_tensors(g)
+    scene = ops.SceneArgs(loc, rot, dim, w if residual else None, 1.0)
+    rays = ops.RayArgs(torch.zeros(n_pts, 3, device=DEV), dirs.to(DEV), dist.to(DEV))
+    field = ops.field_forward(scene, rays).cpu()               # [N, n_pts, 4]
+    for i in range(loc.shape[0]):
+        xd = pos.double().requires_grad_(True)
+        d = oracle.instance_sdf(xd, g["locations"][i].double(), g["rotations"][i].double(),
+                                g["half_extents"][i].double(),
+                                g["mlp_weights"][i].double() if residual else None, 100.0)
+        grad, = torch.autograd.grad(d.sum(), xd)
+        assert (field[i, :, 0].double() - d.squeeze(-1)).abs().max() < 2e-5
+        assert (field[i, :, 1:].double() - grad).abs().max() < 2e-4
+
+
+# ------------------------------------------------------------------------------------------------
+# fine pass on the golden's sample distances
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["box_f32", "residual_f32", "late_f32"])
+def test_render_pass_matches_golden(F, case):
+    g = load_golden(case)
+    kw = render_kwargs(g)
+    loc, rot, dim, w = _scene_tensors(g)
+    o, d = _cuda(g, "ray_positions", "ray_directions")
+    dist = _ray_major(g["fine_distances"]).to(DEV)
+    with torch.no_grad():
+        labels, grads, weights = F.render_pass(loc, rot, dim, w, o, d, dist, temperature=float(g["temperature"]),
+                                               std_deviation=kw["sdf_std_deviation"], cosine_ratio=kw["cosine_ratio"])
+    assert (labels.cpu() - g["labels"]).abs().max() < 1e-4                      # north_star: 1e-4 abs
+    assert (weights.cpu() - _ray_major(g["fine_weights"])).abs().max() < 1e-4
+    near = (g["fine_distances"][1:] < 1e3).expand_as(g["sampled_gradients"])
+    diff = (grads.cpu().permute(1, 0, 2) - g["sampled_gradients"]).abs()
+    assert diff[near].max() < 2e-3
+
+
+@pytest.mark.parametrize("case", ["box_f32", "residual_f32", "late_f32"])
+def test_two_pass_placement_matches_golden(F, ops, case):
+    g = load_golden(case)
+    kw = render_kwargs(g)
+    loc, rot, dim, w = _scene_tensors(g)
+    o, d = _cuda(g, "ray_positions", "ray_directions")
+    with torch.no_grad():
+        labels, grads, cd, cw, fd, fw = F.two_pass_render(
+            loc, rot, dim, w, o, d, num_samples=kw["num_samples"], temperature=float(g["temperature"]),
+            std_deviation=kw["sdf_std_deviation"], cosine_ratio=kw["cosine_ratio"],
+            jitter=g["jitter"].squeeze(1).to(DEV), sorted_uniforms=g["sorted_uniforms"].squeeze(1).to(DEV))
+    # stratified placement is a lerp of identical inputs: bit-exact
+    assert torch.equal(cd.cpu(), _ray_major(g["coarse_distances"]))
+    assert (cw.cpu() - _ray_major(g["coarse_weights"])).abs().max() < 1e-4
+    # importance placement: identical up to rounding except where a 1-ulp CDF difference flips a
+    # searchsorted bin (SURVEY.md §7 hard part 3) -> statistical bound
+    ref = _ray_major(g["fine_distances"])
+    close = (fd.cpu() - ref).abs() <= 1e-4 * (1.0 + ref.abs())
+    assert close.float().mean() > 0.97, float(close.float().mean())
+    # ascending, and the coarse samples are a subset of the merged list
+    assert bool((fd[:, 1:] >= fd[:, :-1]).all())
+    if case != "late_f32":
+        assert (labels.cpu() - g["labels"]).abs().max() < 5e-3
+
+
+def test_place_fine_with_oracle_coarse_pass_is_exact_up_to_rounding(ops):
+    """Feed the oracle's coarse outputs: then every fine sample must agree (no bin flips expected
+    because the CDF is accumulated in double like torch.cumsum on CPU)."""
+    for case in ["box_f32", "residual_f32"]:
+        g = load_golden(case)
+        cd = _ray_major(g["coarse_distances"]).to(DEV)
+        cw = _ray_major(g["coarse_weights"]).to(DEV)
+        fd = ops.place_fine(cd, cw, g["sorted_uniforms"].squeeze(1).to(DEV)).cpu()
+        ref = _ray_major(g["fine_distances"])
+        close = (fd - ref).abs() <= 2e-5 * (1.0 + ref.abs())
+        assert close.float().mean() > 0.995, float(close.float().mean())
+
+
+# ------------------------------------------------------------------------------------------------
+# gradients
+# ------------------------------------------------------------------------------------------------
+def _oracle_grads(g, dist_rm, keep, dtype, loss_fn):
+    scene = scene_from_golden(g, dtype=dtype, requires_grad=True)
+    kw = render_kwargs(g)
+    dist_sm = dist_rm[keep].to(dtype).t()[..., None].contiguous()
+    out = oracle.render_pass(scene.field(), g["ray_positions"][keep].to(dtype), g["ray_directions"][keep].to(dtype),
+                             dist_sm, kw["sdf_std_deviation"], kw["cosine_ratio"])
+    loss = loss_fn(out[0], out[1], out[3], dtype)
+    names = ["locations", "rotations", "half_extents"] + (["mlp_weights"] if scene.mlp_weights is not None else [])
+    return loss.detach(), dict(zip(names, torch.autograd.grad(loss, [getattr(scene, n) for n in names])))
+
+
+def _cuda_grads(F, g, dist_rm, keep, loss_fn):
+    kw = render_kwargs(g)
+    loc, rot, dim, w = _scene_tensors(g, requires_grad=True)
+    o, d = g["ray_positions"][keep].to(DEV), g["ray_directions"][keep].to(DEV)
+    labels, grads, weights = F.render_pass(loc, rot, dim, w, o, d, dist_rm[keep].to(DEV),
+                                           temperature=float(g["temperature"]),
+                                           std_deviation=kw["sdf_std_deviation"], cosine_ratio=kw["cosine_ratio"])
+    # hand the oracle-shaped (sample-major) views to the loss so both sides share one definition
+    loss = loss_fn(labels, grads.permute(1, 0, 2), weights.t()[..., None], torch.float32)
+    leaves = [loc, rot, dim] + ([w] if w is not None else [])
+    names = ["locations", "rotations", "half_extents", "mlp_weights"][:len(leaves)]
+    return loss.detach().cpu(), {n: t.cpu() for n, t in zip(names, torch.autograd.grad(loss, leaves))}
+
+
+@pytest.mark.parametrize("case", ["box_f32", "residual_f32"])
+def test_linear_upstream_gradients_match_fp64_oracle(F, case):
+    """Random linear functional of (labels, gradients, weights): isolates the kernels' adjoint from the
+    ill-conditioned BCE-at-the-clamp.  north_star: parameter gradients within 1e-3 rel."""
+    g = load_golden(case)
+    dist = _ray_major(g["fine_distances"])
+    keep = dist.max(dim=1).values < 1e3
+    R, M, N = int(keep.sum()), dist.shape[1] - 1, g["locations"].shape[0]
+    gen = torch.Generator().manual_seed(11)
+    cl = torch.randn(R, N, generator=gen, dtype=torch.float64)
+    cg = torch.randn(M, R, 3, generator=gen, dtype=torch.float64) * 0.1
+    cw = torch.randn(M, R, 1, generator=gen, dtype=torch.float64)
+
+    def loss_fn(labels, grads, weights, dtype):
+        dev = labels.device
+        return ((labels * cl.to(dev, dtype)).sum() + (grads * cg.to(dev, dtype)).sum()
+                + (weights * cw.to(dev, dtype)).sum())
+
+    l64, want = _oracle_grads(g, dist, keep, torch.float64, loss_fn)
+    l32, got = _cuda_grads(F, g, dist, keep, loss_fn)
+    assert abs(float(l32) - float(l64)) < 1e-3 * max(1.0, abs(float(l64)))
+    for n in want:
+        err = rel_l2(got[n].double(), want[n])
+        assert err < 1e-3, f"{n}: rel-L2 {err}"
+
+
+@pytest.mark.parametrize("case", ["box_f32", "residual_f32"])
+def test_training_loss_gradients(F, case):
+    """BCE + 0.01 eikonal (the loss main.py optimises)."""
+    g = load_golden(case)
+    residual = "mlp_weights" in g
+    dist = _ray_major(g["fine_distances"])
+    keep = dist.max(dim=1).values < 1e3
+    targets = g["targets"][keep]
+
+    def loss_fn(labels, grads, weights, dtype):
+        loss = oracle.silhouette_loss(labels, targets.to(labels.device, dtype))
+        if residual:
+            loss = loss + 0.01 * oracle.eikonal_loss(grads)
+        return loss
+
+    l64, want64 = _oracle_grads(g, dist, keep, torch.float64, loss_fn)
+    l32, want32 = _oracle_grads(g, dist, keep, torch.float32, loss_fn)
+    lc, got = _cuda_grads(F, g, dist, keep, loss_fn)
+    assert abs(float(lc) - float(l32)) < 1e-5
+    for n in want64:
+        e_ref = rel_l2(want32[n].double(), want64[n])
+        e_32 = rel_l2(got[n].double(), want32[n].double())
+        e_64 = rel_l2(got[n].double(), want64[n])
+        assert e_32 < 1e-3, f"{n}: vs fp32 oracle {e_32}"
+        assert e_64 < max(1e-3, 1.5 * e_ref), f"{n}: vs fp64 oracle {e_64} (reference's own error {e_ref})"
+
+
+@pytest.mark.parametrize("case", ["box_f32", "residual_f32"])
+def test_fused_loss_equals_unfused(F, case):
+    g = load_golden(case)
+    kw = render_kwargs(g)
+    residual = "mlp_weights" in g
+    dist = _ray_major(g["fine_distances"]).to(DEV)
+    o, d, targets = _cuda(g, "ray_positions", "ray_directions", "targets")
+    common = dict(temperature=float(g["temperature"]), std_deviation=kw["sdf_std_deviation"],
+                  cosine_ratio=kw["cosine_ratio"])
+    eik_w = 0.01 if residual else 0.0
+
+    leaves_a = _scene_tensors(g, requires_grad=True)
+    labels, grads, _ = F.render_pass(*leaves_a, o, d, dist, **common)
+    loss_a = oracle.silhouette_loss(labels, targets) + eik_w * oracle.eikonal_loss(grads)
+    ga = torch.autograd.grad(loss_a, [t for t in leaves_a if t is not None])
+
+    leaves_b = _scene_tensors(g, requires_grad=True)
+    loss_b, labels_b, parts = F.fused_render_loss(*leaves_b, o, d, dist, targets, eikonal_weight=eik_w, **common)
+    gb = torch.autograd.grad(loss_b * 2.0, [t for t in leaves_b if t is not None])   # also checks grad_output scaling
+
+    assert torch.equal(labels_b, labels.detach())
+    assert abs(float(loss_a) - float(loss_b)) < 2e-6 * max(1.0, abs(float(loss_a)))
+    for a, b in zip(ga, gb):
+        assert rel_l2(b.cpu() / 2.0, a.cpu()) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------
+# rays
+# ------------------------------------------------------------------------------------------------
+def test_ray_directions_match_golden(ops):
+    import numpy as np
+    from tests.helpers import GOLDEN_DIR
+    u = np.load(f"{GOLDEN_DIR}/units.npz")
+    k = torch.from_numpy(u["rc_intrinsic"])
+    e = torch.from_numpy(u["rc_extrinsic"])
+    inv_proj = (torch.linalg.inv(e)[:3, :3] @ torch.linalg.inv(k)).to(DEV)
+    dirs = ops.ray_directions(inv_proj[None], 12, 20).cpu()
+    assert (dirs - torch.from_numpy(u["rc_ray_directions"])).abs().max() < 1e-6
+    cam = torch.linalg.inv(e)[:3, 3].to(DEV)
+    idx = torch.tensor([0, 19, 20, 239, 101], device=DEV)
+    o, d = ops.gather_rays(inv_proj[None], cam[None], idx, 12, 20)
+    assert torch.equal(d.cpu(), dirs.reshape(-1, 3)[idx.cpu()])
+    assert torch.equal(o.cpu(), cam.cpu().expand(5, 3))

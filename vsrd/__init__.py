@@ -1,0 +1,7 @@
+"""Drop-in `vsrd` package: the reference's Python API surface for the per-frame optimisation loop
+(scripts/main.py), backed by the vsrd_b200 sm_100a kernels.  Only what the hot path touches is
+provided; dataset readers, transforms and visualisation are out of scope."""
+from . import models  # noqa: F401
+from . import operations  # noqa: F401
+from . import rendering  # noqa: F401
+from . import utils  # noqa: F401

@@ -1,0 +1,167 @@
+"""`vsrd.rendering.hierarchical_volumetric_rendering` on the fused B200 kernels.
+
+Same signature, argument meaning and return tuple as the reference
+(vsrd/rendering/renderers.py:177-270).  The reference receives the scene as an opaque Python closure
+that scripts/main.py composes every step (main.py:433-618):
+
+    soft_union([translation(rotation(instance_field(box [+ residual]), R_i), t_i) ...], temperature)
+
+`translation` / `rotation` / `box` are ours (tagged objects, vsrd/rendering/sdfs.py); the wrappers
+in between are main.py's own nested functions.  `match_union_field` walks their `__closure__` cells
+(free-variable names as in the script) to recover (t_i, R_i, dim_i, W_i, temperature, scale) and the
+whole field then runs inside the kernels.  A field that does not have this structure is an error:
+there is deliberately no eager fallback.
+"""
+from __future__ import annotations
+
+import dataclasses
+import functools
+import operator
+from typing import List, Optional
+
+import torch
+
+from vsrd_b200 import functional as F
+from vsrd_b200 import ops
+
+from . import sdfs
+from .samplers import _seed
+
+
+class UnsupportedFieldError(RuntimeError):
+    pass
+
+
+@dataclasses.dataclass
+class UnionField:
+    locations: torch.Tensor            # [N,3]
+    rotations: torch.Tensor            # [N,3,3]
+    half_extents: torch.Tensor         # [N,3]
+    mlp_weights: Optional[torch.Tensor]  # [N,1617] | None
+    temperature: float
+    scale: float
+    returns_features: bool = True      # False when wrapped in compose(field, itemgetter(0))
+
+
+def _closure(fn) -> dict:
+    code = getattr(fn, "__code__", None)
+    cells = getattr(fn, "__closure__", None)
+    if code is None or cells is None:
+        raise UnsupportedFieldError(f"vsrd_b200: cannot introspect {fn!r}: not a Python closure")
+    return {name: cell.cell_contents for name, cell in zip(code.co_freevars, cells)}
+
+
+def _expect(cond, what):
+    if not cond:
+        raise UnsupportedFieldError(
+            "vsrd_b200: distance_field is not the soft union of translated/rotated box(+residual) instances "
+            f"that scripts/main.py builds ({what}); there is no eager fallback")
+
+
+def _match_instance(field, index):
+    _expect(isinstance(field, sdfs.TranslatedSDF), "expected sdfs.translation(...) at the top of each instance")
+    location = field.translation_vector
+    _expect(isinstance(field.sdf, sdfs.RotatedSDF), "expected sdfs.rotation(...) under translation")
+    rotation = field.sdf.rotation_matrix
+    inst = _closure(field.sdf.sdf)                                   # main.py:460-475 instance_field.wrapper
+    _expect({"distance_field", "instance_label"} <= set(inst), "expected instance_field(...) under rotation")
+    label = inst["instance_label"]
+    if not (isinstance(label, torch.Tensor) and label.is_cuda):      # reading a CUDA scalar would sync
+        _expect(int(label) == index, "instance labels must be 0..N-1 in order")
+    inner = inst["distance_field"]
+    scale = None
+    if isinstance(inner, sdfs.BoxSDF):                               # warm-up branch, main.py:582-618
+        return location, rotation, inner.dimension, None, scale, inst.get("num_instances")
+    comp = _closure(inner)                                           # main.py:451-458 residual_composition.wrapper
+    _expect({"distance_field", "residual_distance_field"} <= set(comp), "expected residual_composition(...)")
+    _expect(isinstance(comp["distance_field"], sdfs.BoxSDF), "expected sdfs.box(...) inside residual_composition")
+    res = _closure(comp["residual_distance_field"])                  # main.py:433-449 residual_distance_field.wrapper
+    _expect({"distance_field", "config", "models"} <= set(res), "expected residual_distance_field(...)")
+    partial = res["distance_field"]
+    _expect(isinstance(partial, functools.partial) and len(partial.args) == 1 and not partial.keywords,
+            "expected functools.partial(hyper_distance_field.distance_field, weights)")
+    owner = getattr(partial.func, "__self__", None)
+    _expect(owner is not None and getattr(partial.func, "__name__", "") == "distance_field",
+            "residual field must be HyperDistanceField.distance_field")
+    owner.check_fused_layout(res["models"].positional_encoder)
+    scale = float(max(res["config"].volume_rendering.distance_range))  # main.py:441
+    return location, rotation, comp["distance_field"].dimension, partial.args[0], scale, inst.get("num_instances")
+
+
+def match_union_field(distance_field) -> UnionField:
+    """Recover the scene parameters from the closure scripts/main.py hands to the renderer."""
+    if isinstance(distance_field, UnionField):
+        return distance_field
+    returns_features = True
+    composed = getattr(distance_field, "__vsrd_compose__", None)      # vsrd.utils.compose(field, itemgetter(0))
+    if composed is not None:
+        _expect(len(composed) == 2 and isinstance(composed[1], operator.itemgetter), "unsupported compose chain")
+        distance_field, returns_features = composed[0], False
+    top = _closure(distance_field)                                   # main.py:477-492 soft_union.wrapper
+    _expect({"distance_fields", "temperature"} <= set(top), "expected soft_union(distance_fields, temperature)")
+    fields: List = list(top["distance_fields"])
+    _expect(len(fields) >= 1, "empty union")
+    parts = [_match_instance(f, i) for i, f in enumerate(fields)]
+    locs, rots, dims, ws, scales, counts = zip(*parts)
+    _expect(all(c is None or int(c) == len(fields) for c in counts), "num_instances does not match the union size")
+    has_w = [w is not None for w in ws]
+    _expect(all(has_w) or not any(has_w), "mixed box-only / residual instances")
+    scale = next((s for s in scales if s is not None), 100.0)
+    return UnionField(
+        locations=torch.stack(list(locs), dim=0),
+        rotations=torch.stack(list(rots), dim=0),
+        half_extents=torch.stack(list(dims), dim=0),
+        mlp_weights=torch.stack(list(ws), dim=0) if all(has_w) else None,
+        temperature=float(top["temperature"]),
+        scale=scale,
+        returns_features=returns_features,
+    )
+
+
+def hierarchical_volumetric_rendering(
+    distance_field,
+    ray_positions,
+    ray_directions,
+    distance_range,
+    num_samples,
+    sdf_std_deviation,
+    cosine_ratio=1.0,
+    epsilon=1e-6,
+    sampled_distances=None,
+    sampled_weights=None,
+):
+    """Returns `(labels [..., N], sampled_gradients [M, ..., 3], sampled_distances [M+1, ..., 1],
+    sampled_weights [M, ..., 1])` with M = S-1 on the first pass and 2S-1 when the previous pass's
+    `sampled_distances` / `sampled_weights` are fed back (importance resampling)."""
+    field = match_union_field(distance_field)
+    lead = ray_directions.shape[:-1]
+    dirs = ray_directions.reshape(-1, 3)
+    num_rays = dirs.shape[0]
+    device = dirs.device
+    origins = ray_positions if ray_positions.numel() == 3 else ray_positions.expand(*lead, 3).reshape(-1, 3)
+
+    if sampled_distances is None:
+        bins = F.distance_bins(distance_range, num_samples, device)
+        distances = ops.place_coarse(bins, num_rays, None, _seed())
+    else:
+        coarse = sampled_distances.detach().reshape(sampled_distances.shape[0], -1).t().float()
+        weights = sampled_weights.detach().reshape(sampled_weights.shape[0], -1).t().float()
+        if coarse.shape[1] != num_samples:
+            raise RuntimeError(
+                f"vsrd_b200: importance resampling draws len(sampled_distances) samples per ray "
+                f"(got num_samples={num_samples}, sampled_distances={coarse.shape[1]})")
+        distances = ops.place_fine(coarse, weights, None, _seed())
+
+    labels, grads, weights = F.render_pass(
+        field.locations.float(), field.rotations.float(), field.half_extents.float(),
+        None if field.mlp_weights is None else field.mlp_weights.float(),
+        origins.float(), dirs.float(), distances,
+        temperature=field.temperature, std_deviation=float(sdf_std_deviation),
+        cosine_ratio=float(cosine_ratio), epsilon=float(epsilon), scale=field.scale)
+
+    m = distances.shape[1] - 1
+    out_grads = grads.permute(1, 0, 2).reshape(m, *lead, 3)
+    out_dist = distances.t().reshape(m + 1, *lead, 1)
+    out_weights = weights.t().reshape(m, *lead, 1)
+    features = (labels.reshape(*lead, -1),) if field.returns_features else ()
+    return (*features, out_grads, out_dist, out_weights)

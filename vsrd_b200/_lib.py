@@ -1,0 +1,106 @@
+"""ctypes binding of libvsrd_b200.so (include/vsrd_b200.h).
+
+There is no CPU fallback: if the shared library is missing or a call fails, a RuntimeError is
+raised.  The library is built in-tree by `python -m vsrd_b200.build` (or `__graft_entry__.build()`).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libvsrd_b200.so")
+
+MLP_WEIGHTS = 1617
+GRAD_STRIDE = 1632
+MAX_INSTANCES = 32
+MAX_INTERVALS = 512
+
+c_float_p = ctypes.c_void_p  # device pointers travel as opaque addresses
+
+
+class VsrdScene(ctypes.Structure):
+    _fields_ = [
+        ("num_instances", ctypes.c_int32),
+        ("_pad", ctypes.c_int32),
+        ("locations", ctypes.c_void_p),
+        ("rotations", ctypes.c_void_p),
+        ("half_extents", ctypes.c_void_p),
+        ("mlp_weights", ctypes.c_void_p),
+        ("temperature", ctypes.c_float),
+        ("scale", ctypes.c_float),
+    ]
+
+
+class VsrdRays(ctypes.Structure):
+    _fields_ = [
+        ("num_rays", ctypes.c_int32),
+        ("num_intervals", ctypes.c_int32),
+        ("origins", ctypes.c_void_p),
+        ("directions", ctypes.c_void_p),
+        ("distances", ctypes.c_void_p),
+    ]
+
+
+class VsrdRenderParams(ctypes.Structure):
+    _fields_ = [
+        ("std_deviation", ctypes.c_float),
+        ("cosine_ratio", ctypes.c_float),
+        ("epsilon", ctypes.c_float),
+        ("_pad", ctypes.c_float),
+    ]
+
+
+class VsrdLoss(ctypes.Structure):
+    _fields_ = [
+        ("targets", ctypes.c_void_p),
+        ("silhouette_weight", ctypes.c_float),
+        ("eikonal_weight", ctypes.c_float),
+    ]
+
+
+# name -> (restype, argtypes); must list every symbol include/vsrd_b200.h declares
+_P = ctypes.POINTER
+_V = ctypes.c_void_p
+_I = ctypes.c_int
+SIGNATURES = {
+    "vsrd_version": (_I, []),
+    "vsrd_last_error": (ctypes.c_char_p, []),
+    "vsrd_backward_blocks_per_instance": (_I, [_I, _I, _I]),
+    "vsrd_ray_directions": (_I, [_V, _I, _I, _I, _V, _V]),
+    "vsrd_gather_rays": (_I, [_V, _V, _V, _I, _I, _I, _I, _V, _V, _V]),
+    "vsrd_place_coarse": (_I, [_V, _V, ctypes.c_uint64, _I, _I, _V, _V]),
+    "vsrd_place_fine": (_I, [_V, _V, _V, ctypes.c_uint64, _I, _I, _V, _V]),
+    "vsrd_field_forward": (_I, [_P(VsrdScene), _P(VsrdRays), _V, _V]),
+    "vsrd_composite_forward": (_I, [_P(VsrdScene), _P(VsrdRays), _P(VsrdRenderParams), _V, _V, _V, _V,
+                                    _P(VsrdLoss), _V, _V]),
+    "vsrd_composite_backward": (_I, [_P(VsrdScene), _P(VsrdRays), _P(VsrdRenderParams), _V, _V, _V, _V,
+                                     _P(VsrdLoss), _V, _V, _V]),
+    "vsrd_field_backward": (_I, [_P(VsrdScene), _P(VsrdRays), _V, _V, _V, _V, _V, _V, _V]),
+}
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Load the shared library (once) and bind every declared symbol."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"vsrd_b200: {LIB_PATH} not found. Build it with `python -m vsrd_b200.build` "
+            "(needs nvcc, targets sm_100a). There is no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in SIGNATURES.items():
+        fn = getattr(lib, name)   # AttributeError here means header and library disagree
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def check(status: int) -> None:
+    if status != 0:
+        msg = load().vsrd_last_error()
+        raise RuntimeError(msg.decode() if msg else f"vsrd_b200: call failed with status {status}")

@@ -1,0 +1,206 @@
+"""Tensor-level wrappers around the C ABI (include/vsrd_b200.h).  No autograd here.
+
+Tensors are borrowed: every input must be a CUDA float32 tensor (contiguous copies are made when
+needed) and outputs are allocated with torch so they live in its caching allocator.  Kernels are
+enqueued on torch's current stream, so the calls compose with CUDA graphs and stream contexts.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import VsrdLoss, VsrdRays, VsrdRenderParams, VsrdScene
+
+MLP_WEIGHTS = _lib.MLP_WEIGHTS
+GRAD_STRIDE = _lib.GRAD_STRIDE
+
+
+def _stream() -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"vsrd_b200: {name} must be a CUDA tensor (there is no CPU path)")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"vsrd_b200: {name} must be float32, got {t.dtype}")
+    return t.contiguous()
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class SceneArgs:
+    """Keeps the tensors alive and exposes the C struct."""
+
+    def __init__(self, locations, rotations, half_extents, mlp_weights, temperature, scale=100.0):
+        self.locations = _f32(locations, "locations").reshape(-1, 3)
+        n = self.locations.shape[0]
+        self.rotations = _f32(rotations, "rotations").reshape(n, 3, 3)
+        self.half_extents = _f32(half_extents, "half_extents").reshape(n, 3)
+        self.mlp_weights = None
+        if mlp_weights is not None:
+            self.mlp_weights = _f32(mlp_weights, "mlp_weights")
+            if tuple(self.mlp_weights.shape) != (n, MLP_WEIGHTS):
+                raise RuntimeError(
+                    f"vsrd_b200: mlp_weights must be [{n}, {MLP_WEIGHTS}] (48-16-16-16-16-1 residual field), "
+                    f"got {tuple(self.mlp_weights.shape)}")
+        if not 1 <= n <= _lib.MAX_INSTANCES:
+            raise RuntimeError(f"vsrd_b200: number of instances must be in [1, {_lib.MAX_INSTANCES}], got {n}")
+        self.num_instances = n
+        self.temperature = float(temperature)
+        self.scale = float(scale)
+        self.struct = VsrdScene(n, 0, _ptr(self.locations), _ptr(self.rotations), _ptr(self.half_extents),
+                                _ptr(self.mlp_weights), self.temperature, self.scale)
+
+
+class RayArgs:
+    def __init__(self, origins, directions, distances):
+        self.directions = _f32(directions, "ray_directions").reshape(-1, 3)
+        r = self.directions.shape[0]
+        origins = _f32(origins, "ray_positions")
+        self.origins = origins.expand(r, 3).contiguous() if origins.numel() == 3 else origins.reshape(r, 3)
+        self.distances = _f32(distances, "distances")
+        if self.distances.dim() != 2 or self.distances.shape[0] != r or self.distances.shape[1] < 2:
+            raise RuntimeError(f"vsrd_b200: distances must be [R, M+1] with R={r}, got {tuple(self.distances.shape)}")
+        self.num_rays = r
+        self.num_intervals = self.distances.shape[1] - 1
+        if self.num_intervals > _lib.MAX_INTERVALS:
+            raise RuntimeError(f"vsrd_b200: at most {_lib.MAX_INTERVALS} intervals per ray, got {self.num_intervals}")
+        self.struct = VsrdRays(r, self.num_intervals, _ptr(self.origins), _ptr(self.directions), _ptr(self.distances))
+
+
+def _params(std_deviation, cosine_ratio, epsilon) -> VsrdRenderParams:
+    return VsrdRenderParams(float(std_deviation), float(cosine_ratio), float(epsilon), 0.0)
+
+
+def _loss(targets: Optional[torch.Tensor], silhouette_weight: float, eikonal_weight: float, r: int, n: int):
+    if targets is None:
+        return None, None
+    targets = _f32(targets, "targets")
+    if tuple(targets.shape) != (r, n):
+        raise RuntimeError(f"vsrd_b200: targets must be [{r}, {n}], got {tuple(targets.shape)}")
+    return targets, VsrdLoss(_ptr(targets), float(silhouette_weight), float(eikonal_weight))
+
+
+# ---- a1 ---------------------------------------------------------------------------------------
+
+def ray_directions(inv_projection: torch.Tensor, height: int, width: int) -> torch.Tensor:
+    """inv_projection [V,3,3] = inv(E)[:3,:3] @ inv(K)  ->  unit directions [V,H,W,3]."""
+    p = _f32(inv_projection, "inv_projection").reshape(-1, 3, 3)
+    out = torch.empty(p.shape[0], height, width, 3, device=p.device, dtype=torch.float32)
+    _lib.check(_lib.load().vsrd_ray_directions(_ptr(p), p.shape[0], height, width, _ptr(out), _stream()))
+    return out
+
+
+def gather_rays(inv_projection, camera_positions, pixel_indices, height, width) -> Tuple[torch.Tensor, torch.Tensor]:
+    p = _f32(inv_projection, "inv_projection").reshape(-1, 3, 3)
+    c = _f32(camera_positions, "camera_positions").reshape(-1, 3)
+    if pixel_indices.dtype != torch.int64 or not pixel_indices.is_cuda:
+        raise RuntimeError("vsrd_b200: pixel_indices must be a CUDA int64 tensor")
+    idx = pixel_indices.contiguous().reshape(-1)
+    origins = torch.empty(idx.numel(), 3, device=p.device, dtype=torch.float32)
+    dirs = torch.empty_like(origins)
+    _lib.check(_lib.load().vsrd_gather_rays(_ptr(p), _ptr(c), _ptr(idx), idx.numel(), p.shape[0], height, width,
+                                            _ptr(origins), _ptr(dirs), _stream()))
+    return origins, dirs
+
+
+# ---- a9 / a10 ---------------------------------------------------------------------------------
+
+def place_coarse(bins: torch.Tensor, num_rays: int, jitter: Optional[torch.Tensor] = None, seed: int = 0) -> torch.Tensor:
+    bins = _f32(bins, "bins").reshape(-1)
+    s = bins.numel() - 1
+    if jitter is not None:
+        jitter = _f32(jitter, "jitter").reshape(num_rays, s)
+    out = torch.empty(num_rays, s, device=bins.device, dtype=torch.float32)
+    _lib.check(_lib.load().vsrd_place_coarse(_ptr(bins), _ptr(jitter), seed & (2 ** 64 - 1), num_rays, s, _ptr(out), _stream()))
+    return out
+
+
+def place_fine(coarse_distances, coarse_weights, sorted_uniforms: Optional[torch.Tensor] = None, seed: int = 0) -> torch.Tensor:
+    t = _f32(coarse_distances, "coarse_distances")
+    w = _f32(coarse_weights, "coarse_weights")
+    r, s = t.shape
+    if tuple(w.shape) != (r, s - 1):
+        raise RuntimeError(f"vsrd_b200: coarse_weights must be [{r}, {s - 1}], got {tuple(w.shape)}")
+    if sorted_uniforms is not None:
+        sorted_uniforms = _f32(sorted_uniforms, "sorted_uniforms").reshape(r, s)
+    out = torch.empty(r, 2 * s, device=t.device, dtype=torch.float32)
+    _lib.check(_lib.load().vsrd_place_fine(_ptr(t), _ptr(w), _ptr(sorted_uniforms), seed & (2 ** 64 - 1), r, s, _ptr(out), _stream()))
+    return out
+
+
+# ---- field + compositing ----------------------------------------------------------------------
+
+def field_forward(scene: SceneArgs, rays: RayArgs) -> torch.Tensor:
+    field = torch.empty(scene.num_instances, rays.num_rays * rays.num_intervals, 4,
+                        device=rays.directions.device, dtype=torch.float32)
+    _lib.check(_lib.load().vsrd_field_forward(ctypes.byref(scene.struct), ctypes.byref(rays.struct), _ptr(field), _stream()))
+    return field
+
+
+def composite_forward(scene: SceneArgs, rays: RayArgs, field, std_deviation, cosine_ratio, epsilon=1e-6,
+                      targets=None, silhouette_weight=1.0, eikonal_weight=0.0):
+    dev = rays.directions.device
+    r, m, n = rays.num_rays, rays.num_intervals, scene.num_instances
+    labels = torch.empty(r, n, device=dev, dtype=torch.float32)
+    grads = torch.empty(r, m, 3, device=dev, dtype=torch.float32)
+    weights = torch.empty(r, m, device=dev, dtype=torch.float32)
+    targets, loss = _loss(targets, silhouette_weight, eikonal_weight, r, n)
+    loss_out = torch.zeros(2, device=dev, dtype=torch.float32) if loss is not None else None
+    params = _params(std_deviation, cosine_ratio, epsilon)
+    _lib.check(_lib.load().vsrd_composite_forward(
+        ctypes.byref(scene.struct), ctypes.byref(rays.struct), ctypes.byref(params), _ptr(field),
+        _ptr(labels), _ptr(grads), _ptr(weights), ctypes.byref(loss) if loss is not None else None,
+        _ptr(loss_out), _stream()))
+    return labels, grads, weights, loss_out
+
+
+def composite_backward(scene: SceneArgs, rays: RayArgs, field, std_deviation, cosine_ratio, epsilon=1e-6,
+                       grad_labels=None, grad_gradients=None, grad_weights=None,
+                       targets=None, labels=None, silhouette_weight=1.0, eikonal_weight=0.0) -> torch.Tensor:
+    r, m, n = rays.num_rays, rays.num_intervals, scene.num_instances
+    if grad_labels is not None:
+        grad_labels = _f32(grad_labels, "grad_labels").reshape(r, n)
+    if grad_gradients is not None:
+        grad_gradients = _f32(grad_gradients, "grad_gradients").reshape(r, m, 3)
+    if grad_weights is not None:
+        grad_weights = _f32(grad_weights, "grad_weights").reshape(r, m)
+    targets, loss = _loss(targets, silhouette_weight, eikonal_weight, r, n)
+    if loss is not None:
+        labels = _f32(labels, "labels").reshape(r, n)
+    adjoint = torch.empty_like(field)
+    params = _params(std_deviation, cosine_ratio, epsilon)
+    _lib.check(_lib.load().vsrd_composite_backward(
+        ctypes.byref(scene.struct), ctypes.byref(rays.struct), ctypes.byref(params), _ptr(field),
+        _ptr(grad_labels), _ptr(grad_gradients), _ptr(grad_weights),
+        ctypes.byref(loss) if loss is not None else None, _ptr(labels) if loss is not None else None,
+        _ptr(adjoint), _stream()))
+    return adjoint
+
+
+_partials_cache = {}
+
+
+def field_backward(scene: SceneArgs, rays: RayArgs, adjoint: torch.Tensor):
+    dev = rays.directions.device
+    n = scene.num_instances
+    blocks = _lib.load().vsrd_backward_blocks_per_instance(n, rays.num_rays, rays.num_intervals)
+    if blocks < 1:
+        _lib.check(1)
+    partials = torch.empty(n * blocks * GRAD_STRIDE, device=dev, dtype=torch.float32)
+    g_loc = torch.empty(n, 3, device=dev, dtype=torch.float32)
+    g_rot = torch.empty(n, 3, 3, device=dev, dtype=torch.float32)
+    g_dim = torch.empty(n, 3, device=dev, dtype=torch.float32)
+    g_w = torch.empty(n, MLP_WEIGHTS, device=dev, dtype=torch.float32) if scene.mlp_weights is not None else None
+    _lib.check(_lib.load().vsrd_field_backward(
+        ctypes.byref(scene.struct), ctypes.byref(rays.struct), _ptr(adjoint), _ptr(partials),
+        _ptr(g_loc), _ptr(g_rot), _ptr(g_dim), _ptr(g_w), _stream()))
+    return g_loc, g_rot, g_dim, g_w
