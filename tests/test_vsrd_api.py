@@ -1,0 +1,188 @@
+"""CPU-side checks of the drop-in `vsrd` API: closure pattern-matcher, models, operations, utils."""
+import functools
+import operator
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+import vsrd
+from tests.helpers import GOLDEN_DIR
+from vsrd.rendering import UnsupportedFieldError, match_union_field, sdfs
+
+
+def _attr(**kw):
+    return vsrd.utils.Dict.apply(kw)
+
+
+def compose_like_main(locations, dimensions, orientations, weights, temperature, models, config, num_instances):
+    """Closures with the same nesting and free-variable names as scripts/main.py:433-578 (written
+    for this test; the GPU-box tests cannot read the reference script)."""
+
+    def residual_distance_field(distance_field):
+        def wrapper(positions):
+            positions = positions / max(config.volume_rendering.distance_range)
+            return torch.sigmoid(distance_field(models.positional_encoder(positions)) - 1.0)
+        return wrapper
+
+    def residual_composition(distance_field, residual_distance_field):
+        def wrapper(positions):
+            return distance_field(positions) + residual_distance_field(positions)
+        return wrapper
+
+    def instance_field(distance_field, instance_label):
+        def wrapper(positions):
+            distances = distance_field(positions)
+            labels = nn.functional.one_hot(instance_label, num_instances)
+            return distances, labels.expand(*distances.shape[:-1], -1)
+        return wrapper
+
+    def soft_union(distance_fields, temperature):
+        def wrapper(positions):
+            distances, labels = map(torch.stack, zip(*[f(positions) for f in distance_fields]))
+            w = nn.functional.softmin(distances / temperature, dim=0)
+            return torch.sum(distances * w, dim=0), torch.sum(labels * w, dim=0)
+        return wrapper
+
+    fields = []
+    for i in range(num_instances):
+        inner = sdfs.box(dimensions[i])
+        if weights is not None:
+            inner = residual_composition(
+                distance_field=inner,
+                residual_distance_field=residual_distance_field(
+                    distance_field=functools.partial(models.hyper_distance_field.distance_field, weights[i])))
+        inst = instance_field(distance_field=inner, instance_label=torch.tensor(i))
+        fields.append(sdfs.translation(sdfs.rotation(inst, orientations[i]), locations[i]))
+    return soft_union(distance_fields=fields, temperature=temperature)
+
+
+@pytest.fixture(scope="module")
+def scene():
+    torch.manual_seed(0)
+    n = 3
+    detector = vsrd.models.BoxParameters3D(batch_size=1, num_instances=n)
+    hdf = vsrd.models.HyperDistanceField(48, [16, 16, 16, 16], 256, [256, 256, 256, 256])
+    enc = vsrd.models.SinusoidalEncoder(8)
+    models = _attr(detector=detector, hyper_distance_field=hdf, positional_encoder=enc)
+    config = _attr(volume_rendering=dict(distance_range=[0.0, 100.0]))
+    world = detector()
+    return n, models, config, world, hdf(world["embeddings"])
+
+
+@pytest.mark.parametrize("residual", [False, True])
+def test_matcher_recovers_scene(scene, residual):
+    n, models, config, world, weights = scene
+    field = compose_like_main(world["locations"][0], world["dimensions"][0], world["orientations"][0],
+                              weights[0] if residual else None, 0.37, models, config, n)
+    u = match_union_field(field)
+    assert u.temperature == pytest.approx(0.37) and u.scale == 100.0 and u.returns_features
+    assert torch.equal(u.locations, world["locations"][0])
+    assert torch.equal(u.rotations, world["orientations"][0])
+    assert torch.equal(u.half_extents, world["dimensions"][0])
+    if residual:
+        assert torch.equal(u.mlp_weights, weights[0])
+        # autograd connectivity: gradients reach the detector and the hypernetwork through the stack
+        (u.locations.sum() + u.mlp_weights.sum()).backward()
+        assert models.detector.locations.grad is not None
+        assert all(p.grad is not None for p in models.hyper_distance_field.parameters())
+    else:
+        assert u.mlp_weights is None
+    # logging path: compose(field, itemgetter(0))  (main.py:1030)
+    u2 = match_union_field(vsrd.utils.compose(field, operator.itemgetter(0)))
+    assert not u2.returns_features and torch.equal(u2.locations, u.locations)
+
+
+def test_composed_field_still_evaluates_in_plain_pytorch(scene):
+    """The tagged leaves keep the reference's call protocol (positions -> distances)."""
+    n, models, config, world, weights = scene
+    field = compose_like_main(world["locations"][0], world["dimensions"][0], world["orientations"][0],
+                              weights[0], 0.5, models, config, n)
+    sdf, labels = field(torch.randn(5, 7, 3) * 10)
+    assert sdf.shape == (5, 7, 1) and labels.shape == (5, 7, n)
+    torch.testing.assert_close(labels.sum(-1), torch.ones(5, 7))
+
+
+def test_unrecognised_fields_raise(scene):
+    n, models, config, world, weights = scene
+    with pytest.raises(UnsupportedFieldError):
+        match_union_field(lambda x: (x.norm(dim=-1, keepdim=True), x))
+    with pytest.raises(UnsupportedFieldError):
+        match_union_field(sdfs.box(torch.ones(3)))
+    # a union whose members are not translation(rotation(...))
+    def soft_union(distance_fields, temperature):
+        def wrapper(positions):
+            return distance_fields[0](positions) / temperature
+        return wrapper
+    with pytest.raises(UnsupportedFieldError, match="translation"):
+        match_union_field(soft_union([sdfs.box(torch.ones(3))], 1.0))
+    # unsupported MLP geometry
+    small = vsrd.models.HyperDistanceField(48, [8, 8], 16, [16])
+    with pytest.raises(RuntimeError, match="48-16-16-16-16-1"):
+        small.check_fused_layout()
+
+
+def test_models_match_reference_fixtures():
+    u = np.load(os.path.join(GOLDEN_DIR, "units.npz"))
+    t = lambda k: torch.from_numpy(u[k])
+    det = vsrd.models.BoxParameters3D(batch_size=1, num_instances=5)
+    assert sorted(det.state_dict()) == ["dimension_range", "dimensions", "embeddings", "location_range",
+                                        "locations", "orientations"]
+    with torch.no_grad():
+        det.locations.copy_(t("bp_raw_locations"))
+        det.dimensions.copy_(t("bp_raw_dimensions"))
+        det.orientations.copy_(t("bp_raw_orientations"))
+    world = det()
+    torch.testing.assert_close(world["locations"], t("bp_locations"), rtol=0, atol=0)
+    torch.testing.assert_close(world["dimensions"], t("bp_dimensions"), rtol=0, atol=0)
+    torch.testing.assert_close(world["orientations"], t("bp_orientations"), rtol=0, atol=0)
+    torch.testing.assert_close(world["boxes_3d"], t("bp_boxes_3d"), rtol=0, atol=1e-6)
+    loc, dim, rot = det.encode_box_3d(world["boxes_3d"])
+    torch.testing.assert_close(loc, t("bp_enc_locations"), rtol=0, atol=1e-6)
+    torch.testing.assert_close(dim, t("bp_enc_dimensions"), rtol=0, atol=1e-6)
+    torch.testing.assert_close(rot, t("bp_enc_orientations"), rtol=0, atol=1e-6)
+
+    hdf = vsrd.models.HyperDistanceField(48, [16, 16, 16, 16], 256, [256, 256, 256, 256])
+    keys = sorted(hdf.state_dict())
+    assert keys == list(u["hyper_state_keys"])
+    assert [hdf.state_dict()[k].numel() for k in keys] == list(u["hyper_state_numel"])
+    assert hdf.num_neurons_list == [784, 272, 272, 272, 17]
+    enc = vsrd.models.SinusoidalEncoder(8)
+    torch.testing.assert_close(enc(t("mlp_points")), t("mlp_encoding"), rtol=0, atol=1e-6)
+    w = t("mlp_weights")
+    torch.testing.assert_close(hdf.distance_field(w[0], t("mlp_encoding")), t("mlp_out0"), rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(hdf.distance_field(w[1], t("mlp_encoding")), t("mlp_out1"), rtol=1e-5, atol=1e-5)
+
+
+def test_project_box_3d_matches_reference_fixtures():
+    u = np.load(os.path.join(GOLDEN_DIR, "units.npz"))
+    boxes, k = torch.from_numpy(u["pb_boxes_3d"]), torch.from_numpy(u["pb_intrinsic"])
+    lines = u["pb_line_indices"].tolist()
+    got = torch.stack([vsrd.operations.project_box_3d(b, lines, k) for b in boxes])
+    torch.testing.assert_close(got, torch.from_numpy(u["pb_boxes_2d"]), rtol=1e-5, atol=1e-3)
+    assert torch.equal(got[2], torch.zeros(2, 2))       # box behind the camera
+
+
+def test_box_3d_iou_and_utils():
+    b = np.array([[-1, -1, 1], [1, -1, 1], [1, 1, 1], [-1, 1, 1], [-1, -1, -1], [1, -1, -1], [1, 1, -1], [-1, 1, -1]], float)
+    iou, bev = vsrd.operations.box_3d_iou(b, b)
+    assert float(iou) == pytest.approx(1.0) and float(bev) == pytest.approx(1.0)
+    iou, bev = vsrd.operations.box_3d_iou(b, b + np.array([1.0, 0, 0]))
+    assert float(iou) == pytest.approx(1 / 3) and float(bev) == pytest.approx(1 / 3)
+    iou, _ = vsrd.operations.box_3d_iou(b, b + np.array([5.0, 0, 0]))
+    assert float(iou) == 0.0
+    c, s = np.cos(0.3), np.sin(0.3)
+    rot = b @ np.array([[c, -s, 0], [s, c, 0], [0, 0, 1]]).T
+    iou_rot, _ = vsrd.operations.box_3d_iou(b, rot)
+    assert 0.5 < float(iou_rot) < 1.0
+
+    d = vsrd.utils.Dict.apply({"a": {"b": 1}, "c": [{"d": 2}]})
+    assert d.a.b == 1 and d.c[0].d == 2
+    f = vsrd.utils.compose(lambda x: x + 1, lambda x: x * 2)
+    assert f(3) == 8
+    made = vsrd.utils.import_module({"function": "torch.zeros", "args": [2], "kwargs": {"dtype": "eval:torch.float64"}},
+                                    globals())
+    assert made.dtype == torch.float64 and made.shape == (2,)
+    assert torch.equal(vsrd.operations.expand_to_4x4(torch.ones(2, 3, 3))[0, 3], torch.tensor([0.0, 0.0, 0.0, 1.0]))
