@@ -63,9 +63,9 @@ void hs_field_forward(const float* x, const float* t, const float* R, const floa
     std::vector<float> Wt;
     if (W) stage(W, Wt);
     for (int s = 0; s < S; ++s) {
-        float d, G[3];
-        if (W) field_forward<true>(x + 3 * s, I, Wt.data(), scale, d, G);
-        else field_forward<false>(x + 3 * s, I, nullptr, scale, d, G);
+        float d, G[3], act[kFwdActRows];
+        if (W) field_forward_looped<true>(x + 3 * s, I, Wt.data(), scale, act, 1, d, G);
+        else field_forward_looped<false>(x + 3 * s, I, nullptr, scale, act, 1, d, G);
         out[4 * s] = d; out[4 * s + 1] = G[0]; out[4 * s + 2] = G[1]; out[4 * s + 3] = G[2];
     }
 }

@@ -10,6 +10,7 @@ namespace vsrd {
 template <bool kResidual>
 __global__ void __launch_bounds__(kThreads) field_forward_kernel(SceneDev scene, RaysDev rays, float4* __restrict__ field) {
     __shared__ __align__(16) float sW[kResidual ? kNumW : 4];
+    __shared__ float sAct[kResidual ? kThreads * kFwdActRows : 1];   // [warp][row][lane]: lane-private, conflict-free
     const int inst = blockIdx.y;
     if (kResidual) {
         stage_weights(scene.W + (size_t)inst * kNumW, sW);
@@ -24,7 +25,8 @@ __global__ void __launch_bounds__(kThreads) field_forward_kernel(SceneDev scene,
     load_instance(scene, inst, I);
     float x[3], d, G[3];
     sample_position(rays, r, j, x);
-    field_forward<kResidual>(x, I, sW, scene.scale, d, G);
+    float* act = sAct + (kResidual ? (threadIdx.x >> 5) * 32 * kFwdActRows + (threadIdx.x & 31) : 0);
+    field_forward_looped<kResidual>(x, I, sW, scene.scale, act, 32, d, G);
     field[(size_t)inst * total + idx] = make_float4(d, G[0], G[1], G[2]);
 }
 

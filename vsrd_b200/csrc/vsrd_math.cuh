@@ -26,8 +26,12 @@
 
 #if defined(__CUDA_ARCH__)
 #define VSRD_UNROLL _Pragma("unroll")
+#define VSRD_NOUNROLL _Pragma("unroll 1")
+#define VSRD_UNROLL2 _Pragma("unroll 2")
 #else
 #define VSRD_UNROLL
+#define VSRD_NOUNROLL
+#define VSRD_UNROLL2
 #endif
 
 namespace vsrd {
@@ -133,9 +137,29 @@ struct MlpStash {
     float m[4];             // mean(z * centred tangent)
 };
 
+// Phi(z) = standard normal CDF, phi(z) = its density: gelu(z) = z Phi, gelu' = Phi + z phi,
+// gelu'' = phi (2 - z^2).  The reference uses the exact erf GELU (F.gelu default).  Here erf comes from
+// Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, i.e. fp32 rounding level), which shares its single
+// exponential with phi: ~15 instructions instead of ~40 for erff + expf.
+#if defined(__CUDA_ARCH__)
+#define VSRD_EXPF(x) __expf(x)
+#define VSRD_RCPF(x) __frcp_rn(x)
+#else
+#define VSRD_EXPF(x) expf(x)
+#define VSRD_RCPF(x) (1.0f / (x))
+#endif
 VSRD_HD void gelu_terms(float z, float& Phi, float& phi) {
-    Phi = 0.5f * (1.0f + erff(z * kInvSqrt2));
-    phi = kInvSqrt2Pi * expf(-0.5f * z * z);
+    const float az = fabsf(z);
+    const float E = VSRD_EXPF(-0.5f * z * z);
+    const float t = VSRD_RCPF(1.0f + (0.3275911f * kInvSqrt2) * az);
+    float poly = 1.061405429f;
+    poly = poly * t - 1.453152027f;
+    poly = poly * t + 1.421413741f;
+    poly = poly * t - 0.284496736f;
+    poly = poly * t + 0.254829592f;
+    const float tail = 0.5f * poly * t * E;        // 1 - Phi(|z|)
+    Phi = z >= 0.0f ? 1.0f - tail : tail;
+    phi = kInvSqrt2Pi * E;
 }
 
 template <int NT, bool kDiagonal, bool kStash>
@@ -251,6 +275,124 @@ VSRD_HD void field_forward(const float x[3], const Instance& I, const float* __r
         float out, outd[3];
         MlpStash dummy;
         mlp_forward_dual<3, true, false>(Wt, a, adot, out, outd, dummy);
+        const float res = sigmoidf_(out - 1.0f);
+        const float sp = res * (1.0f - res);
+        d += res;
+        VSRD_UNROLL for (int c = 0; c < 3; ++c) gp[c] += sp * outd[c];
+    }
+    VSRD_UNROLL for (int m = 0; m < 3; ++m)
+        G[m] = I.R[3 * m] * gp[0] + I.R[3 * m + 1] * gp[1] + I.R[3 * m + 2] * gp[2];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Forward, looped form used by the kernel (v3).  Same mathematics as field_forward above, organised
+// for a small instruction footprint: the profile of the fully unrolled version showed every kernel
+// stalled on instruction fetch (`stalled_no_instruction` 4 cycles per issue, profiles/r01_v2_*), so
+// layers and input neurons are real loops and the layer inputs (gelu outputs and their 3 tangents)
+// live in 64 lane-private scratch floats `act[row * stride]` (shared memory on the device).
+// The positional encoding takes accurate sincosf at frequencies k = 0 and 4 and the double-angle
+// recurrence for the three octaves in between (absolute error <= 8 * 2^-24, far below the 1e-4 bar).
+// ---------------------------------------------------------------------------------------------
+constexpr int kFwdActRows = 4 * kHid;   // g, gd_x, gd_y, gd_z
+
+template <bool kResidual>
+VSRD_HD void field_forward_looped(const float x[3], const Instance& I, const float* Wt, float scale,
+                                  float* act, int stride, float& d, float G[3]) {
+    BoxEval b;
+    box_eval(x, I, b);
+    float gp[3] = {b.gp[0], b.gp[1], b.gp[2]};
+    d = b.value;
+    if (kResidual) {
+        float a[3], coef[3];
+        {
+            const float sx[3] = {b.s[0], 1.0f, 1.0f};
+            const float m[3] = {fabsf(b.p[0]), b.p[1], b.p[2]};
+            VSRD_UNROLL for (int c = 0; c < 3; ++c) { a[c] = kPiF * (m[c] / scale); coef[c] = sx[c] * (kPiF / scale); }
+        }
+        float hv[kHid], ht[3][kHid];
+        VSRD_UNROLL for (int o = 0; o < kHid; ++o) {
+            hv[o] = Wt[kEnc * kHid + o];
+            ht[0][o] = 0.0f; ht[1][o] = 0.0f; ht[2][o] = 0.0f;
+        }
+        // ---- layer 0 fused with the positional encoding: loop over octaves
+        float cs[3], sn[3];
+        VSRD_NOUNROLL for (int k = 0; k < kFreq; ++k) {
+            const float f = (float)(1 << k);
+            if ((k & 3) == 0) {
+                VSRD_UNROLL for (int c = 0; c < 3; ++c) sincosf(f * a[c], &sn[c], &cs[c]);   // f * a exact
+            } else {
+                VSRD_UNROLL for (int c = 0; c < 3; ++c) {
+                    const float s2 = 2.0f * sn[c] * cs[c];
+                    cs[c] = (cs[c] - sn[c]) * (cs[c] + sn[c]);
+                    sn[c] = s2;
+                }
+            }
+            VSRD_UNROLL for (int c = 0; c < 3; ++c) {
+                const float da = f * coef[c];
+                const float de0 = -da * sn[c], de1 = da * cs[c];
+                const float* w0 = Wt + (c * 2 * kFreq + 2 * k) * kHid;
+                const float* w1 = w0 + kHid;
+                VSRD_UNROLL for (int o = 0; o < kHid; ++o) {
+                    hv[o] += w0[o] * cs[c] + w1[o] * sn[c];
+                    ht[c][o] += w0[o] * de0 + w1[o] * de1;
+                }
+            }
+        }
+        // ---- layers 1..4: LayerNorm -> GELU (registers) -> linear (loop over inputs, from scratch)
+        float out = 0.0f, outd[3] = {0.0f, 0.0f, 0.0f};
+        VSRD_NOUNROLL for (int l = 1; l <= 4; ++l) {
+            float mean = 0.0f;
+            VSRD_UNROLL for (int o = 0; o < kHid; ++o) mean += hv[o];
+            mean *= (1.0f / kHid);
+            float var = 0.0f;
+            VSRD_UNROLL for (int o = 0; o < kHid; ++o) { hv[o] -= mean; var += hv[o] * hv[o]; }
+            const float r = 1.0f / sqrtf(var * (1.0f / kHid) + kLnEps);
+            VSRD_UNROLL for (int o = 0; o < kHid; ++o) hv[o] *= r;
+            VSRD_UNROLL for (int t = 0; t < 3; ++t) {
+                float mt = 0.0f;
+                VSRD_UNROLL for (int o = 0; o < kHid; ++o) mt += ht[t][o];
+                mt *= (1.0f / kHid);
+                float mz = 0.0f;
+                VSRD_UNROLL for (int o = 0; o < kHid; ++o) { ht[t][o] -= mt; mz += hv[o] * ht[t][o]; }
+                mz *= (1.0f / kHid);
+                VSRD_UNROLL for (int o = 0; o < kHid; ++o) ht[t][o] = r * (ht[t][o] - hv[o] * mz);
+            }
+            VSRD_UNROLL for (int o = 0; o < kHid; ++o) {
+                float Phi, phi;
+                gelu_terms(hv[o], Phi, phi);
+                const float g1 = Phi + hv[o] * phi;
+                act[o * stride] = hv[o] * Phi;
+                act[(kHid + o) * stride] = g1 * ht[0][o];
+                act[(2 * kHid + o) * stride] = g1 * ht[1][o];
+                act[(3 * kHid + o) * stride] = g1 * ht[2][o];
+            }
+            if (l < 4) {
+                const float* W = Wt + kW1 + (l - 1) * kWStride;
+                VSRD_UNROLL for (int o = 0; o < kHid; ++o) {
+                    hv[o] = W[kHid * kHid + o];
+                    ht[0][o] = 0.0f; ht[1][o] = 0.0f; ht[2][o] = 0.0f;
+                }
+                VSRD_UNROLL2 for (int i = 0; i < kHid; ++i) {
+                    const float g = act[i * stride], t0 = act[(kHid + i) * stride];
+                    const float t1 = act[(2 * kHid + i) * stride], t2 = act[(3 * kHid + i) * stride];
+                    const float* w = W + i * kHid;
+                    VSRD_UNROLL for (int o = 0; o < kHid; ++o) {
+                        const float wo = w[o];
+                        hv[o] += wo * g; ht[0][o] += wo * t0; ht[1][o] += wo * t1; ht[2][o] += wo * t2;
+                    }
+                }
+            } else {
+                const float* w = Wt + kW4;
+                out = w[kHid];
+                VSRD_UNROLL2 for (int i = 0; i < kHid; ++i) {
+                    const float wi = w[i];
+                    out += wi * act[i * stride];
+                    outd[0] += wi * act[(kHid + i) * stride];
+                    outd[1] += wi * act[(2 * kHid + i) * stride];
+                    outd[2] += wi * act[(3 * kHid + i) * stride];
+                }
+            }
+        }
         const float res = sigmoidf_(out - 1.0f);
         const float sp = res * (1.0f - res);
         d += res;
