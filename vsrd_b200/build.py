@@ -19,7 +19,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ_DIR = os.path.join(HERE, "_obj")
 LIB_PATH = os.path.join(HERE, "libvsrd_b200.so")
 SOURCES = ["vsrd_render.cu", "vsrd_field_fwd.cu", "vsrd_field_bwd.cu"]
-HEADERS = ["vsrd_common.cuh", "vsrd_math.cuh", os.path.join("..", "..", "include", "vsrd_b200.h")]
+HEADERS = ["vsrd_common.cuh", "vsrd_math.cuh", "vsrd_frag.cuh", os.path.join("..", "..", "include", "vsrd_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
