@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/vsrd_b200.h"
@@ -93,5 +94,10 @@ inline int check_rays(const VsrdRays* r, RaysDev& d) {
     return 0;
 }
 
+// vsrd_field_bwd_mma.cu: tensor-core field backward for residual instances.
+// Rows of VSRD_GRAD_STRIDE floats the caller must provide in `partials` (-1 on error).
+int backward_mma_partial_rows(int num_instances);
+int launch_field_backward_mma(const SceneDev& s, const RaysDev& r, const float* adjoint, float* partials,
+                              float* gloc, float* grot, float* gdim, float* gW, cudaStream_t st);
 
 }  // namespace vsrd

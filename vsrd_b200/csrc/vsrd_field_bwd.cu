@@ -544,6 +544,13 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partials, int G
 static int g_num_sms = 0;
 static int g_bwd_blocks_per_sm[2] = {0, 0};
 
+// 0 = tensor-core kernel (default), 1 = SIMT kernel kept as an independent cross-check
+// (VSRD_FIELD_IMPL=simt, read per call so a test can flip it inside one process)
+static int backward_impl() {
+    const char* impl = getenv("VSRD_FIELD_IMPL");
+    return (impl && strcmp(impl, "simt") == 0) ? 1 : 0;
+}
+
 static int device_setup() {
     if (g_num_sms) return 0;
     int dev = 0;
@@ -583,7 +590,12 @@ int vsrd_backward_blocks_per_instance(int num_instances, int num_rays, int num_i
     // the residual kernel has the lower occupancy; size for the larger grid so one buffer fits both
     const int a = backward_blocks(num_instances, num_rays, num_intervals, false);
     const int b = backward_blocks(num_instances, num_rays, num_intervals, true);
-    return a > b ? a : b;
+    // the tensor-core kernel writes one row per (CTA, instance) segment: at most #SMs + N rows
+    const int rows = backward_mma_partial_rows(num_instances);
+    if (rows < 0) return -1;
+    const int n = num_instances > 0 ? num_instances : 1;
+    const int c = (rows + n - 1) / n;
+    return a > b ? (a > c ? a : c) : (b > c ? b : c);
 }
 
 int vsrd_field_backward(const VsrdScene* scene, const VsrdRays* rays, const float* adjoint, float* partials,
@@ -597,6 +609,9 @@ int vsrd_field_backward(const VsrdScene* scene, const VsrdRays* rays, const floa
     cudaStream_t st = (cudaStream_t)stream;
     const size_t total = (size_t)r.R * r.M;
     VSRD_CHECK_ARG(total < (size_t)1 << 31, "R*M must be < 2^31");
+    if (total > 0 && s.W && backward_impl() == 0)
+        return launch_field_backward_mma(s, r, adjoint, partials, grad_locations, grad_rotations, grad_half_extents,
+                                         grad_mlp_weights, st);
     int G = 1;
     if (total == 0) {
         cudaMemsetAsync(partials, 0, (size_t)s.N * kGradStride * sizeof(float), st);

@@ -1,0 +1,650 @@
+// sm_100a kernels of the VSRD silhouette-renderer hot path, part 3b: tensor-core field backward (v5).
+//
+// Replaces the autograd double-backward replay of the reference (renderers.py:218-228 create_graph=True,
+// main.py:859) for the residual-MLP instances.  Given the adjoints (dd, dG) of every (sample, instance)
+// field value and spatial gradient it accumulates the gradient of
+//      phi = dd * d(p; theta) + (R^T dG) . grad_p d(p; theta)
+// w.r.t. the 1617 MLP weights and the 15 pose parameters of the instance ("one tangent + one reverse
+// sweep"; the scalar restatement is vsrd_math.cuh::field_backward).
+//
+// One warp owns a tile of 32 samples of one instance in the mma.sync fragment layout of vsrd_frag.cuh:
+//   1. lane == sample: position, box SDF, tangent direction v = R^T dG, PE arguments
+//   2. dual forward sweep (value + tangent along v): 3xTF32 mma.sync contractions chained in registers,
+//      LayerNorm statistics by quad reductions; LayerNorm outputs (z, zd) of layers 1..3 go to a
+//      lane-private shared-memory stash, those of layer 4 stay in registers
+//   3. reverse sweep layer by layer: transposed contractions (3xTF32), LayerNorm/GELU second-order
+//      adjoints, and the weight gradient dW_l += hbar^T g + hdbar^T gd as a sample-contracted bf16x2
+//      mma.sync m16n8k16 whose operands are transposed in registers by movmatrix
+//   4. lane == sample: chain through |p_x|, the box SDF and the pose
+// Weight-gradient accumulators live in per-warp shared memory in fragment layout (plain float4
+// load/add/store, no atomics, deterministic) and are reduced once per (CTA, instance) segment into one
+// partial row; reduce_segment_rows_kernel sums the rows of each instance.
+//
+// Persistent: gridDim.x CTAs split the N * tiles_per_inst warp tiles evenly (any N fills the SMs); a
+// CTA restages the weight fragments when its range crosses an instance boundary.  Segment (cta b,
+// instance i) writes partial row b + i (strictly increasing along the tile order, hence unique).
+#include "vsrd_frag.cuh"
+
+namespace vsrd {
+namespace bwd5 {
+
+constexpr int kWarpsB = 8;
+constexpr int kThreadsB = kWarpsB * 32;
+constexpr int kStashFloats = 3 * 32 * 32;     // per warp: layers 1..3 x [z 16 rows | zd 16 rows] x 32 lanes
+constexpr int kAccHidden = 0;                 // hidden layer l: fragments 3 (l-1) + {inputs 0-7, inputs 8-15, bias}
+constexpr int kAccL0 = 9;                     // layer 0: input tiles 0..5, bias
+constexpr int kAccLast = 16;                  // last layer: this lane's 4 channels
+constexpr int kAccPose = 17;                  // (sum obar, pose 0..2) (pose 3..6) (pose 7..10) (pose 11..14), lane == sample
+constexpr int kAccFrags = 21;
+constexpr int kAccFloat4 = kAccFrags * 32;
+constexpr size_t kSmemBytes = frag::kWeightBytes
+    + (size_t)kWarpsB * (kAccFloat4 * sizeof(float4) + kStashFloats * sizeof(float) + 32 * sizeof(float));
+
+__device__ __forceinline__ void slot_get(const float (&a)[2][2][4], int s, float (&v)[4]) {
+    const int mt = s >> 1, q = 2 * (s & 1);
+    v[0] = a[mt][0][q]; v[1] = a[mt][0][q + 1]; v[2] = a[mt][1][q]; v[3] = a[mt][1][q + 1];
+}
+__device__ __forceinline__ void slot_put(float (&a)[2][2][4], int s, const float (&v)[4]) {
+    const int mt = s >> 1, q = 2 * (s & 1);
+    a[mt][0][q] = v[0]; a[mt][0][q + 1] = v[1]; a[mt][1][q] = v[2]; a[mt][1][q + 1] = v[3];
+}
+
+// LayerNorm (no affine, eps 1e-5) of one row and of its tangent.  In: v = h, d = hd (this lane's 4 of the
+// 16 channels).  Out: v = z, d = zd, rs = 1/sigma, mz = mean(z * centred tangent).
+__device__ __forceinline__ void ln_dual(float (&v)[4], float (&d)[4], float& rs, float& mz) {
+    constexpr float inv = 1.0f / kHid;
+    const float mean = frag::quad_sum((v[0] + v[1]) + (v[2] + v[3])) * inv;
+    const float mt = frag::quad_sum((d[0] + d[1]) + (d[2] + d[3])) * inv;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { v[k] -= mean; d[k] -= mt; }
+    const float var = frag::quad_sum(fmaf(v[0], v[0], v[1] * v[1]) + fmaf(v[2], v[2], v[3] * v[3])) * inv;
+    rs = rsqrtf(var + kLnEps);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] *= rs;
+    mz = frag::quad_sum(fmaf(v[0], d[0], v[1] * d[1]) + fmaf(v[2], d[2], v[3] * d[3])) * inv;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) d[k] = rs * (d[k] - v[k] * mz);
+}
+
+// Adjoint of (LayerNorm -> GELU) and of its tangent for one row (vsrd_math.cuh::ln_gelu_reverse).
+// gb / gdb: adjoints of gelu(z) and of its tangent; out hb / hdb: adjoints of the LayerNorm input and
+// of its tangent.
+__device__ __forceinline__ void ln_gelu_reverse_row(const float (&z)[4], const float (&zd)[4], const float (&g1)[4],
+                                                    const float (&g2)[4], float rs, float m, const float (&gb)[4],
+                                                    const float (&gdb)[4], float (&hb)[4], float (&hdb)[4]) {
+    constexpr float inv = 1.0f / kHid;
+    float zb[4], zdb[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        zdb[k] = gdb[k] * g1[k];
+        zb[k] = fmaf(gb[k], g1[k], gdb[k] * g2[k] * zd[k]);
+    }
+    const float s_zb = frag::quad_sum((zb[0] + zb[1]) + (zb[2] + zb[3])) * inv;
+    const float s_zzb = frag::quad_sum(fmaf(z[0], zb[0], z[1] * zb[1]) + fmaf(z[2], zb[2], z[3] * zb[3])) * inv;
+    const float s_zdb = frag::quad_sum((zdb[0] + zdb[1]) + (zdb[2] + zdb[3])) * inv;
+    const float s_zzdb = frag::quad_sum(fmaf(z[0], zdb[0], z[1] * zdb[1]) + fmaf(z[2], zdb[2], z[3] * zdb[3])) * inv;
+    const float s_zdzdb = frag::quad_sum(fmaf(zd[0], zdb[0], zd[1] * zdb[1]) + fmaf(zd[2], zdb[2], zd[3] * zdb[3])) * inv;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        hdb[k] = rs * (zdb[k] - s_zdb - z[k] * s_zzdb);
+        hb[k] = rs * (zb[k] - s_zb - z[k] * (s_zzb + s_zdzdb) - m * hdb[k] - s_zzdb * zd[k]);
+    }
+}
+
+// GELU value / first / second derivative factors of one row.
+__device__ __forceinline__ void gelu_row(const float (&z)[4], const float (&zd)[4], float (&g)[4], float (&gd)[4],
+                                         float (&g1)[4], float (&g2)[4]) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        float Phi, phi;
+        frag::gelu_terms_fast(z[k], Phi, phi);
+        g[k] = z[k] * Phi;
+        g1[k] = fmaf(z[k], phi, Phi);
+        g2[k] = phi * (2.0f - z[k] * z[k]);
+        gd[k] = g1[k] * zd[k];
+    }
+}
+
+// Box part of the backward at one sample (vsrd_math.cuh::field_backward, first half).
+struct PoseTerms {
+    BoxEval b;
+    float v[3], pbar[3], vbar[3], dimbar[3], coef[3];
+};
+
+__device__ __forceinline__ void pose_terms(const float x[3], const Instance& I, float pi_scale, float dd,
+                                           const float dG[3], PoseTerms& p) {
+    box_eval(x, I, p.b);
+    const BoxEval& b = p.b;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) p.v[k] = I.R[k] * dG[0] + I.R[3 + k] * dG[1] + I.R[6 + k] * dG[2];
+    float vs = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) vs += p.v[k] * b.s[k] * b.a[k];
+    const float inv_n = 1.0f / b.nrm;
+    const float inv_n3 = inv_n * inv_n * inv_n;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float act = b.q[k] > 0.0f ? 1.0f : 0.0f;
+        const float hess = act * p.v[k] * b.s[k] * inv_n - b.a[k] * vs * inv_n3;
+        p.pbar[k] = dd * b.gp[k] + b.s[k] * hess;
+        p.dimbar[k] = -(dd * (b.a[k] * inv_n + b.ind[k]) + hess);
+        p.vbar[k] = b.gp[k];
+    }
+    p.coef[0] = b.s[0] * pi_scale;
+    p.coef[1] = pi_scale;
+    p.coef[2] = pi_scale;
+}
+
+__global__ void __launch_bounds__(kThreadsB, 1) field_backward_mma_kernel(
+        SceneDev scene, RaysDev rays, const float4* __restrict__ adjoint, float* __restrict__ partials,
+        int tiles_per_inst) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4* sF = reinterpret_cast<float4*>(smem_raw);
+    float* sTail = reinterpret_cast<float*>(sF + frag::kFragFloat4);
+    float4* sAcc = reinterpret_cast<float4*>(sTail + frag::kTailFloats);
+    float* sStash = reinterpret_cast<float*>(sAcc + kWarpsB * kAccFloat4);
+    float* sRed = sStash + kWarpsB * kStashFloats;          // [warp][32]: last layer (17) + pose (15)
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t = lane & 3;
+    const int quad_base = lane & ~3;
+    float4* accL = sAcc + warp * kAccFloat4 + lane;         // accL[fragment * 32]
+    float* stash = sStash + warp * kStashFloats + lane;
+    const float4* fragL = sF + lane;
+
+    const int total = rays.R * rays.M;
+    const long long all_tiles = (long long)scene.N * tiles_per_inst;
+    const long long begin = all_tiles * blockIdx.x / gridDim.x;
+    const long long end = all_tiles * (blockIdx.x + 1) / gridDim.x;
+    const float pi_scale = kPiF / scene.scale;
+
+    for (long long seg = begin; seg < end;) {
+        const int inst = (int)(seg / tiles_per_inst);
+        const long long seg_end = min(end, (long long)(inst + 1) * tiles_per_inst);
+        __syncthreads();                                    // previous segment fully flushed
+        frag::stage_weight_fragments(scene.W + (size_t)inst * kNumW, sF, sTail);
+#pragma unroll
+        for (int f = 0; f < kAccFrags; ++f) accL[f * 32] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        __syncthreads();
+        Instance I;
+        load_instance(scene, inst, I);
+        const float4* adj_inst = adjoint + (size_t)inst * total;
+        const float w4v[4] = {sTail[frag::kTailW4 + 2 * t], sTail[frag::kTailW4 + 2 * t + 1],
+                              sTail[frag::kTailW4 + 8 + 2 * t], sTail[frag::kTailW4 + 8 + 2 * t + 1]};
+        const float b4 = sTail[frag::kTailB4];
+
+#pragma unroll 1
+        for (long long tile = seg + warp; tile < seg_end; tile += kWarpsB) {
+            const int base = (int)(tile - (long long)inst * tiles_per_inst) * 32;
+            const int idx = min(base + lane, total - 1);
+            const bool valid = base + lane < total;
+            const int r = idx / rays.M;
+            const int j = idx - r * rays.M;
+            // ------------------------------------------------------------ 1. lane == sample
+            float4 adj = make_float4(0.0f, 0.0f, 0.0f, 0.0f);   // zero adjoints contribute exactly zero
+            if (valid) adj = __ldg(adj_inst + idx);
+            if (!__any_sync(kFull, adj.x != 0.0f || adj.y != 0.0f || adj.z != 0.0f || adj.w != 0.0f)) continue;
+            float arow[4][3], adrow[4][3], ddrow[4];
+            {
+                float x[3];
+                sample_position(rays, r, j, x);
+                BoxEval b;
+                box_eval(x, I, b);
+                const float m[3] = {fabsf(b.p[0]), b.p[1], b.p[2]};
+                const float coef[3] = {b.s[0] * pi_scale, pi_scale, pi_scale};
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float vc = I.R[c] * adj.y + I.R[3 + c] * adj.z + I.R[6 + c] * adj.w;
+                    float v[4];
+                    frag::lanes_to_rows(kPiF * (m[c] / scene.scale), lane, v);
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) arow[s][c] = v[s];
+                    frag::lanes_to_rows(coef[c] * vc, lane, v);
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) adrow[s][c] = v[s];
+                }
+                frag::lanes_to_rows(adj.x, lane, ddrow);
+            }
+            // ------------------------------------------------------------ 2. dual forward sweep
+            frag::Encoding e;
+            frag::encode(arow, t, e);
+            const float f0 = (float)(1 << t), f1 = 16.0f * f0;
+            float h[2][2][4], hd[2][2][4];
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                const float b0 = sTail[8 * nt + 2 * t], b1 = sTail[8 * nt + 2 * t + 1];
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    h[mt][nt][0] = b0; h[mt][nt][1] = b1; h[mt][nt][2] = b0; h[mt][nt][3] = b1;
+                    hd[mt][nt][0] = 0.0f; hd[mt][nt][1] = 0.0f; hd[mt][nt][2] = 0.0f; hd[mt][nt][3] = 0.0f;
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int f = 0; f < 2; ++f) {
+                    const int ks = 2 * c + f;
+                    const float fk = f ? f1 : f0;
+                    const float4 w0 = fragL[(frag::kF0 + 2 * ks) * 32], w1 = fragL[(frag::kF0 + 2 * ks + 1) * 32];
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt) {
+                        const float cs0 = e.cs[2 * mt][c][f], cs1 = e.cs[2 * mt + 1][c][f];
+                        const float sn0 = e.sn[2 * mt][c][f], sn1 = e.sn[2 * mt + 1][c][f];
+                        const float da0 = fk * adrow[2 * mt][c], da1 = fk * adrow[2 * mt + 1][c];
+                        uint32_t ah[4], al[4];
+                        frag::split(cs0, ah[0], al[0]);
+                        frag::split(cs1, ah[1], al[1]);
+                        frag::split(sn0, ah[2], al[2]);
+                        frag::split(sn1, ah[3], al[3]);
+                        frag::mma3(h[mt][0], ah, al, w0);
+                        frag::mma3(h[mt][1], ah, al, w1);
+                        frag::split(-da0 * sn0, ah[0], al[0]);
+                        frag::split(-da1 * sn1, ah[1], al[1]);
+                        frag::split(da0 * cs0, ah[2], al[2]);
+                        frag::split(da1 * cs1, ah[3], al[3]);
+                        frag::mma3(hd[mt][0], ah, al, w0);
+                        frag::mma3(hd[mt][1], ah, al, w1);
+                    }
+                }
+            // layers 1..3: LayerNorm -> GELU -> linear; lane t keeps 1/sigma and mz of layer t + 1
+            float rreg[4] = {0.0f, 0.0f, 0.0f, 0.0f}, mreg[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll 1
+            for (int l = 1; l <= 3; ++l) {
+                float* st = stash + (l - 1) * 32 * 32;
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    float v[4], d[4], rs, mz;
+                    slot_get(h, s, v);
+                    slot_get(hd, s, d);
+                    ln_dual(v, d, rs, mz);
+                    if (t == l - 1) { rreg[s] = rs; mreg[s] = mz; }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        float Phi, phi;
+                        frag::gelu_terms_fast(v[k], Phi, phi);
+                        st[(4 * s + k) * 32] = v[k];
+                        st[(16 + 4 * s + k) * 32] = d[k];
+                        d[k] *= fmaf(v[k], phi, Phi);
+                        v[k] *= Phi;
+                    }
+                    slot_put(h, s, v);
+                    slot_put(hd, s, d);
+                }
+                float hn[2][2][4], hdn[2][2][4];
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) {
+                    const float b0 = sTail[16 * l + 8 * nt + 2 * t], b1 = sTail[16 * l + 8 * nt + 2 * t + 1];
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt) {
+                        hn[mt][nt][0] = b0; hn[mt][nt][1] = b1; hn[mt][nt][2] = b0; hn[mt][nt][3] = b1;
+                        hdn[mt][nt][0] = 0.0f; hdn[mt][nt][1] = 0.0f; hdn[mt][nt][2] = 0.0f; hdn[mt][nt][3] = 0.0f;
+                    }
+                }
+                const float4* fl = fragL + (frag::kF1 + 4 * (l - 1)) * 32;
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {
+                    const float4 w0 = fl[(2 * ks) * 32], w1 = fl[(2 * ks + 1) * 32];
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt) {
+                        uint32_t ah[4], al[4];
+                        frag::a_from_c(h[mt][ks], ah, al);
+                        frag::mma3(hn[mt][0], ah, al, w0);
+                        frag::mma3(hn[mt][1], ah, al, w1);
+                        frag::a_from_c(hd[mt][ks], ah, al);
+                        frag::mma3(hdn[mt][0], ah, al, w0);
+                        frag::mma3(hdn[mt][1], ah, al, w1);
+                    }
+                }
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) { h[mt][nt][q] = hn[mt][nt][q]; hd[mt][nt][q] = hdn[mt][nt][q]; }
+            }
+            // ------------------------------------------------------------ 3. reverse sweep
+            // layer 4 (16 -> 1), LayerNorm outputs stay in registers; hb / hdb: adjoints of the output of
+            // linear layer 3 and of its tangent (C layout)
+            float hb[2][2][4], hdb[2][2][4];
+            {
+                float4 last = accL[kAccLast * 32];
+                float obsum = 0.0f;
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    float z[4], zd[4], rs, mz, g[4], gd[4], g1[4], g2[4];
+                    slot_get(h, s, z);
+                    slot_get(hd, s, zd);
+                    ln_dual(z, zd, rs, mz);
+                    gelu_row(z, zd, g, gd, g1, g2);
+                    float po = fmaf(w4v[0], g[0], w4v[1] * g[1]) + fmaf(w4v[2], g[2], w4v[3] * g[3]);
+                    float pod = fmaf(w4v[0], gd[0], w4v[1] * gd[1]) + fmaf(w4v[2], gd[2], w4v[3] * gd[3]);
+                    const float out = frag::quad_sum(po) + b4;
+                    const float outd = frag::quad_sum(pod);
+                    const float res = sigmoidf_(out - 1.0f);
+                    const float sp = res * (1.0f - res);
+                    const float obar = fmaf(ddrow[s], sp, sp * (1.0f - 2.0f * res) * outd);
+                    const float odbar = sp;
+                    obsum += obar;
+                    last.x += fmaf(obar, g[0], odbar * gd[0]);
+                    last.y += fmaf(obar, g[1], odbar * gd[1]);
+                    last.z += fmaf(obar, g[2], odbar * gd[2]);
+                    last.w += fmaf(obar, g[3], odbar * gd[3]);
+                    float gb[4], gdb[4], hbv[4], hdbv[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { gb[k] = w4v[k] * obar; gdb[k] = w4v[k] * odbar; }
+                    ln_gelu_reverse_row(z, zd, g1, g2, rs, mz, gb, gdb, hbv, hdbv);
+                    slot_put(hb, s, hbv);
+                    slot_put(hdb, s, hdbv);
+                }
+                accL[kAccLast * 32] = last;
+                float4 p0 = accL[kAccPose * 32];
+                p0.x += obsum;
+                accL[kAccPose * 32] = p0;
+            }
+#pragma unroll 1
+            for (int l = 3; l >= 1; --l) {
+                // adjoints of gelu(z_l) and its tangent: W_l^T hb, W_l^T hdb
+                float gb[2][2][4], gdb[2][2][4];
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) { gb[mt][nt][q] = 0.0f; gdb[mt][nt][q] = 0.0f; }
+                {
+                    const float4* fl = fragL + (frag::kR1 + 4 * (l - 1)) * 32;
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks) {
+                        const float4 w0 = fl[(2 * ks) * 32], w1 = fl[(2 * ks + 1) * 32];
+#pragma unroll
+                        for (int mt = 0; mt < 2; ++mt) {
+                            uint32_t ah[4], al[4];
+                            frag::a_from_c(hb[mt][ks], ah, al);
+                            frag::mma3(gb[mt][0], ah, al, w0);
+                            frag::mma3(gb[mt][1], ah, al, w1);
+                            frag::a_from_c(hdb[mt][ks], ah, al);
+                            frag::mma3(gdb[mt][0], ah, al, w0);
+                            frag::mma3(gdb[mt][1], ah, al, w1);
+                        }
+                    }
+                }
+                float4* accW = accL + (kAccHidden + 3 * (l - 1)) * 32;
+                float D[3][4];
+#pragma unroll
+                for (int n = 0; n < 3; ++n) {
+                    const float4 a = accW[n * 32];
+                    D[n][0] = a.x; D[n][1] = a.y; D[n][2] = a.z; D[n][3] = a.w;
+                }
+                const float* st = stash + (l - 1) * 32 * 32;
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    float z[2][4], zd[2][4], g[2][4], gd[2][4], g1[2][4], g2[2][4];
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {
+                        const int s = 2 * mt + hf;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) { z[hf][k] = st[(4 * s + k) * 32]; zd[hf][k] = st[(16 + 4 * s + k) * 32]; }
+                        gelu_row(z[hf], zd[hf], g[hf], gd[hf], g1[hf], g2[hf]);
+                    }
+                    // weight gradient of linear layer l over the 16 samples of this m-tile
+                    {
+                        uint32_t ah[4], al[4];
+                        frag::wgrad_a_operand(hb[mt], ah, al);
+                        frag::wgrad_tile(D[0], ah, al, g[0][0], g[0][1], g[1][0], g[1][1]);
+                        frag::wgrad_tile(D[1], ah, al, g[0][2], g[0][3], g[1][2], g[1][3]);
+                        frag::wgrad_bias(D[2], ah, al);
+                        frag::wgrad_a_operand(hdb[mt], ah, al);
+                        frag::wgrad_tile(D[0], ah, al, gd[0][0], gd[0][1], gd[1][0], gd[1][1]);
+                        frag::wgrad_tile(D[1], ah, al, gd[0][2], gd[0][3], gd[1][2], gd[1][3]);
+                    }
+                    // LayerNorm / GELU adjoint: hb, hdb <- adjoints of the output of linear layer l - 1
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {
+                        const int s = 2 * mt + hf;
+                        const float rs = __shfl_sync(kFull, rreg[s], quad_base | (l - 1));
+                        const float mz = __shfl_sync(kFull, mreg[s], quad_base | (l - 1));
+                        float gbv[4], gdbv[4], hbv[4], hdbv[4];
+                        slot_get(gb, s, gbv);
+                        slot_get(gdb, s, gdbv);
+                        ln_gelu_reverse_row(z[hf], zd[hf], g1[hf], g2[hf], rs, mz, gbv, gdbv, hbv, hdbv);
+                        slot_put(hb, s, hbv);
+                        slot_put(hdb, s, hdbv);
+                    }
+                }
+#pragma unroll
+                for (int n = 0; n < 3; ++n) accW[n * 32] = make_float4(D[n][0], D[n][1], D[n][2], D[n][3]);
+            }
+            // layer 0: weight gradient against the encoding and its tangent, then the encoding adjoint
+            //   abar_c  = sum_k 2^k (ebar_sin cos - ebar_cos sin - da (edbar_cos cos + edbar_sin sin))
+            //   adbar_c = sum_k 2^k (edbar_sin cos - edbar_cos sin)
+            float abar[4][3], adbar[4][3];
+            {
+                float D0[7][4];
+#pragma unroll
+                for (int n = 0; n < 7; ++n) {
+                    const float4 a = accL[(kAccL0 + n) * 32];
+                    D0[n][0] = a.x; D0[n][1] = a.y; D0[n][2] = a.z; D0[n][3] = a.w;
+                }
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    const int s0 = 2 * mt, s1 = 2 * mt + 1;
+                    {
+                        uint32_t ah[4], al[4], adh[4], adl[4];
+                        frag::wgrad_a_operand(hb[mt], ah, al);
+                        frag::wgrad_a_operand(hdb[mt], adh, adl);
+                        frag::wgrad_bias(D0[6], ah, al);
+#pragma unroll
+                        for (int c = 0; c < 3; ++c)
+#pragma unroll
+                            for (int f = 0; f < 2; ++f) {
+                                const float fk = f ? f1 : f0;
+                                const float cs0 = e.cs[s0][c][f], cs1 = e.cs[s1][c][f];
+                                const float sn0 = e.sn[s0][c][f], sn1 = e.sn[s1][c][f];
+                                const float da0 = fk * adrow[s0][c], da1 = fk * adrow[s1][c];
+                                frag::wgrad_tile(D0[2 * c + f], ah, al, cs0, sn0, cs1, sn1);
+                                frag::wgrad_tile(D0[2 * c + f], adh, adl, -da0 * sn0, da0 * cs0, -da1 * sn1, da1 * cs1);
+                            }
+                    }
+                    uint32_t ah[2][4], al[2][4], adh[2][4], adl[2][4];
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks) {
+                        frag::a_from_c(hb[mt][ks], ah[ks], al[ks]);
+                        frag::a_from_c(hdb[mt][ks], adh[ks], adl[ks]);
+                    }
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        float acc0 = 0.0f, acc1 = 0.0f, accd0 = 0.0f, accd1 = 0.0f;
+#pragma unroll
+                        for (int f = 0; f < 2; ++f) {
+                            const int nt = 2 * c + f;
+                            const float fk = f ? f1 : f0;
+                            const float4 w0 = fragL[(frag::kR0 + nt) * 32], w1 = fragL[(frag::kR0 + 6 + nt) * 32];
+                            float eb[4] = {0.0f, 0.0f, 0.0f, 0.0f}, edb[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                            frag::mma3(eb, ah[0], al[0], w0);
+                            frag::mma3(eb, ah[1], al[1], w1);
+                            frag::mma3(edb, adh[0], adl[0], w0);
+                            frag::mma3(edb, adh[1], adl[1], w1);
+                            const float cs0 = e.cs[s0][c][f], cs1 = e.cs[s1][c][f];
+                            const float sn0 = e.sn[s0][c][f], sn1 = e.sn[s1][c][f];
+                            const float da0 = fk * adrow[s0][c], da1 = fk * adrow[s1][c];
+                            acc0 += fk * (eb[1] * cs0 - eb[0] * sn0 - da0 * (edb[0] * cs0 + edb[1] * sn0));
+                            accd0 += fk * (edb[1] * cs0 - edb[0] * sn0);
+                            acc1 += fk * (eb[3] * cs1 - eb[2] * sn1 - da1 * (edb[2] * cs1 + edb[3] * sn1));
+                            accd1 += fk * (edb[3] * cs1 - edb[2] * sn1);
+                        }
+                        abar[s0][c] = frag::quad_sum(acc0);
+                        abar[s1][c] = frag::quad_sum(acc1);
+                        adbar[s0][c] = frag::quad_sum(accd0);
+                        adbar[s1][c] = frag::quad_sum(accd1);
+                    }
+                }
+#pragma unroll
+                for (int n = 0; n < 7; ++n) accL[(kAccL0 + n) * 32] = make_float4(D0[n][0], D0[n][1], D0[n][2], D0[n][3]);
+            }
+            // ------------------------------------------------------------ 4. lane == sample: pose
+            {
+                float ga[3], gad[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float va[4] = {abar[0][c], abar[1][c], abar[2][c], abar[3][c]};
+                    const float vd[4] = {adbar[0][c], adbar[1][c], adbar[2][c], adbar[3][c]};
+                    ga[c] = frag::rows_to_lanes(va, lane);
+                    gad[c] = frag::rows_to_lanes(vd, lane);
+                }
+                float x[3];
+                sample_position(rays, r, j, x);
+                const float dG[3] = {adj.y, adj.z, adj.w};
+                PoseTerms p;
+                pose_terms(x, I, pi_scale, adj.x, dG, p);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    p.pbar[c] = fmaf(ga[c], p.coef[c], p.pbar[c]);
+                    p.vbar[c] = fmaf(gad[c], p.coef[c], p.vbar[c]);
+                }
+                float pose[kNumPose];
+#pragma unroll
+                for (int m = 0; m < 3; ++m) {
+                    pose[m] = -(I.R[3 * m] * p.pbar[0] + I.R[3 * m + 1] * p.pbar[1] + I.R[3 * m + 2] * p.pbar[2]);
+                    pose[3 + m] = p.dimbar[m];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) pose[6 + 3 * m + k] = p.b.y[m] * p.pbar[k] + dG[m] * p.vbar[k];
+                }
+                float4 a0 = accL[kAccPose * 32], a1 = accL[(kAccPose + 1) * 32];
+                float4 a2 = accL[(kAccPose + 2) * 32], a3 = accL[(kAccPose + 3) * 32];
+                a0.y += pose[0]; a0.z += pose[1]; a0.w += pose[2];
+                a1.x += pose[3]; a1.y += pose[4]; a1.z += pose[5]; a1.w += pose[6];
+                a2.x += pose[7]; a2.y += pose[8]; a2.z += pose[9]; a2.w += pose[10];
+                a3.x += pose[11]; a3.y += pose[12]; a3.z += pose[13]; a3.w += pose[14];
+                accL[kAccPose * 32] = a0; accL[(kAccPose + 1) * 32] = a1;
+                accL[(kAccPose + 2) * 32] = a2; accL[(kAccPose + 3) * 32] = a3;
+            }
+            __syncwarp();
+        }
+        // ---------------------------------------------------------------- flush this segment
+        {
+            // last layer: reduce over the 8 quads (lane bits 2..4); bias / pose: over all 32 lanes
+            float4 last = accL[kAccLast * 32];
+            float v[16];
+            {
+                const float4 a0 = accL[kAccPose * 32], a1 = accL[(kAccPose + 1) * 32];
+                const float4 a2 = accL[(kAccPose + 2) * 32], a3 = accL[(kAccPose + 3) * 32];
+                v[0] = 0.25f * a0.x;                       // obar was accumulated by all 4 lanes of each quad
+                v[1] = a0.y; v[2] = a0.z; v[3] = a0.w;
+                v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
+                v[8] = a2.x; v[9] = a2.y; v[10] = a2.z; v[11] = a2.w;
+                v[12] = a3.x; v[13] = a3.y; v[14] = a3.z; v[15] = a3.w;
+            }
+#pragma unroll
+            for (int sh = 16; sh >= 1; sh >>= 1) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) v[k] += __shfl_xor_sync(kFull, v[k], sh);
+                if (sh >= 4) {
+                    last.x += __shfl_xor_sync(kFull, last.x, sh);
+                    last.y += __shfl_xor_sync(kFull, last.y, sh);
+                    last.z += __shfl_xor_sync(kFull, last.z, sh);
+                    last.w += __shfl_xor_sync(kFull, last.w, sh);
+                }
+            }
+            float* red = sRed + warp * 32;
+            if (lane < 4) {
+                red[2 * lane] = last.x; red[2 * lane + 1] = last.y;
+                red[8 + 2 * lane] = last.z; red[8 + 2 * lane + 1] = last.w;
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) red[16 + k] = v[k];
+            }
+        }
+        __syncthreads();
+        {
+            float* out = partials + ((size_t)blockIdx.x + inst) * kGradStride;
+            for (int f = threadIdx.x; f < kGradStride; f += kThreadsB) {
+                float s = 0.0f;
+                if (f >= kW4) {
+#pragma unroll
+                    for (int w = 0; w < kWarpsB; ++w) s += sRed[w * 32 + f - kW4];
+                } else {
+                    int fragment, o, i, fan_in;
+                    if (f < kW1) {
+                        o = f / (kEnc + 1); i = f - o * (kEnc + 1); fan_in = kEnc;
+                        fragment = kAccL0 + (i < kEnc ? (i >> 3) : 6);
+                    } else {
+                        int q = f - kW1;
+                        const int l = q / kWStride;
+                        q -= l * kWStride;
+                        o = q / (kHid + 1); i = q - o * (kHid + 1); fan_in = kHid;
+                        fragment = kAccHidden + 3 * l + (i < kHid ? (i >> 3) : 2);
+                    }
+                    const bool bias = i == fan_in;
+                    const int tt = bias ? 0 : ((i & 7) >> 1);
+                    const int comp = ((o >> 3) << 1) | (bias ? 0 : (i & 1));
+                    const float* p = reinterpret_cast<const float*>(sAcc + fragment * 32 + 4 * (o & 7) + tt) + comp;
+#pragma unroll
+                    for (int w = 0; w < kWarpsB; ++w) s += p[(size_t)w * kAccFloat4 * 4];
+                }
+                out[f] = s;
+            }
+        }
+        seg = seg_end;
+    }
+}
+
+// Sum the partial rows of every instance: the CTAs whose tile range intersects the instance's tiles are
+// b0..b1 (cta(T) = ((T + 1) * grid - 1) / all_tiles for tile T), their rows b + inst.
+__global__ void reduce_segment_rows_kernel(const float* __restrict__ partials, int grid, int tiles_per_inst,
+                                           long long all_tiles, float* __restrict__ gloc, float* __restrict__ grot,
+                                           float* __restrict__ gdim, float* __restrict__ gW) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    const int inst = blockIdx.y;
+    if (f >= kNumW + kNumPose) return;
+    const long long first = (long long)inst * tiles_per_inst, last = first + tiles_per_inst - 1;
+    const int b0 = (int)(((first + 1) * grid - 1) / all_tiles);
+    const int b1 = (int)(((last + 1) * grid - 1) / all_tiles);
+    float s = 0.0f;
+    for (int b = b0; b <= b1; ++b) s += partials[((size_t)b + inst) * kGradStride + f];
+    if (f < kNumW) gW[(size_t)inst * kNumW + f] = s;
+    else if (f < kNumW + 3) gloc[3 * inst + (f - kNumW)] = s;
+    else if (f < kNumW + 6) gdim[3 * inst + (f - kNumW - 3)] = s;
+    else grot[9 * inst + (f - kNumW - 6)] = s;
+}
+
+static int g_sms = 0;
+
+static int setup() {
+    if (g_sms) return 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return fail("vsrd_b200: no CUDA device%s");
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return fail("vsrd_b200: cudaGetDeviceProperties failed%s");
+    if (cudaFuncSetAttribute(field_backward_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)kSmemBytes) != cudaSuccess)
+        return fail("vsrd_b200: cannot reserve %s of shared memory for field_backward_mma_kernel (built for sm_100a)", "206 KB");
+    g_sms = prop.multiProcessorCount;
+    return 0;
+}
+
+}  // namespace bwd5
+
+int backward_mma_partial_rows(int num_instances) {
+    if (bwd5::setup()) return -1;
+    return bwd5::g_sms + num_instances;
+}
+
+int launch_field_backward_mma(const SceneDev& s, const RaysDev& r, const float* adjoint, float* partials,
+                              float* gloc, float* grot, float* gdim, float* gW, cudaStream_t st) {
+    if (bwd5::setup()) return 1;
+    const long long total = (long long)r.R * r.M;
+    const int tiles_per_inst = (int)((total + 31) / 32);
+    const long long all_tiles = (long long)s.N * tiles_per_inst;
+    const long long want = (all_tiles + bwd5::kWarpsB - 1) / bwd5::kWarpsB;
+    const int grid = (int)(want < bwd5::g_sms ? want : bwd5::g_sms);
+    bwd5::field_backward_mma_kernel<<<grid, bwd5::kThreadsB, bwd5::kSmemBytes, st>>>(
+        s, r, (const float4*)adjoint, partials, tiles_per_inst);
+    VSRD_CHECK_LAUNCH();
+    const dim3 rgrid((kGradStride + 127) / 128, (unsigned)s.N);
+    bwd5::reduce_segment_rows_kernel<<<rgrid, 128, 0, st>>>(partials, grid, tiles_per_inst, all_tiles, gloc, grot, gdim, gW);
+    VSRD_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // namespace vsrd

@@ -307,7 +307,12 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_forward_mma_kernel(
 }
 
 static int g_fwd_sms = 0;
-static int g_fwd_impl = -1;   // 0 = mma (default), 1 = simt
+
+// 0 = tensor-core kernel (default), 1 = SIMT cross-check (VSRD_FIELD_IMPL=simt, read per call)
+static int forward_impl() {
+    const char* impl = getenv("VSRD_FIELD_IMPL");
+    return (impl && strcmp(impl, "simt") == 0) ? 1 : 0;
+}
 
 static int forward_setup() {
     if (g_fwd_sms) return 0;
@@ -318,8 +323,6 @@ static int forward_setup() {
     if (cudaFuncSetAttribute(field_forward_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)kFwdSmemBytes) != cudaSuccess)
         return fail("vsrd_b200: cannot reserve %s of shared memory for field_forward_mma_kernel (built for sm_100a)", "217 KB");
-    const char* impl = getenv("VSRD_FIELD_IMPL");
-    g_fwd_impl = (impl && strcmp(impl, "simt") == 0) ? 1 : 0;
     g_fwd_sms = prop.multiProcessorCount;
     return 0;
 }
@@ -339,7 +342,7 @@ int vsrd_field_forward(const VsrdScene* scene, const VsrdRays* rays, float* fiel
     VSRD_CHECK_ARG(total < (size_t)1 << 31, "R*M must be < 2^31");
     if (forward_setup()) return 1;
     cudaStream_t st = (cudaStream_t)stream;
-    if (s.W && g_fwd_impl == 0) {
+    if (s.W && forward_impl() == 0) {
         const int tiles_per_inst = (int)((total + 31) / 32);
         const long long all_tiles = (long long)s.N * tiles_per_inst;
         const long long want = (all_tiles + kFwdWarps - 1) / kFwdWarps;

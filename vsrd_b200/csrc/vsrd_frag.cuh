@@ -69,6 +69,67 @@ __device__ __forceinline__ void a_from_c(const float (&c)[4], uint32_t (&ah)[4],
     split(c[3], ah[3], al[3]);
 }
 
+// ---- sample-contracted products (weight gradients) ---------------------------------------------
+// dW[o][i] = sum_samples hbar[s][o] g[s][i] contracts over the SAMPLE index, which the C layout keeps in
+// the 8-valued lane coordinate g while both MMA operands need the contracted index in the 4-valued
+// coordinate t.  movmatrix transposes an 8x8 tile of 16-bit pairs inside the register file, so the
+// operands are carried as bf16 hi + bf16 lo (16 mantissa bits, products hi*hi + hi*lo + lo*hi): one
+// m16n8k16 covers 16 samples.  Gradient tolerance is 1e-3; this keeps ~1e-5 per product.
+__device__ __forceinline__ uint32_t movmatrix_trans(uint32_t x) {
+    uint32_t y;
+    asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(y) : "r"(x));
+    return y;
+}
+
+// (x0, x1) -> packed bf16 pairs {lo half = x0, hi half = x1}: rounded value and rounded remainder.
+__device__ __forceinline__ void pack_bf16_split(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+    const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(x1 - h1), "f"(x0 - h0));
+}
+
+// Pair (x0, x1) = C-layout elements (sample g, channels 2t, 2t+1) of an 8x8 block -> transposed operand
+// register (samples 2t, 2t+1; channel g), hi and lo parts.
+__device__ __forceinline__ void pack_transposed(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    uint32_t h, l;
+    pack_bf16_split(x0, x1, h, l);
+    hi = movmatrix_trans(h);
+    lo = movmatrix_trans(l);
+}
+
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// A operand (16 outputs x 16 samples of one m-tile) of the weight-gradient product from the adjoint's
+// two C tiles c[nt][q] (nt = output half): rows = outputs, k = samples.
+__device__ __forceinline__ void wgrad_a_operand(const float (&c)[2][4], uint32_t (&ah)[4], uint32_t (&al)[4]) {
+    pack_transposed(c[0][0], c[0][1], ah[0], al[0]);   // outputs 0-7,  samples 0-7
+    pack_transposed(c[1][0], c[1][1], ah[1], al[1]);   // outputs 8-15, samples 0-7
+    pack_transposed(c[0][2], c[0][3], ah[2], al[2]);   // outputs 0-7,  samples 8-15
+    pack_transposed(c[1][2], c[1][3], ah[3], al[3]);   // outputs 8-15, samples 8-15
+}
+
+// D (16 outputs x 8 inputs) += A (adjoint) x B, B = one C tile (16 samples x 8 input channels).
+__device__ __forceinline__ void wgrad_tile(float (&D)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
+                                           float b0, float b1, float b2, float b3) {
+    uint32_t bh0, bl0, bh1, bl1;
+    pack_transposed(b0, b1, bh0, bl0);
+    pack_transposed(b2, b3, bh1, bl1);
+    mma_bf16(D, ah, bl0, bl1);
+    mma_bf16(D, al, bh0, bh1);
+    mma_bf16(D, ah, bh0, bh1);
+}
+
+// D += A x ones: every column holds the sum over the 16 samples (bias gradient).
+__device__ __forceinline__ void wgrad_bias(float (&D)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4]) {
+    constexpr uint32_t kOnes = 0x3f803f80u;
+    mma_bf16(D, al, kOnes, kOnes);
+    mma_bf16(D, ah, kOnes, kOnes);
+}
+
 // Reference weight layout (hyper_distance_field.py:57-73): layer l rows [out][fan_in + 1], bias last.
 __device__ __forceinline__ void stage_weight_fragments(const float* __restrict__ W, float4* sF, float* sTail) {
     for (int f = threadIdx.x; f < kFragFloat4; f += blockDim.x) {
