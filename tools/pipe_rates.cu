@@ -67,6 +67,22 @@ __global__ void rate_kernel(float* out, long long* cycles, int seedi) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) f[i] = fmaf(f[i], 1.0001f, 0.5f);
         }
+        if (MODE == 10 || MODE == 11) {       // packed fp32 pairs (Blackwell FFMA2): 16 independent chains
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) {
+                unsigned long long v, c1 = 0x3f8003473f800347ull, c2 = 0x3f0000003f000000ull;
+                asm volatile("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(f[i]), "f"(f[i + 1]));
+#pragma unroll
+                for (int r = 0; r < 8; ++r) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(v) : "l"(c1), "l"(c2));
+                asm volatile("mov.b64 {%0, %1}, %2;" : "=f"(f[i]), "=f"(f[i + 1]) : "l"(v));
+            }
+        }
+        if (MODE == 11) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int i = 0; i < 16; ++i) f[i] = fmaf(f[i], 1.0001f, 0.5f);
+        }
         if (MODE == 5) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(f[i]));
@@ -122,6 +138,8 @@ int main() {
     run<3>("shfl.xor", 8, out, cyc, sms);
     run<4>("ffma", 16, out, cyc, sms);
     run<5>("mufu.ex2", 8, out, cyc, sms);
+    run<10>("ffma2 (fma.rn.f32x2)", 64, out, cyc, sms);
+    run<11>("64 ffma2 + 64 ffma (all)", 128, out, cyc, sms);
     run<6>("tf32 mma + 8 ffma/mma (mma)", 8, out, cyc, sms);
     run<9>("tf32 mma + 16 ffma/mma (mma)", 8, out, cyc, sms);
     run<7>("bf16 mma + 8 ffma/mma (mma)", 8, out, cyc, sms);

@@ -1,5 +1,5 @@
 // sm_100a kernels of the VSRD silhouette-renderer hot path, part 1/3: ray generation, sample
-// placement and the warp-per-ray compositing kernels (forward and adjoint) + their C entry points.
+// placement and the CTA-per-ray compositing kernels (forward and adjoint) + their C entry points.
 // See include/vsrd_b200.h for the ABI and DESIGN.md for the kernel map and rooflines.
 #include "vsrd_common.cuh"
 
@@ -167,8 +167,12 @@ __global__ void __launch_bounds__(kThreads) place_fine_kernel(
 }
 
 // =============================================================================================
-// a8/a11: compositing forward.  One warp per ray; lane l owns samples l, l+32, ...
+// a8/a11: compositing forward.  One CTA per ray, one thread per sample: the per-sample work (soft union
+// over the instances, SDF -> opacity) is fully parallel, transmittance is a multiplicative scan over the
+// CTA (warp shuffles + one shared-memory hop), labels / loss terms are block reductions.
 // =============================================================================================
+constexpr int kMaxRayWarps = VSRD_MAX_INTERVALS / 32;    // 16 warps cover 512 intervals
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
@@ -182,6 +186,19 @@ __device__ __forceinline__ float warp_scan_mul(float v, int lane) {
     return v;
 }
 
+// Exclusive product of (1 - alpha) over all earlier samples of the ray (transmittance).
+__device__ __forceinline__ float block_transmittance(float alpha, int warp, int lane, int num_warps, float* s_tot) {
+    const float inc = warp_scan_mul(1.0f - alpha, lane);
+    float excl = __shfl_up_sync(kFull, inc, 1);
+    if (lane == 0) excl = 1.0f;
+    if (lane == 31) s_tot[warp] = inc;
+    __syncthreads();
+    float carry = 1.0f;
+    for (int w = 0; w < warp; ++w) carry *= s_tot[w];     // sequential like the per-ray cumprod
+    (void)num_warps;
+    return carry * excl;
+}
+
 struct LossDev {
     const float* targets;
     float sil_w;
@@ -189,195 +206,163 @@ struct LossDev {
 };
 
 template <int NMAX>
-__global__ void __launch_bounds__(kThreads) composite_forward_kernel(
+__global__ void __launch_bounds__(VSRD_MAX_INTERVALS) composite_forward_kernel(
         SceneDev scene, RaysDev rays, float sigma, float rho, float eps, const float4* __restrict__ field,
         float* __restrict__ labels, float* __restrict__ grads, float* __restrict__ weights,
         LossDev loss, float* __restrict__ loss_out) {
+    __shared__ float s_tot[kMaxRayWarps];
+    __shared__ float s_lab[kMaxRayWarps][NMAX + 1];     // per-warp label partials, [NMAX] = eikonal partial
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int r = blockIdx.x * kWarps + warp;
-    if (r >= rays.R) return;
+    const int num_warps = blockDim.x >> 5;
+    const int r = blockIdx.x;
     const int N = scene.N, M = rays.M;
     const size_t stride = (size_t)rays.R * M;
     const float T = scene.T;
-    const float dir[3] = {__ldg(rays.dirs + 3 * r), __ldg(rays.dirs + 3 * r + 1), __ldg(rays.dirs + 3 * r + 2)};
-    const float* trow = rays.dist + (size_t)r * (M + 1);
+    const int j = threadIdx.x;
+    const bool valid = j < M;
+    const size_t idx = (size_t)r * M + (valid ? j : 0);
+    auto load = [&](int i) { return ld4(field + (size_t)i * stride + idx); };
 
-    float lab[NMAX];
-#pragma unroll
-    for (int n = 0; n < NMAX; ++n) lab[n] = 0.0f;
-    float carry = 1.0f, eik = 0.0f;
-
-    for (int base = 0; base < M; base += 32) {
-        const int j = base + lane;
-        const bool valid = j < M;
-        const size_t idx = (size_t)r * M + (valid ? j : 0);
-        auto load = [&](int i) { return ld4(field + (size_t)i * stride + idx); };
-        UnionEval u;
-        OpacityEval o;
-        float alpha = 0.0f;
-        if (valid) {
-            union_forward(load, N, T, u);
-            const float delta = __ldg(trow + j + 1) - __ldg(trow + j);
-            opacity_forward(u, dir, delta, sigma, rho, eps, o);
-            alpha = o.alpha;
-        }
-        const float inc = warp_scan_mul(1.0f - alpha, lane);
-        float excl = __shfl_up_sync(kFull, inc, 1);
-        if (lane == 0) excl = 1.0f;
-        const float omega = carry * excl * alpha;
-        carry *= __shfl_sync(kFull, inc, 31);
-        if (valid) {
-            weights[idx] = omega;
-            grads[3 * idx] = u.g[0]; grads[3 * idx + 1] = u.g[1]; grads[3 * idx + 2] = u.g[2];
-            const float k = omega / u.Z;
-#pragma unroll
-            for (int n = 0; n < NMAX; ++n)
-                if (n < N) lab[n] += k * expf(-(load(n).x / T) - u.mneg);
-            const float e = o.gn - 1.0f;
-            eik += e * e;
-        }
+    UnionEval u;
+    OpacityEval o;
+    float alpha = 0.0f;
+    if (valid) {
+        const float dir[3] = {__ldg(rays.dirs + 3 * r), __ldg(rays.dirs + 3 * r + 1), __ldg(rays.dirs + 3 * r + 2)};
+        const float* trow = rays.dist + (size_t)r * (M + 1);
+        union_forward(load, N, T, u);
+        const float delta = __ldg(trow + j + 1) - __ldg(trow + j);
+        opacity_forward(u, dir, delta, sigma, rho, eps, o);
+        alpha = o.alpha;
     }
-    float mine = 0.0f;
+    const float omega = block_transmittance(alpha, warp, lane, num_warps, s_tot) * alpha;
+    float eik = 0.0f;
+    if (valid) {
+        weights[idx] = omega;
+        grads[3 * idx] = u.g[0]; grads[3 * idx + 1] = u.g[1]; grads[3 * idx + 2] = u.g[2];
+        const float e = o.gn - 1.0f;
+        eik = e * e;
+    }
+    const float k = valid ? omega / u.Z : 0.0f;
 #pragma unroll
     for (int n = 0; n < NMAX; ++n) {
         if (n < N) {
-            const float tot = warp_sum(lab[n]);
-            if (lane == n) mine = tot;
+            const float part = warp_sum(valid ? k * expf(-(load(n).x / T) - u.mneg) : 0.0f);
+            if (lane == 0) s_lab[warp][n] = part;
         }
     }
-    if (lane < N) labels[(size_t)r * N + lane] = mine;
-    if (loss.targets != nullptr && loss_out != nullptr) {
-        float bce = 0.0f;
+    eik = warp_sum(eik);
+    if (lane == 0) s_lab[warp][NMAX] = eik;
+    __syncthreads();
+    if (warp == 0) {
+        float mine = 0.0f;
         if (lane < N) {
-            const float y = __ldg(loss.targets + (size_t)r * N + lane);
-            const float l = fminf(fmaxf(mine, 1.0e-6f), 1.0f - 1.0e-6f);
-            bce = -(y * fmaxf(logf(l), -100.0f) + (1.0f - y) * fmaxf(logf(1.0f - l), -100.0f));
+            for (int w = 0; w < num_warps; ++w) mine += s_lab[w][lane];
+            labels[(size_t)r * N + lane] = mine;
         }
-        bce = warp_sum(bce);
-        eik = warp_sum(eik);
-        if (lane == 0) {
-            atomicAdd(loss_out, loss.sil_w * bce / ((float)rays.R * (float)N));
-            atomicAdd(loss_out + 1, loss.eik_w * eik / ((float)rays.R * (float)M));
+        if (loss.targets != nullptr && loss_out != nullptr) {
+            float bce = 0.0f;
+            if (lane < N) {
+                const float y = __ldg(loss.targets + (size_t)r * N + lane);
+                const float l = fminf(fmaxf(mine, 1.0e-6f), 1.0f - 1.0e-6f);
+                bce = -(y * fmaxf(logf(l), -100.0f) + (1.0f - y) * fmaxf(logf(1.0f - l), -100.0f));
+            }
+            bce = warp_sum(bce);
+            float e = lane < num_warps ? s_lab[lane][NMAX] : 0.0f;
+            e = warp_sum(e);
+            if (lane == 0) {
+                atomicAdd(loss_out, loss.sil_w * bce / ((float)rays.R * (float)N));
+                atomicAdd(loss_out + 1, loss.eik_w * e / ((float)rays.R * (float)M));
+            }
         }
     }
 }
 
 // =============================================================================================
-// compositing backward.  Same layout; MAXB = max 32-sample blocks per ray held in registers.
+// compositing backward.  Same layout: one CTA per ray, one thread per sample;
+// the forward quantities are recomputed once and stay in registers across the two block scans
+// (transmittance prefix product, suffix sum of a_k omega_k).
 // =============================================================================================
-template <int NMAX, int MAXB>
-__global__ void __launch_bounds__(kThreads) composite_backward_kernel(
+template <int NMAX>
+__global__ void __launch_bounds__(VSRD_MAX_INTERVALS) composite_backward_kernel(
         SceneDev scene, RaysDev rays, float sigma, float rho, float eps, const float4* __restrict__ field,
         const float* __restrict__ grad_labels, const float* __restrict__ grad_grads, const float* __restrict__ grad_weights,
         LossDev loss, const float* __restrict__ labels, float4* __restrict__ adjoint) {
+    __shared__ float s_tot[kMaxRayWarps];
+    __shared__ float s_suf[kMaxRayWarps];
+    __shared__ float s_gl[NMAX];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int r = blockIdx.x * kWarps + warp;
-    if (r >= rays.R) return;
+    const int num_warps = blockDim.x >> 5;
+    const int r = blockIdx.x;
     const int N = scene.N, M = rays.M;
     const size_t stride = (size_t)rays.R * M;
     const float T = scene.T;
-    const float dir[3] = {__ldg(rays.dirs + 3 * r), __ldg(rays.dirs + 3 * r + 1), __ldg(rays.dirs + 3 * r + 2)};
-    const float* trow = rays.dist + (size_t)r * (M + 1);
     const bool fused = loss.targets != nullptr;
     const float eik_scale = fused ? loss.eik_w * 2.0f / ((float)rays.R * (float)M) : 0.0f;
 
     // upstream gradient w.r.t. labels[r, :] (explicit + in-kernel BCE, main.py:653-671)
-    float gl[NMAX];
-#pragma unroll
-    for (int n = 0; n < NMAX; ++n) {
-        gl[n] = 0.0f;
+    if (threadIdx.x < NMAX) {
+        const int n = threadIdx.x;
+        float g = 0.0f;
         if (n < N) {
-            if (grad_labels) gl[n] = __ldg(grad_labels + (size_t)r * N + n);
+            if (grad_labels) g = __ldg(grad_labels + (size_t)r * N + n);
             if (fused) {
                 const float lraw = __ldg(labels + (size_t)r * N + n);
                 if (lraw >= 1.0e-6f && lraw <= 1.0f - 1.0e-6f) {   // clamp passes gradient inside the range
                     const float y = __ldg(loss.targets + (size_t)r * N + n);
-                    gl[n] += loss.sil_w * (lraw - y) / (lraw * (1.0f - lraw)) / ((float)rays.R * (float)N);
+                    g += loss.sil_w * (lraw - y) / (lraw * (1.0f - lraw)) / ((float)rays.R * (float)N);
                 }
             }
         }
+        s_gl[n] = g;
     }
+    __syncthreads();
 
-    float alpha[MAXB], trans[MAXB], aj[MAXB];
-    float carry = 1.0f;
-#pragma unroll
-    for (int b = 0; b < MAXB; ++b) {
-        alpha[b] = 0.0f; trans[b] = 1.0f; aj[b] = 0.0f;
-        const int base = b * 32;
-        if (base < M) {
-            const int j = base + lane;
-            const bool valid = j < M;
-            const size_t idx = (size_t)r * M + (valid ? j : 0);
-            auto load = [&](int i) { return ld4(field + (size_t)i * stride + idx); };
-            float a = 0.0f, al = 0.0f;
-            if (valid) {
-                UnionEval u;
-                OpacityEval o;
-                union_forward(load, N, T, u);
-                const float delta = __ldg(trow + j + 1) - __ldg(trow + j);
-                opacity_forward(u, dir, delta, sigma, rho, eps, o);
-                al = o.alpha;
-                if (grad_weights) a = __ldg(grad_weights + idx);
-#pragma unroll
-                for (int n = 0; n < NMAX; ++n)
-                    if (n < N) a += gl[n] * (expf(-(load(n).x / T) - u.mneg) / u.Z);
-            }
-            const float inc = warp_scan_mul(1.0f - al, lane);
-            float excl = __shfl_up_sync(kFull, inc, 1);
-            if (lane == 0) excl = 1.0f;
-            alpha[b] = al;
-            trans[b] = carry * excl;
-            aj[b] = a;
-            carry *= __shfl_sync(kFull, inc, 31);
-        }
+    const int j = threadIdx.x;
+    const bool valid = j < M;
+    const size_t idx = (size_t)r * M + (valid ? j : 0);
+    auto load = [&](int i) { return ld4(field + (size_t)i * stride + idx); };
+    const float dir[3] = {__ldg(rays.dirs + 3 * r), __ldg(rays.dirs + 3 * r + 1), __ldg(rays.dirs + 3 * r + 2)};
+    UnionEval u;
+    OpacityEval o;
+    float alpha = 0.0f, a = 0.0f, delta = 0.0f;
+    if (valid) {
+        const float* trow = rays.dist + (size_t)r * (M + 1);
+        union_forward(load, N, T, u);
+        delta = __ldg(trow + j + 1) - __ldg(trow + j);
+        opacity_forward(u, dir, delta, sigma, rho, eps, o);
+        alpha = o.alpha;
+        if (grad_weights) a = __ldg(grad_weights + idx);
+        for (int n = 0; n < N; ++n) a += s_gl[n] * (expf(-(load(n).x / T) - u.mneg) / u.Z);
     }
-
-    float suffix_carry = 0.0f;   // sum over later blocks of a_k * omega_k
+    const float trans = block_transmittance(alpha, warp, lane, num_warps, s_tot);
+    const float omega = trans * alpha;
+    // exclusive suffix sum over later samples of a_k * omega_k
+    const float v = a * omega;
+    float inc = v;
 #pragma unroll
-    for (int b = MAXB - 1; b >= 0; --b) {
-        const int base = b * 32;
-        if (base < M) {
-            const int j = base + lane;
-            const bool valid = j < M;
-            const size_t idx = (size_t)r * M + (valid ? j : 0);
-            const float omega = trans[b] * alpha[b];
-            const float v = aj[b] * omega;
-            float inc = v;   // inclusive suffix sum within the warp
+    for (int sh = 1; sh < 32; sh <<= 1) { const float n = __shfl_down_sync(kFull, inc, sh); if (lane + sh < 32) inc += n; }
+    if (lane == 0) s_suf[warp] = inc;
+    __syncthreads();
+    float suffix = inc - v;
+    for (int w = num_warps - 1; w > warp; --w) suffix += s_suf[w];
+    if (valid) {
+        const float alpha_bar = a * trans - suffix / (1.0f - alpha);
+        float dbar_adj, gbar[3];
+        opacity_backward(o, dir, delta, sigma, rho, eps, alpha_bar, dbar_adj, gbar);
+        if (grad_grads) {
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const float n = __shfl_down_sync(kFull, inc, o); if (lane + o < 32) inc += n; }
-            const float suffix = suffix_carry + (inc - v);
-            suffix_carry += __shfl_sync(kFull, inc, 0);
-            if (valid) {
-                auto load = [&](int i) { return ld4(field + (size_t)i * stride + idx); };
-                UnionEval u;
-                OpacityEval o;
-                union_forward(load, N, T, u);
-                const float delta = __ldg(trow + j + 1) - __ldg(trow + j);
-                opacity_forward(u, dir, delta, sigma, rho, eps, o);
-                const float alpha_bar = aj[b] * trans[b] - suffix / (1.0f - alpha[b]);
-                float dbar_adj, gbar[3];
-                opacity_backward(o, dir, delta, sigma, rho, eps, alpha_bar, dbar_adj, gbar);
-                if (grad_grads) {
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) gbar[c] += __ldg(grad_grads + 3 * idx + c);
-                }
-                if (fused && o.gn > 0.0f) {      // d/dg of eik_w * mean((|g| - 1)^2), main.py:679-687
-                    const float k = eik_scale * (o.gn - 1.0f) / o.gn;
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) gbar[c] += k * u.g[c];
-                }
-                auto wbar = [&](int i) {
-                    float g = 0.0f;
-#pragma unroll
-                    for (int n = 0; n < NMAX; ++n) if (n == i) g = gl[n];
-                    return omega * g;
-                };
-                auto store = [&](int i, const Vec4& a) {
-                    adjoint[(size_t)i * stride + idx] = make_float4(a.x, a.y, a.z, a.w);
-                };
-                union_backward(load, wbar, store, N, T, u, dbar_adj, gbar);
-            }
+            for (int c = 0; c < 3; ++c) gbar[c] += __ldg(grad_grads + 3 * idx + c);
         }
+        if (fused && o.gn > 0.0f) {      // d/dg of eik_w * mean((|g| - 1)^2), main.py:679-687
+            const float k = eik_scale * (o.gn - 1.0f) / o.gn;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) gbar[c] += k * u.g[c];
+        }
+        auto wbar = [&](int i) { return omega * s_gl[i]; };
+        auto store = [&](int i, const Vec4& q) {
+            adjoint[(size_t)i * stride + idx] = make_float4(q.x, q.y, q.z, q.w);
+        };
+        union_backward(load, wbar, store, N, T, u, dbar_adj, gbar);
     }
 }
 
@@ -465,9 +450,9 @@ int vsrd_composite_forward(const VsrdScene* scene, const VsrdRays* rays, const V
         VSRD_CHECK_ARG(loss_out != nullptr, "loss_out is NULL while loss targets are given");
         l = LossDev{loss->targets, loss->silhouette_weight, loss->eikonal_weight};
     }
-    const int grid = (r.R + kWarps - 1) / kWarps;
+    const int grid = r.R, block = 32 * ((r.M + 31) / 32);
     cudaStream_t st = (cudaStream_t)stream;
-#define VSRD_LAUNCH_CF(NMAX) composite_forward_kernel<NMAX><<<grid, kThreads, 0, st>>>( \
+#define VSRD_LAUNCH_CF(NMAX) composite_forward_kernel<NMAX><<<grid, block, 0, st>>>( \
         s, r, params->std_deviation, params->cosine_ratio, params->epsilon, (const float4*)field, labels, gradients, weights, l, loss_out)
     if (s.N <= 8) VSRD_LAUNCH_CF(8);
     else if (s.N <= 16) VSRD_LAUNCH_CF(16);
@@ -492,15 +477,14 @@ int vsrd_composite_backward(const VsrdScene* scene, const VsrdRays* rays, const 
         VSRD_CHECK_ARG(labels != nullptr, "labels (forward output) required for the in-kernel loss gradient");
         l = LossDev{loss->targets, loss->silhouette_weight, loss->eikonal_weight};
     }
-    const int grid = (r.R + kWarps - 1) / kWarps;
+    const int grid = r.R, block = 32 * ((r.M + 31) / 32);
     cudaStream_t st = (cudaStream_t)stream;
-#define VSRD_LAUNCH_CB(NMAX, MAXB) composite_backward_kernel<NMAX, MAXB><<<grid, kThreads, 0, st>>>( \
+#define VSRD_LAUNCH_CB(NMAX) composite_backward_kernel<NMAX><<<grid, block, 0, st>>>( \
         s, r, params->std_deviation, params->cosine_ratio, params->epsilon, (const float4*)field, \
         grad_labels, grad_gradients, grad_weights, l, labels, (float4*)adjoint)
-    const bool small = r.M <= 256;
-    if (s.N <= 8) { if (small) VSRD_LAUNCH_CB(8, 8); else VSRD_LAUNCH_CB(8, 16); }
-    else if (s.N <= 16) { if (small) VSRD_LAUNCH_CB(16, 8); else VSRD_LAUNCH_CB(16, 16); }
-    else { if (small) VSRD_LAUNCH_CB(32, 8); else VSRD_LAUNCH_CB(32, 16); }
+    if (s.N <= 8) VSRD_LAUNCH_CB(8);
+    else if (s.N <= 16) VSRD_LAUNCH_CB(16);
+    else VSRD_LAUNCH_CB(32);
 #undef VSRD_LAUNCH_CB
     VSRD_CHECK_LAUNCH();
     return 0;
