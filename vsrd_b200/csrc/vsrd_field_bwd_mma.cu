@@ -30,7 +30,7 @@ namespace bwd5 {
 
 constexpr int kWarpsB = 8;
 constexpr int kThreadsB = kWarpsB * 32;
-constexpr int kStashFloats = 3 * 32 * 32;     // per warp: layers 1..3 x [z 16 rows | zd 16 rows] x 32 lanes
+constexpr int kStashFloats = 3 * 32 * 32;     // per warp: layers 1..3 x [z 8 pair rows | zd 8 pair rows] x 32 lanes (float2)
 constexpr int kAccHidden = 0;                 // hidden layer l: fragments 3 (l-1) + {inputs 0-7, inputs 8-15, bias}
 constexpr int kAccL0 = 9;                     // layer 0: input tiles 0..5, bias
 constexpr int kAccLast = 16;                  // last layer: this lane's 4 channels
@@ -40,68 +40,61 @@ constexpr int kAccFloat4 = kAccFrags * 32;
 constexpr size_t kSmemBytes = frag::kWeightBytes
     + (size_t)kWarpsB * (kAccFloat4 * sizeof(float4) + kStashFloats * sizeof(float) + 32 * sizeof(float));
 
-__device__ __forceinline__ void slot_get(const float (&a)[2][2][4], int s, float (&v)[4]) {
-    const int mt = s >> 1, q = 2 * (s & 1);
-    v[0] = a[mt][0][q]; v[1] = a[mt][0][q + 1]; v[2] = a[mt][1][q]; v[3] = a[mt][1][q + 1];
-}
-__device__ __forceinline__ void slot_put(float (&a)[2][2][4], int s, const float (&v)[4]) {
-    const int mt = s >> 1, q = 2 * (s & 1);
-    a[mt][0][q] = v[0]; a[mt][0][q + 1] = v[1]; a[mt][1][q] = v[2]; a[mt][1][q + 1] = v[3];
+using frag::f2;
+using frag::bc;
+using frag::mul2;
+using frag::add2;
+using frag::fma2;
+using frag::hsum;
+
+// LayerNorm (no affine, eps 1e-5) of one row and of its tangent, on channel pairs.  In: p = h, d = hd
+// (this lane's 2 x 2 of the 16 channels).  Out: p = z, d = zd, rs = 1/sigma, mz = mean(z * centred tangent).
+__device__ __forceinline__ void ln_dual2(f2& p0, f2& p1, f2& d0, f2& d1, float& rs, float& mz) {
+    constexpr float inv = 1.0f / kHid;
+    const f2 m = frag::quad_sum2(make_float2(hsum(add2(p0, p1)), hsum(add2(d0, d1))));
+    const float nmean = m.x * -inv, nmt = m.y * -inv;
+    p0 = add2(p0, bc(nmean)); p1 = add2(p1, bc(nmean));
+    d0 = add2(d0, bc(nmt)); d1 = add2(d1, bc(nmt));
+    // (16 var, sum v d) in one packed reduction; z = v rs, so mean(z d) = rs * sum(v d) / 16
+    const f2 q = frag::quad_sum2(make_float2(hsum(fma2(p0, p0, mul2(p1, p1))), hsum(fma2(p0, d0, mul2(p1, d1)))));
+    rs = rsqrtf(fmaf(q.x, inv, kLnEps));
+    mz = rs * q.y * inv;
+    p0 = mul2(p0, bc(rs)); p1 = mul2(p1, bc(rs));
+    d0 = mul2(fma2(p0, bc(-mz), d0), bc(rs));
+    d1 = mul2(fma2(p1, bc(-mz), d1), bc(rs));
 }
 
-// LayerNorm (no affine, eps 1e-5) of one row and of its tangent.  In: v = h, d = hd (this lane's 4 of the
-// 16 channels).  Out: v = z, d = zd, rs = 1/sigma, mz = mean(z * centred tangent).
-__device__ __forceinline__ void ln_dual(float (&v)[4], float (&d)[4], float& rs, float& mz) {
-    constexpr float inv = 1.0f / kHid;
-    const float mean = frag::quad_sum((v[0] + v[1]) + (v[2] + v[3])) * inv;
-    const float mt = frag::quad_sum((d[0] + d[1]) + (d[2] + d[3])) * inv;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { v[k] -= mean; d[k] -= mt; }
-    const float var = frag::quad_sum(fmaf(v[0], v[0], v[1] * v[1]) + fmaf(v[2], v[2], v[3] * v[3])) * inv;
-    rs = rsqrtf(var + kLnEps);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) v[k] *= rs;
-    mz = frag::quad_sum(fmaf(v[0], d[0], v[1] * d[1]) + fmaf(v[2], d[2], v[3] * d[3])) * inv;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) d[k] = rs * (d[k] - v[k] * mz);
+// GELU value / first / second derivative factors of one channel pair.
+__device__ __forceinline__ void gelu_pair(f2 z, f2 zd, f2& g, f2& gd, f2& g1, f2& g2) {
+    f2 Phi, phi, zz;
+    frag::gelu_terms2(z, Phi, phi, zz);
+    g = mul2(z, Phi);
+    g1 = fma2(z, phi, Phi);
+    g2 = mul2(phi, fma2(zz, bc(-1.0f), bc(2.0f)));
+    gd = mul2(g1, zd);
 }
 
 // Adjoint of (LayerNorm -> GELU) and of its tangent for one row (vsrd_math.cuh::ln_gelu_reverse).
 // gb / gdb: adjoints of gelu(z) and of its tangent; out hb / hdb: adjoints of the LayerNorm input and
-// of its tangent.
-__device__ __forceinline__ void ln_gelu_reverse_row(const float (&z)[4], const float (&zd)[4], const float (&g1)[4],
-                                                    const float (&g2)[4], float rs, float m, const float (&gb)[4],
-                                                    const float (&gdb)[4], float (&hb)[4], float (&hdb)[4]) {
+// of its tangent.  [0] / [1]: the lane's two channel pairs.
+__device__ __forceinline__ void ln_gelu_reverse_row2(const f2 (&z)[2], const f2 (&zd)[2], const f2 (&g1)[2],
+                                                     const f2 (&g2)[2], float rs, float m, const f2 (&gb)[2],
+                                                     const f2 (&gdb)[2], f2 (&hb)[2], f2 (&hdb)[2]) {
     constexpr float inv = 1.0f / kHid;
-    float zb[4], zdb[4];
+    f2 zb[2], zdb[2];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        zdb[k] = gdb[k] * g1[k];
-        zb[k] = fmaf(gb[k], g1[k], gdb[k] * g2[k] * zd[k]);
+    for (int k = 0; k < 2; ++k) {
+        zdb[k] = mul2(gdb[k], g1[k]);
+        zb[k] = fma2(gb[k], g1[k], mul2(mul2(gdb[k], g2[k]), zd[k]));
     }
-    const float s_zb = frag::quad_sum((zb[0] + zb[1]) + (zb[2] + zb[3])) * inv;
-    const float s_zzb = frag::quad_sum(fmaf(z[0], zb[0], z[1] * zb[1]) + fmaf(z[2], zb[2], z[3] * zb[3])) * inv;
-    const float s_zdb = frag::quad_sum((zdb[0] + zdb[1]) + (zdb[2] + zdb[3])) * inv;
-    const float s_zzdb = frag::quad_sum(fmaf(z[0], zdb[0], z[1] * zdb[1]) + fmaf(z[2], zdb[2], z[3] * zdb[3])) * inv;
-    const float s_zdzdb = frag::quad_sum(fmaf(zd[0], zdb[0], zd[1] * zdb[1]) + fmaf(zd[2], zdb[2], zd[3] * zdb[3])) * inv;
+    const f2 sa = frag::quad_sum2(make_float2(hsum(add2(zb[0], zb[1])), hsum(fma2(z[0], zb[0], mul2(z[1], zb[1])))));
+    const f2 sb = frag::quad_sum2(make_float2(hsum(add2(zdb[0], zdb[1])), hsum(fma2(z[0], zdb[0], mul2(z[1], zdb[1])))));
+    const float sc = frag::quad_sum(hsum(fma2(zd[0], zdb[0], mul2(zd[1], zdb[1]))));
+    const float n_zb = sa.x * -inv, n_zz = (sa.y + sc) * -inv, n_zdb = sb.x * -inv, n_zzdb = sb.y * -inv;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        hdb[k] = rs * (zdb[k] - s_zdb - z[k] * s_zzdb);
-        hb[k] = rs * (zb[k] - s_zb - z[k] * (s_zzb + s_zdzdb) - m * hdb[k] - s_zzdb * zd[k]);
-    }
-}
-
-// GELU value / first / second derivative factors of one row.
-__device__ __forceinline__ void gelu_row(const float (&z)[4], const float (&zd)[4], float (&g)[4], float (&gd)[4],
-                                         float (&g1)[4], float (&g2)[4]) {
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        float Phi, phi;
-        frag::gelu_terms_fast(z[k], Phi, phi);
-        g[k] = z[k] * Phi;
-        g1[k] = fmaf(z[k], phi, Phi);
-        g2[k] = phi * (2.0f - z[k] * z[k]);
-        gd[k] = g1[k] * zd[k];
+    for (int k = 0; k < 2; ++k) {
+        hdb[k] = mul2(bc(rs), fma2(z[k], bc(n_zzdb), add2(zdb[k], bc(n_zdb))));
+        hb[k] = mul2(bc(rs), fma2(zd[k], bc(n_zzdb), fma2(hdb[k], bc(-m), fma2(z[k], bc(n_zz), add2(zb[k], bc(n_zb))))));
     }
 }
 
@@ -149,7 +142,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) field_backward_mma_kernel(
     const int t = lane & 3;
     const int quad_base = lane & ~3;
     float4* accL = sAcc + warp * kAccFloat4 + lane;         // accL[fragment * 32]
-    float* stash = sStash + warp * kStashFloats + lane;
+    float2* stash = reinterpret_cast<float2*>(sStash + warp * kStashFloats) + lane;
     const float4* fragL = sF + lane;
 
     const int total = rays.R * rays.M;
@@ -169,8 +162,8 @@ __global__ void __launch_bounds__(kThreadsB, 1) field_backward_mma_kernel(
         Instance I;
         load_instance(scene, inst, I);
         const float4* adj_inst = adjoint + (size_t)inst * total;
-        const float w4v[4] = {sTail[frag::kTailW4 + 2 * t], sTail[frag::kTailW4 + 2 * t + 1],
-                              sTail[frag::kTailW4 + 8 + 2 * t], sTail[frag::kTailW4 + 8 + 2 * t + 1]};
+        const f2 w4p0 = make_float2(sTail[frag::kTailW4 + 2 * t], sTail[frag::kTailW4 + 2 * t + 1]);
+        const f2 w4p1 = make_float2(sTail[frag::kTailW4 + 8 + 2 * t], sTail[frag::kTailW4 + 8 + 2 * t + 1]);
         const float b4 = sTail[frag::kTailB4];
 
 #pragma unroll 1
@@ -184,7 +177,8 @@ __global__ void __launch_bounds__(kThreadsB, 1) field_backward_mma_kernel(
             float4 adj = make_float4(0.0f, 0.0f, 0.0f, 0.0f);   // zero adjoints contribute exactly zero
             if (valid) adj = __ldg(adj_inst + idx);
             if (!__any_sync(kFull, adj.x != 0.0f || adj.y != 0.0f || adj.z != 0.0f || adj.w != 0.0f)) continue;
-            float arow[4][3], adrow[4][3], ddrow[4];
+            f2 arow[2][3], adrow[2][3];                    // pairs = rows (g, g + 8) of each m-tile
+            float ddrow[4];
             {
                 float x[3];
                 sample_position(rays, r, j, x);
@@ -197,27 +191,24 @@ __global__ void __launch_bounds__(kThreadsB, 1) field_backward_mma_kernel(
                     const float vc = I.R[c] * adj.y + I.R[3 + c] * adj.z + I.R[6 + c] * adj.w;
                     float v[4];
                     frag::lanes_to_rows(kPiF * (m[c] / scene.scale), lane, v);
-#pragma unroll
-                    for (int s = 0; s < 4; ++s) arow[s][c] = v[s];
+                    arow[0][c] = make_float2(v[0], v[1]);
+                    arow[1][c] = make_float2(v[2], v[3]);
                     frag::lanes_to_rows(coef[c] * vc, lane, v);
-#pragma unroll
-                    for (int s = 0; s < 4; ++s) adrow[s][c] = v[s];
+                    adrow[0][c] = make_float2(v[0], v[1]);
+                    adrow[1][c] = make_float2(v[2], v[3]);
                 }
                 frag::lanes_to_rows(adj.x, lane, ddrow);
             }
             // ------------------------------------------------------------ 2. dual forward sweep
-            frag::Encoding e;
-            frag::encode(arow, t, e);
+            frag::Encoding2 e;
+            frag::encode2(arow, t, e);
             const float f0 = (float)(1 << t), f1 = 16.0f * f0;
-            float h[2][2][4], hd[2][2][4];
+            f2 h[2][2][2], hd[2][2][2];                    // [m-tile][n-tile][row g | row g + 8]
 #pragma unroll
             for (int nt = 0; nt < 2; ++nt) {
-                const float b0 = sTail[8 * nt + 2 * t], b1 = sTail[8 * nt + 2 * t + 1];
+                const f2 bias = make_float2(sTail[8 * nt + 2 * t], sTail[8 * nt + 2 * t + 1]);
 #pragma unroll
-                for (int mt = 0; mt < 2; ++mt) {
-                    h[mt][nt][0] = b0; h[mt][nt][1] = b1; h[mt][nt][2] = b0; h[mt][nt][3] = b1;
-                    hd[mt][nt][0] = 0.0f; hd[mt][nt][1] = 0.0f; hd[mt][nt][2] = 0.0f; hd[mt][nt][3] = 0.0f;
-                }
+                for (int mt = 0; mt < 2; ++mt) { h[mt][nt][0] = bias; h[mt][nt][1] = bias; }
             }
 #pragma unroll
             for (int c = 0; c < 3; ++c)
@@ -228,56 +219,53 @@ __global__ void __launch_bounds__(kThreadsB, 1) field_backward_mma_kernel(
                     const float4 w0 = fragL[(frag::kF0 + 2 * ks) * 32], w1 = fragL[(frag::kF0 + 2 * ks + 1) * 32];
 #pragma unroll
                     for (int mt = 0; mt < 2; ++mt) {
-                        const float cs0 = e.cs[2 * mt][c][f], cs1 = e.cs[2 * mt + 1][c][f];
-                        const float sn0 = e.sn[2 * mt][c][f], sn1 = e.sn[2 * mt + 1][c][f];
-                        const float da0 = fk * adrow[2 * mt][c], da1 = fk * adrow[2 * mt + 1][c];
-                        uint32_t ah[4], al[4];
-                        frag::split(cs0, ah[0], al[0]);
-                        frag::split(cs1, ah[1], al[1]);
-                        frag::split(sn0, ah[2], al[2]);
-                        frag::split(sn1, ah[3], al[3]);
-                        frag::mma3(h[mt][0], ah, al, w0);
-                        frag::mma3(h[mt][1], ah, al, w1);
-                        frag::split(-da0 * sn0, ah[0], al[0]);
-                        frag::split(-da1 * sn1, ah[1], al[1]);
-                        frag::split(da0 * cs0, ah[2], al[2]);
-                        frag::split(da1 * cs1, ah[3], al[3]);
-                        frag::mma3(hd[mt][0], ah, al, w0);
-                        frag::mma3(hd[mt][1], ah, al, w1);
+                        const f2 cs = e.cs[mt][c][f], sn = e.sn[mt][c][f];
+                        uint32_t ah[4], al[4], adh[4], adl[4];
+                        frag::a_from_row_pairs(cs, sn, ah, al);
+                        const f2 da = mul2(adrow[mt][c], bc(fk));
+                        frag::a_from_row_pairs(mul2(mul2(da, bc(-1.0f)), sn), mul2(da, cs), adh, adl);
+                        if (ks == 0) {       // the value accumulators start from the bias, the tangent ones from zero
+                            frag::mma3(h[mt][0], ah, al, w0);
+                            frag::mma3_zero(hd[mt][0], adh, adl, w0);
+                            frag::mma3(h[mt][1], ah, al, w1);
+                            frag::mma3_zero(hd[mt][1], adh, adl, w1);
+                        } else {
+                            frag::mma3_quad<false>(h[mt][0], h[mt][1], hd[mt][0], hd[mt][1], ah, al, adh, adl, w0, w1);
+                        }
                     }
                 }
             // layers 1..3: LayerNorm -> GELU -> linear; lane t keeps 1/sigma and mz of layer t + 1
             float rreg[4] = {0.0f, 0.0f, 0.0f, 0.0f}, mreg[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll 1
             for (int l = 1; l <= 3; ++l) {
-                float* st = stash + (l - 1) * 32 * 32;
+                float2* st = stash + (l - 1) * 16 * 32;
 #pragma unroll
                 for (int s = 0; s < 4; ++s) {
-                    float v[4], d[4], rs, mz;
-                    slot_get(h, s, v);
-                    slot_get(hd, s, d);
-                    ln_dual(v, d, rs, mz);
+                    f2& p0 = h[s >> 1][0][s & 1];
+                    f2& p1 = h[s >> 1][1][s & 1];
+                    f2& d0 = hd[s >> 1][0][s & 1];
+                    f2& d1 = hd[s >> 1][1][s & 1];
+                    float rs, mz;
+                    ln_dual2(p0, p1, d0, d1, rs, mz);
                     if (t == l - 1) { rreg[s] = rs; mreg[s] = mz; }
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        float Phi, phi;
-                        frag::gelu_terms_fast(v[k], Phi, phi);
-                        st[(4 * s + k) * 32] = v[k];
-                        st[(16 + 4 * s + k) * 32] = d[k];
-                        d[k] *= fmaf(v[k], phi, Phi);
-                        v[k] *= Phi;
-                    }
-                    slot_put(h, s, v);
-                    slot_put(hd, s, d);
+                    st[(2 * s) * 32] = p0; st[(2 * s + 1) * 32] = p1;
+                    st[(8 + 2 * s) * 32] = d0; st[(8 + 2 * s + 1) * 32] = d1;
+                    f2 Phi, phi, zz;
+                    frag::gelu_terms2(p0, Phi, phi, zz);
+                    d0 = mul2(d0, fma2(p0, phi, Phi));
+                    p0 = mul2(p0, Phi);
+                    frag::gelu_terms2(p1, Phi, phi, zz);
+                    d1 = mul2(d1, fma2(p1, phi, Phi));
+                    p1 = mul2(p1, Phi);
                 }
-                float hn[2][2][4], hdn[2][2][4];
+                f2 hn[2][2][2], hdn[2][2][2];
 #pragma unroll
                 for (int nt = 0; nt < 2; ++nt) {
-                    const float b0 = sTail[16 * l + 8 * nt + 2 * t], b1 = sTail[16 * l + 8 * nt + 2 * t + 1];
+                    const f2 bias = make_float2(sTail[16 * l + 8 * nt + 2 * t], sTail[16 * l + 8 * nt + 2 * t + 1]);
 #pragma unroll
                     for (int mt = 0; mt < 2; ++mt) {
-                        hn[mt][nt][0] = b0; hn[mt][nt][1] = b1; hn[mt][nt][2] = b0; hn[mt][nt][3] = b1;
-                        hdn[mt][nt][0] = 0.0f; hdn[mt][nt][1] = 0.0f; hdn[mt][nt][2] = 0.0f; hdn[mt][nt][3] = 0.0f;
+                        hn[mt][nt][0] = bias; hn[mt][nt][1] = bias;
+                        hdn[mt][nt][0] = bc(0.0f); hdn[mt][nt][1] = bc(0.0f);
                     }
                 }
                 const float4* fl = fragL + (frag::kF1 + 4 * (l - 1)) * 32;
@@ -286,13 +274,10 @@ __global__ void __launch_bounds__(kThreadsB, 1) field_backward_mma_kernel(
                     const float4 w0 = fl[(2 * ks) * 32], w1 = fl[(2 * ks + 1) * 32];
 #pragma unroll
                     for (int mt = 0; mt < 2; ++mt) {
-                        uint32_t ah[4], al[4];
+                        uint32_t ah[4], al[4], adh[4], adl[4];
                         frag::a_from_c(h[mt][ks], ah, al);
-                        frag::mma3(hn[mt][0], ah, al, w0);
-                        frag::mma3(hn[mt][1], ah, al, w1);
-                        frag::a_from_c(hd[mt][ks], ah, al);
-                        frag::mma3(hdn[mt][0], ah, al, w0);
-                        frag::mma3(hdn[mt][1], ah, al, w1);
+                        frag::a_from_c(hd[mt][ks], adh, adl);
+                        frag::mma3_quad<false>(hn[mt][0], hn[mt][1], hdn[mt][0], hdn[mt][1], ah, al, adh, adl, w0, w1);
                     }
                 }
 #pragma unroll
@@ -300,43 +285,43 @@ __global__ void __launch_bounds__(kThreadsB, 1) field_backward_mma_kernel(
 #pragma unroll
                     for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) { h[mt][nt][q] = hn[mt][nt][q]; hd[mt][nt][q] = hdn[mt][nt][q]; }
+                        for (int q = 0; q < 2; ++q) { h[mt][nt][q] = hn[mt][nt][q]; hd[mt][nt][q] = hdn[mt][nt][q]; }
             }
             // ------------------------------------------------------------ 3. reverse sweep
             // layer 4 (16 -> 1), LayerNorm outputs stay in registers; hb / hdb: adjoints of the output of
             // linear layer 3 and of its tangent (C layout)
-            float hb[2][2][4], hdb[2][2][4];
+            f2 hb[2][2][2], hdb[2][2][2];
             {
-                float4 last = accL[kAccLast * 32];
+                const float4 last4 = accL[kAccLast * 32];
+                f2 last0 = make_float2(last4.x, last4.y), last1 = make_float2(last4.z, last4.w);
                 float obsum = 0.0f;
 #pragma unroll
                 for (int s = 0; s < 4; ++s) {
-                    float z[4], zd[4], rs, mz, g[4], gd[4], g1[4], g2[4];
-                    slot_get(h, s, z);
-                    slot_get(hd, s, zd);
-                    ln_dual(z, zd, rs, mz);
-                    gelu_row(z, zd, g, gd, g1, g2);
-                    float po = fmaf(w4v[0], g[0], w4v[1] * g[1]) + fmaf(w4v[2], g[2], w4v[3] * g[3]);
-                    float pod = fmaf(w4v[0], gd[0], w4v[1] * gd[1]) + fmaf(w4v[2], gd[2], w4v[3] * gd[3]);
-                    const float out = frag::quad_sum(po) + b4;
-                    const float outd = frag::quad_sum(pod);
+                    f2 z[2] = {h[s >> 1][0][s & 1], h[s >> 1][1][s & 1]};
+                    f2 zd[2] = {hd[s >> 1][0][s & 1], hd[s >> 1][1][s & 1]};
+                    float rs, mz;
+                    ln_dual2(z[0], z[1], zd[0], zd[1], rs, mz);
+                    f2 g[2], gd[2], g1[2], g2[2];
+                    gelu_pair(z[0], zd[0], g[0], gd[0], g1[0], g2[0]);
+                    gelu_pair(z[1], zd[1], g[1], gd[1], g1[1], g2[1]);
+                    const f2 oo = frag::quad_sum2(make_float2(hsum(fma2(w4p0, g[0], mul2(w4p1, g[1]))),
+                                                              hsum(fma2(w4p0, gd[0], mul2(w4p1, gd[1])))));
+                    const float out = oo.x + b4, outd = oo.y;
                     const float res = sigmoidf_(out - 1.0f);
                     const float sp = res * (1.0f - res);
                     const float obar = fmaf(ddrow[s], sp, sp * (1.0f - 2.0f * res) * outd);
                     const float odbar = sp;
                     obsum += obar;
-                    last.x += fmaf(obar, g[0], odbar * gd[0]);
-                    last.y += fmaf(obar, g[1], odbar * gd[1]);
-                    last.z += fmaf(obar, g[2], odbar * gd[2]);
-                    last.w += fmaf(obar, g[3], odbar * gd[3]);
-                    float gb[4], gdb[4], hbv[4], hdbv[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) { gb[k] = w4v[k] * obar; gdb[k] = w4v[k] * odbar; }
-                    ln_gelu_reverse_row(z, zd, g1, g2, rs, mz, gb, gdb, hbv, hdbv);
-                    slot_put(hb, s, hbv);
-                    slot_put(hdb, s, hdbv);
+                    last0 = fma2(bc(obar), g[0], fma2(bc(odbar), gd[0], last0));
+                    last1 = fma2(bc(obar), g[1], fma2(bc(odbar), gd[1], last1));
+                    const f2 gb[2] = {mul2(w4p0, bc(obar)), mul2(w4p1, bc(obar))};
+                    const f2 gdb[2] = {mul2(w4p0, bc(odbar)), mul2(w4p1, bc(odbar))};
+                    f2 hbv[2], hdbv[2];
+                    ln_gelu_reverse_row2(z, zd, g1, g2, rs, mz, gb, gdb, hbv, hdbv);
+                    hb[s >> 1][0][s & 1] = hbv[0]; hb[s >> 1][1][s & 1] = hbv[1];
+                    hdb[s >> 1][0][s & 1] = hdbv[0]; hdb[s >> 1][1][s & 1] = hdbv[1];
                 }
-                accL[kAccLast * 32] = last;
+                accL[kAccLast * 32] = make_float4(last0.x, last0.y, last1.x, last1.y);
                 float4 p0 = accL[kAccPose * 32];
                 p0.x += obsum;
                 accL[kAccPose * 32] = p0;
@@ -344,13 +329,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) field_backward_mma_kernel(
 #pragma unroll 1
             for (int l = 3; l >= 1; --l) {
                 // adjoints of gelu(z_l) and its tangent: W_l^T hb, W_l^T hdb
-                float gb[2][2][4], gdb[2][2][4];
-#pragma unroll
-                for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-                    for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) { gb[mt][nt][q] = 0.0f; gdb[mt][nt][q] = 0.0f; }
+                f2 gb[2][2][2], gdb[2][2][2];
                 {
                     const float4* fl = fragL + (frag::kR1 + 4 * (l - 1)) * 32;
 #pragma unroll
@@ -358,44 +337,43 @@ __global__ void __launch_bounds__(kThreadsB, 1) field_backward_mma_kernel(
                         const float4 w0 = fl[(2 * ks) * 32], w1 = fl[(2 * ks + 1) * 32];
 #pragma unroll
                         for (int mt = 0; mt < 2; ++mt) {
-                            uint32_t ah[4], al[4];
+                            uint32_t ah[4], al[4], adh[4], adl[4];
                             frag::a_from_c(hb[mt][ks], ah, al);
-                            frag::mma3(gb[mt][0], ah, al, w0);
-                            frag::mma3(gb[mt][1], ah, al, w1);
-                            frag::a_from_c(hdb[mt][ks], ah, al);
-                            frag::mma3(gdb[mt][0], ah, al, w0);
-                            frag::mma3(gdb[mt][1], ah, al, w1);
+                            frag::a_from_c(hdb[mt][ks], adh, adl);
+                            if (ks == 0) frag::mma3_quad<true>(gb[mt][0], gb[mt][1], gdb[mt][0], gdb[mt][1], ah, al, adh, adl, w0, w1);
+                            else frag::mma3_quad<false>(gb[mt][0], gb[mt][1], gdb[mt][0], gdb[mt][1], ah, al, adh, adl, w0, w1);
                         }
                     }
                 }
                 float4* accW = accL + (kAccHidden + 3 * (l - 1)) * 32;
-                float D[3][4];
+                f2 D[3][2];
 #pragma unroll
                 for (int n = 0; n < 3; ++n) {
                     const float4 a = accW[n * 32];
-                    D[n][0] = a.x; D[n][1] = a.y; D[n][2] = a.z; D[n][3] = a.w;
+                    D[n][0] = make_float2(a.x, a.y); D[n][1] = make_float2(a.z, a.w);
                 }
-                const float* st = stash + (l - 1) * 32 * 32;
+                const float2* st = stash + (l - 1) * 16 * 32;
 #pragma unroll
                 for (int mt = 0; mt < 2; ++mt) {
-                    float z[2][4], zd[2][4], g[2][4], gd[2][4], g1[2][4], g2[2][4];
+                    f2 z[2][2], zd[2][2], g[2][2], gd[2][2], g1[2][2], g2[2][2];      // [row half][channel pair]
 #pragma unroll
                     for (int hf = 0; hf < 2; ++hf) {
                         const int s = 2 * mt + hf;
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) { z[hf][k] = st[(4 * s + k) * 32]; zd[hf][k] = st[(16 + 4 * s + k) * 32]; }
-                        gelu_row(z[hf], zd[hf], g[hf], gd[hf], g1[hf], g2[hf]);
+                        z[hf][0] = st[(2 * s) * 32]; z[hf][1] = st[(2 * s + 1) * 32];
+                        zd[hf][0] = st[(8 + 2 * s) * 32]; zd[hf][1] = st[(8 + 2 * s + 1) * 32];
+                        gelu_pair(z[hf][0], zd[hf][0], g[hf][0], gd[hf][0], g1[hf][0], g2[hf][0]);
+                        gelu_pair(z[hf][1], zd[hf][1], g[hf][1], gd[hf][1], g1[hf][1], g2[hf][1]);
                     }
                     // weight gradient of linear layer l over the 16 samples of this m-tile
                     {
                         uint32_t ah[4], al[4];
                         frag::wgrad_a_operand(hb[mt], ah, al);
-                        frag::wgrad_tile(D[0], ah, al, g[0][0], g[0][1], g[1][0], g[1][1]);
-                        frag::wgrad_tile(D[1], ah, al, g[0][2], g[0][3], g[1][2], g[1][3]);
+                        frag::wgrad_tile(D[0], ah, al, g[0][0], g[1][0]);
+                        frag::wgrad_tile(D[1], ah, al, g[0][1], g[1][1]);
                         frag::wgrad_bias(D[2], ah, al);
                         frag::wgrad_a_operand(hdb[mt], ah, al);
-                        frag::wgrad_tile(D[0], ah, al, gd[0][0], gd[0][1], gd[1][0], gd[1][1]);
-                        frag::wgrad_tile(D[1], ah, al, gd[0][2], gd[0][3], gd[1][2], gd[1][3]);
+                        frag::wgrad_tile(D[0], ah, al, gd[0][0], gd[1][0]);
+                        frag::wgrad_tile(D[1], ah, al, gd[0][1], gd[1][1]);
                     }
                     // LayerNorm / GELU adjoint: hb, hdb <- adjoints of the output of linear layer l - 1
 #pragma unroll
@@ -403,27 +381,27 @@ __global__ void __launch_bounds__(kThreadsB, 1) field_backward_mma_kernel(
                         const int s = 2 * mt + hf;
                         const float rs = __shfl_sync(kFull, rreg[s], quad_base | (l - 1));
                         const float mz = __shfl_sync(kFull, mreg[s], quad_base | (l - 1));
-                        float gbv[4], gdbv[4], hbv[4], hdbv[4];
-                        slot_get(gb, s, gbv);
-                        slot_get(gdb, s, gdbv);
-                        ln_gelu_reverse_row(z[hf], zd[hf], g1[hf], g2[hf], rs, mz, gbv, gdbv, hbv, hdbv);
-                        slot_put(hb, s, hbv);
-                        slot_put(hdb, s, hdbv);
+                        const f2 gbv[2] = {gb[mt][0][hf], gb[mt][1][hf]};
+                        const f2 gdbv[2] = {gdb[mt][0][hf], gdb[mt][1][hf]};
+                        f2 hbv[2], hdbv[2];
+                        ln_gelu_reverse_row2(z[hf], zd[hf], g1[hf], g2[hf], rs, mz, gbv, gdbv, hbv, hdbv);
+                        hb[mt][0][hf] = hbv[0]; hb[mt][1][hf] = hbv[1];
+                        hdb[mt][0][hf] = hdbv[0]; hdb[mt][1][hf] = hdbv[1];
                     }
                 }
 #pragma unroll
-                for (int n = 0; n < 3; ++n) accW[n * 32] = make_float4(D[n][0], D[n][1], D[n][2], D[n][3]);
+                for (int n = 0; n < 3; ++n) accW[n * 32] = make_float4(D[n][0].x, D[n][0].y, D[n][1].x, D[n][1].y);
             }
             // layer 0: weight gradient against the encoding and its tangent, then the encoding adjoint
             //   abar_c  = sum_k 2^k (ebar_sin cos - ebar_cos sin - da (edbar_cos cos + edbar_sin sin))
             //   adbar_c = sum_k 2^k (edbar_sin cos - edbar_cos sin)
             float abar[4][3], adbar[4][3];
             {
-                float D0[7][4];
+                f2 D0[7][2];
 #pragma unroll
                 for (int n = 0; n < 7; ++n) {
                     const float4 a = accL[(kAccL0 + n) * 32];
-                    D0[n][0] = a.x; D0[n][1] = a.y; D0[n][2] = a.z; D0[n][3] = a.w;
+                    D0[n][0] = make_float2(a.x, a.y); D0[n][1] = make_float2(a.z, a.w);
                 }
 #pragma unroll
                 for (int mt = 0; mt < 2; ++mt) {
@@ -438,11 +416,11 @@ __global__ void __launch_bounds__(kThreadsB, 1) field_backward_mma_kernel(
 #pragma unroll
                             for (int f = 0; f < 2; ++f) {
                                 const float fk = f ? f1 : f0;
-                                const float cs0 = e.cs[s0][c][f], cs1 = e.cs[s1][c][f];
-                                const float sn0 = e.sn[s0][c][f], sn1 = e.sn[s1][c][f];
-                                const float da0 = fk * adrow[s0][c], da1 = fk * adrow[s1][c];
-                                frag::wgrad_tile(D0[2 * c + f], ah, al, cs0, sn0, cs1, sn1);
-                                frag::wgrad_tile(D0[2 * c + f], adh, adl, -da0 * sn0, da0 * cs0, -da1 * sn1, da1 * cs1);
+                                const f2 cs = e.cs[mt][c][f], sn = e.sn[mt][c][f];
+                                const f2 da = mul2(adrow[mt][c], bc(fk));
+                                const f2 dcs = mul2(mul2(da, bc(-1.0f)), sn), dsn = mul2(da, cs);   // tangents of (cos, sin)
+                                frag::wgrad_tile_scalar(D0[2 * c + f], ah, al, cs.x, sn.x, cs.y, sn.y);
+                                frag::wgrad_tile_scalar(D0[2 * c + f], adh, adl, dcs.x, dsn.x, dcs.y, dsn.y);
                             }
                     }
                     uint32_t ah[2][4], al[2][4], adh[2][4], adl[2][4];
@@ -454,32 +432,30 @@ __global__ void __launch_bounds__(kThreadsB, 1) field_backward_mma_kernel(
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
                         float acc0 = 0.0f, acc1 = 0.0f, accd0 = 0.0f, accd1 = 0.0f;
+                        f2 eb[2][2], edb[2][2];                 // [octave half f]: (cos, sin) adjoints of rows g, g + 8
+                        frag::mma3_quad<true>(eb[0], eb[1], edb[0], edb[1], ah[0], al[0], adh[0], adl[0],
+                                              fragL[(frag::kR0 + 2 * c) * 32], fragL[(frag::kR0 + 2 * c + 1) * 32]);
+                        frag::mma3_quad<false>(eb[0], eb[1], edb[0], edb[1], ah[1], al[1], adh[1], adl[1],
+                                               fragL[(frag::kR0 + 6 + 2 * c) * 32], fragL[(frag::kR0 + 6 + 2 * c + 1) * 32]);
 #pragma unroll
                         for (int f = 0; f < 2; ++f) {
-                            const int nt = 2 * c + f;
                             const float fk = f ? f1 : f0;
-                            const float4 w0 = fragL[(frag::kR0 + nt) * 32], w1 = fragL[(frag::kR0 + 6 + nt) * 32];
-                            float eb[4] = {0.0f, 0.0f, 0.0f, 0.0f}, edb[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-                            frag::mma3(eb, ah[0], al[0], w0);
-                            frag::mma3(eb, ah[1], al[1], w1);
-                            frag::mma3(edb, adh[0], adl[0], w0);
-                            frag::mma3(edb, adh[1], adl[1], w1);
-                            const float cs0 = e.cs[s0][c][f], cs1 = e.cs[s1][c][f];
-                            const float sn0 = e.sn[s0][c][f], sn1 = e.sn[s1][c][f];
-                            const float da0 = fk * adrow[s0][c], da1 = fk * adrow[s1][c];
-                            acc0 += fk * (eb[1] * cs0 - eb[0] * sn0 - da0 * (edb[0] * cs0 + edb[1] * sn0));
-                            accd0 += fk * (edb[1] * cs0 - edb[0] * sn0);
-                            acc1 += fk * (eb[3] * cs1 - eb[2] * sn1 - da1 * (edb[2] * cs1 + edb[3] * sn1));
-                            accd1 += fk * (edb[3] * cs1 - edb[2] * sn1);
+                            const f2 cs = e.cs[mt][c][f], sn = e.sn[mt][c][f];
+                            const f2 da = mul2(adrow[mt][c], bc(fk));
+                            acc0 += fk * (eb[f][0].y * cs.x - eb[f][0].x * sn.x - da.x * (edb[f][0].x * cs.x + edb[f][0].y * sn.x));
+                            accd0 += fk * (edb[f][0].y * cs.x - edb[f][0].x * sn.x);
+                            acc1 += fk * (eb[f][1].y * cs.y - eb[f][1].x * sn.y - da.y * (edb[f][1].x * cs.y + edb[f][1].y * sn.y));
+                            accd1 += fk * (edb[f][1].y * cs.y - edb[f][1].x * sn.y);
                         }
-                        abar[s0][c] = frag::quad_sum(acc0);
-                        abar[s1][c] = frag::quad_sum(acc1);
-                        adbar[s0][c] = frag::quad_sum(accd0);
-                        adbar[s1][c] = frag::quad_sum(accd1);
+                        const f2 qa = frag::quad_sum2(make_float2(acc0, acc1));
+                        const f2 qd = frag::quad_sum2(make_float2(accd0, accd1));
+                        abar[s0][c] = qa.x; abar[s1][c] = qa.y;
+                        adbar[s0][c] = qd.x; adbar[s1][c] = qd.y;
                     }
                 }
 #pragma unroll
-                for (int n = 0; n < 7; ++n) accL[(kAccL0 + n) * 32] = make_float4(D0[n][0], D0[n][1], D0[n][2], D0[n][3]);
+                for (int n = 0; n < 7; ++n)
+                    accL[(kAccL0 + n) * 32] = make_float4(D0[n][0].x, D0[n][0].y, D0[n][1].x, D0[n][1].y);
             }
             // ------------------------------------------------------------ 4. lane == sample: pose
             {

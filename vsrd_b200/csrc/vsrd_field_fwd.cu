@@ -53,17 +53,18 @@ __global__ void __launch_bounds__(kThreads) field_forward_kernel(SceneDev scene,
 // =============================================================================================
 constexpr int kFwdWarps = 12;
 constexpr int kFwdThreads = kFwdWarps * 32;
-constexpr int kFwdStashFloats = 4 * 32 * 32;     // per warp: [layer][z 16 | g1/sigma 16][lane]
-constexpr size_t kFwdSmemBytes = frag::kWeightBytes + (size_t)kFwdWarps * kFwdStashFloats * sizeof(float);
+constexpr int kFwdStashPairs = 4 * 16 * 32;      // per warp, float2: [layer][z pairs 8 | g1/sigma pairs 8][lane]
+constexpr size_t kFwdSmemBytes = frag::kWeightBytes + (size_t)kFwdWarps * kFwdStashPairs * sizeof(float2);
 
 __global__ void __launch_bounds__(kFwdThreads, 1) field_forward_mma_kernel(
         SceneDev scene, RaysDev rays, float4* __restrict__ field, int tiles_per_inst) {
+    using namespace frag;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4* sF = reinterpret_cast<float4*>(smem_raw);
-    float* sTail = reinterpret_cast<float*>(sF + frag::kFragFloat4);
+    float* sTail = reinterpret_cast<float*>(sF + kFragFloat4);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int t = lane & 3;
-    float* stash = sTail + frag::kTailFloats + (size_t)warp * kFwdStashFloats + lane;
+    float2* stash = reinterpret_cast<float2*>(sTail + kTailFloats) + (size_t)warp * kFwdStashPairs + lane;
     const float4* fragL = sF + lane;
 
     const int total = rays.R * rays.M;
@@ -75,11 +76,14 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_forward_mma_kernel(
         const int inst = (int)(seg / tiles_per_inst);
         const long long seg_end = min(end, (long long)(inst + 1) * tiles_per_inst);
         __syncthreads();                                   // previous instance's tiles are done
-        frag::stage_weight_fragments(scene.W + (size_t)inst * kNumW, sF, sTail);
+        stage_weight_fragments(scene.W + (size_t)inst * kNumW, sF, sTail);
         __syncthreads();
         Instance I;
         load_instance(scene, inst, I);
         const float pi_scale = kPiF / scene.scale;
+        const f2 w4p0 = make_float2(sTail[kTailW4 + 2 * t], sTail[kTailW4 + 2 * t + 1]);
+        const f2 w4p1 = make_float2(sTail[kTailW4 + 8 + 2 * t], sTail[kTailW4 + 8 + 2 * t + 1]);
+        const float b4 = sTail[kTailB4];
 
 #pragma unroll 1
         for (long long tile = seg + warp; tile < seg_end; tile += kFwdWarps) {
@@ -92,201 +96,168 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_forward_mma_kernel(
             sample_position(rays, r, j, x);
             BoxEval b;
             box_eval(x, I, b);
-            float arow[4][3];
+            f2 arow[2][3];                                 // PE arguments of rows (g, g + 8) of each m-tile
             {
                 const float m[3] = {fabsf(b.p[0]), b.p[1], b.p[2]};
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     float v[4];
-                    frag::lanes_to_rows(kPiF * (m[c] / scene.scale), lane, v);
-#pragma unroll
-                    for (int s = 0; s < 4; ++s) arow[s][c] = v[s];
+                    lanes_to_rows(kPiF * (m[c] / scene.scale), lane, v);
+                    arow[0][c] = make_float2(v[0], v[1]);
+                    arow[1][c] = make_float2(v[2], v[3]);
                 }
             }
             // ------------------------------------------------------------ 2. forward sweep
-            frag::Encoding e;
-            frag::encode(arow, t, e);
-            float h[2][2][4];
+            Encoding2 e;
+            encode2(arow, t, e);
+            f2 h[2][2][2];                                 // [m-tile][n-tile][row g | row g + 8]
 #pragma unroll
             for (int nt = 0; nt < 2; ++nt) {
-                const float b0 = sTail[8 * nt + 2 * t], b1 = sTail[8 * nt + 2 * t + 1];
+                const f2 bias = make_float2(sTail[8 * nt + 2 * t], sTail[8 * nt + 2 * t + 1]);
 #pragma unroll
-                for (int mt = 0; mt < 2; ++mt) { h[mt][nt][0] = b0; h[mt][nt][1] = b1; h[mt][nt][2] = b0; h[mt][nt][3] = b1; }
+                for (int mt = 0; mt < 2; ++mt) { h[mt][nt][0] = bias; h[mt][nt][1] = bias; }
             }
 #pragma unroll
             for (int c = 0; c < 3; ++c)
 #pragma unroll
                 for (int f = 0; f < 2; ++f) {
                     const int ks = 2 * c + f;
-                    const float4 w0 = fragL[(frag::kF0 + 2 * ks) * 32], w1 = fragL[(frag::kF0 + 2 * ks + 1) * 32];
-#pragma unroll
-                    for (int mt = 0; mt < 2; ++mt) {
-                        uint32_t ah[4], al[4];
-                        frag::split(e.cs[2 * mt][c][f], ah[0], al[0]);
-                        frag::split(e.cs[2 * mt + 1][c][f], ah[1], al[1]);
-                        frag::split(e.sn[2 * mt][c][f], ah[2], al[2]);
-                        frag::split(e.sn[2 * mt + 1][c][f], ah[3], al[3]);
-                        frag::mma3(h[mt][0], ah, al, w0);
-                        frag::mma3(h[mt][1], ah, al, w1);
-                    }
+                    const float4 w0 = fragL[(kF0 + 2 * ks) * 32], w1 = fragL[(kF0 + 2 * ks + 1) * 32];
+                    uint32_t ah[2][4], al[2][4];
+                    a_from_row_pairs(e.cs[0][c][f], e.sn[0][c][f], ah[0], al[0]);
+                    a_from_row_pairs(e.cs[1][c][f], e.sn[1][c][f], ah[1], al[1]);
+                    mma3_quad<false>(h[0][0], h[0][1], h[1][0], h[1][1], ah[0], al[0], ah[1], al[1], w0, w1);
                 }
             float out[4];
 #pragma unroll 1
             for (int l = 1; l <= 4; ++l) {
-                float* st = stash + (l - 1) * 32 * 32;
-                // LayerNorm (no affine, eps 1e-5) + GELU per row slot
+                float2* st = stash + (l - 1) * 16 * 32;
+                // LayerNorm (no affine, eps 1e-5) + GELU per row slot (slot s = 2 mt + half)
 #pragma unroll
                 for (int s = 0; s < 4; ++s) {
-                    const int mt = s >> 1, q = 2 * (s & 1);
-                    float v0 = h[mt][0][q], v1 = h[mt][0][q + 1], v2 = h[mt][1][q], v3 = h[mt][1][q + 1];
-                    const float mean = frag::quad_sum((v0 + v1) + (v2 + v3)) * (1.0f / kHid);
-                    v0 -= mean; v1 -= mean; v2 -= mean; v3 -= mean;
-                    const float var = frag::quad_sum(fmaf(v0, v0, v1 * v1) + fmaf(v2, v2, v3 * v3)) * (1.0f / kHid);
+                    f2& p0 = h[s >> 1][0][s & 1];
+                    f2& p1 = h[s >> 1][1][s & 1];
+                    const float mean = quad_sum(hsum(add2(p0, p1))) * (1.0f / kHid);
+                    p0 = add2(p0, bc(-mean)); p1 = add2(p1, bc(-mean));
+                    const float var = quad_sum(hsum(fma2(p0, p0, mul2(p1, p1)))) * (1.0f / kHid);
                     const float rs = rsqrtf(var + kLnEps);
-                    float z[4] = {v0 * rs, v1 * rs, v2 * rs, v3 * rs};
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        float Phi, phi;
-                        frag::gelu_terms_fast(z[k], Phi, phi);
-                        st[(4 * s + k) * 32] = z[k];
-                        st[(16 + 4 * s + k) * 32] = fmaf(z[k], phi, Phi) * rs;      // gelu'(z) / sigma
-                        z[k] *= Phi;
-                    }
-                    h[mt][0][q] = z[0]; h[mt][0][q + 1] = z[1]; h[mt][1][q] = z[2]; h[mt][1][q + 1] = z[3];
+                    p0 = mul2(p0, bc(rs)); p1 = mul2(p1, bc(rs));
+                    f2 Phi0, phi0, Phi1, phi1, zz;
+                    gelu_terms2(p0, Phi0, phi0, zz);
+                    gelu_terms2(p1, Phi1, phi1, zz);
+                    st[(2 * s) * 32] = p0;
+                    st[(2 * s + 1) * 32] = p1;
+                    st[(8 + 2 * s) * 32] = mul2(fma2(p0, phi0, Phi0), bc(rs));      // gelu'(z) / sigma
+                    st[(8 + 2 * s + 1) * 32] = mul2(fma2(p1, phi1, Phi1), bc(rs));
+                    p0 = mul2(p0, Phi0); p1 = mul2(p1, Phi1);
                 }
                 if (l < 4) {
-                    float hn[2][2][4];
+                    f2 hn[2][2][2];
 #pragma unroll
                     for (int nt = 0; nt < 2; ++nt) {
-                        const float b0 = sTail[16 * l + 8 * nt + 2 * t], b1 = sTail[16 * l + 8 * nt + 2 * t + 1];
+                        const f2 bias = make_float2(sTail[16 * l + 8 * nt + 2 * t], sTail[16 * l + 8 * nt + 2 * t + 1]);
 #pragma unroll
-                        for (int mt = 0; mt < 2; ++mt) { hn[mt][nt][0] = b0; hn[mt][nt][1] = b1; hn[mt][nt][2] = b0; hn[mt][nt][3] = b1; }
+                        for (int mt = 0; mt < 2; ++mt) { hn[mt][nt][0] = bias; hn[mt][nt][1] = bias; }
                     }
-                    const float4* fl = fragL + (frag::kF1 + 4 * (l - 1)) * 32;
+                    const float4* fl = fragL + (kF1 + 4 * (l - 1)) * 32;
 #pragma unroll
                     for (int ks = 0; ks < 2; ++ks) {
                         const float4 w0 = fl[(2 * ks) * 32], w1 = fl[(2 * ks + 1) * 32];
-#pragma unroll
-                        for (int mt = 0; mt < 2; ++mt) {
-                            uint32_t ah[4], al[4];
-                            frag::a_from_c(h[mt][ks], ah, al);
-                            frag::mma3(hn[mt][0], ah, al, w0);
-                            frag::mma3(hn[mt][1], ah, al, w1);
-                        }
+                        uint32_t ah[2][4], al[2][4];
+                        a_from_c(h[0][ks], ah[0], al[0]);
+                        a_from_c(h[1][ks], ah[1], al[1]);
+                        mma3_quad<false>(hn[0][0], hn[0][1], hn[1][0], hn[1][1], ah[0], al[0], ah[1], al[1], w0, w1);
                     }
 #pragma unroll
                     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-                        for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) h[mt][nt][q] = hn[mt][nt][q];
+                        for (int nt = 0; nt < 2; ++nt) { h[mt][nt][0] = hn[mt][nt][0]; h[mt][nt][1] = hn[mt][nt][1]; }
                 } else {
-                    const float w00 = sTail[frag::kTailW4 + 2 * t], w01 = sTail[frag::kTailW4 + 2 * t + 1];
-                    const float w10 = sTail[frag::kTailW4 + 8 + 2 * t], w11 = sTail[frag::kTailW4 + 8 + 2 * t + 1];
-                    const float b4 = sTail[frag::kTailB4];
 #pragma unroll
-                    for (int s = 0; s < 4; ++s) {
-                        const int mt = s >> 1, q = 2 * (s & 1);
-                        out[s] = frag::quad_sum(fmaf(w00, h[mt][0][q], w01 * h[mt][0][q + 1])
-                                                + fmaf(w10, h[mt][1][q], w11 * h[mt][1][q + 1])) + b4;
-                    }
+                    for (int s = 0; s < 4; ++s)
+                        out[s] = quad_sum(hsum(fma2(w4p0, h[s >> 1][0][s & 1], mul2(w4p1, h[s >> 1][1][s & 1])))) + b4;
                 }
             }
             // ------------------------------------------------------------ 3. reverse sweep: d out / d a
-            // gbar: adjoint of the GELU outputs of layer l (C layout); starts as the last layer's weights
-            float gb[2][2][4];
-            {
-                const float w00 = sTail[frag::kTailW4 + 2 * t], w01 = sTail[frag::kTailW4 + 2 * t + 1];
-                const float w10 = sTail[frag::kTailW4 + 8 + 2 * t], w11 = sTail[frag::kTailW4 + 8 + 2 * t + 1];
+            // gb: adjoint of the GELU outputs of layer l (C layout); starts as the last layer's weights
+            f2 gb[2][2][2];
 #pragma unroll
-                for (int mt = 0; mt < 2; ++mt) {
-                    gb[mt][0][0] = w00; gb[mt][0][1] = w01; gb[mt][0][2] = w00; gb[mt][0][3] = w01;
-                    gb[mt][1][0] = w10; gb[mt][1][1] = w11; gb[mt][1][2] = w10; gb[mt][1][3] = w11;
-                }
+            for (int mt = 0; mt < 2; ++mt) {
+                gb[mt][0][0] = w4p0; gb[mt][0][1] = w4p0;
+                gb[mt][1][0] = w4p1; gb[mt][1][1] = w4p1;
             }
 #pragma unroll 1
             for (int l = 4; l >= 1; --l) {
-                const float* st = stash + (l - 1) * 32 * 32;
+                const float2* st = stash + (l - 1) * 16 * 32;
                 // hbar = zb - mean(zb) - z mean(z zb),  zb = gbar * gelu'(z) / sigma
 #pragma unroll
                 for (int s = 0; s < 4; ++s) {
-                    const int mt = s >> 1, q = 2 * (s & 1);
-                    float z[4], zb[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) { z[k] = st[(4 * s + k) * 32]; zb[k] = st[(16 + 4 * s + k) * 32]; }
-                    zb[0] *= gb[mt][0][q]; zb[1] *= gb[mt][0][q + 1]; zb[2] *= gb[mt][1][q]; zb[3] *= gb[mt][1][q + 1];
-                    const float m1 = frag::quad_sum((zb[0] + zb[1]) + (zb[2] + zb[3])) * (1.0f / kHid);
-                    const float m2 = frag::quad_sum(fmaf(z[0], zb[0], z[1] * zb[1]) + fmaf(z[2], zb[2], z[3] * zb[3])) * (1.0f / kHid);
-                    gb[mt][0][q] = zb[0] - m1 - z[0] * m2;
-                    gb[mt][0][q + 1] = zb[1] - m1 - z[1] * m2;
-                    gb[mt][1][q] = zb[2] - m1 - z[2] * m2;
-                    gb[mt][1][q + 1] = zb[3] - m1 - z[3] * m2;
+                    f2& g0 = gb[s >> 1][0][s & 1];
+                    f2& g1 = gb[s >> 1][1][s & 1];
+                    const f2 z0 = st[(2 * s) * 32], z1 = st[(2 * s + 1) * 32];
+                    const f2 zb0 = mul2(st[(8 + 2 * s) * 32], g0), zb1 = mul2(st[(8 + 2 * s + 1) * 32], g1);
+                    const f2 m = quad_sum2(make_float2(hsum(add2(zb0, zb1)), hsum(fma2(z0, zb0, mul2(z1, zb1)))));
+                    const float m1 = m.x * (-1.0f / kHid), m2 = m.y * (-1.0f / kHid);
+                    g0 = fma2(z0, bc(m2), add2(zb0, bc(m1)));
+                    g1 = fma2(z1, bc(m2), add2(zb1, bc(m1)));
                 }
                 if (l > 1) {        // gbar_{l-1} = W_{l-1}^T hbar  (hidden layer l-1 maps gelu(z_{l-1}) to h_l)
-                    float gn[2][2][4];
-#pragma unroll
-                    for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-                        for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) gn[mt][nt][q] = 0.0f;
-                    const float4* fl = fragL + (frag::kR1 + 4 * (l - 2)) * 32;
+                    f2 gn[2][2][2];
+                    const float4* fl = fragL + (kR1 + 4 * (l - 2)) * 32;
 #pragma unroll
                     for (int ks = 0; ks < 2; ++ks) {
                         const float4 w0 = fl[(2 * ks) * 32], w1 = fl[(2 * ks + 1) * 32];
-#pragma unroll
-                        for (int mt = 0; mt < 2; ++mt) {
-                            uint32_t ah[4], al[4];
-                            frag::a_from_c(gb[mt][ks], ah, al);
-                            frag::mma3(gn[mt][0], ah, al, w0);
-                            frag::mma3(gn[mt][1], ah, al, w1);
-                        }
+                        uint32_t ah[2][4], al[2][4];
+                        a_from_c(gb[0][ks], ah[0], al[0]);
+                        a_from_c(gb[1][ks], ah[1], al[1]);
+                        if (ks == 0) mma3_quad<true>(gn[0][0], gn[0][1], gn[1][0], gn[1][1], ah[0], al[0], ah[1], al[1], w0, w1);
+                        else mma3_quad<false>(gn[0][0], gn[0][1], gn[1][0], gn[1][1], ah[0], al[0], ah[1], al[1], w0, w1);
                     }
 #pragma unroll
                     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-                        for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) gb[mt][nt][q] = gn[mt][nt][q];
+                        for (int nt = 0; nt < 2; ++nt) { gb[mt][nt][0] = gn[mt][nt][0]; gb[mt][nt][1] = gn[mt][nt][1]; }
                 }
             }
             // layer 0 transposed + positional-encoding adjoint: abar_c = sum_k 2^k (ebar_sin cos - ebar_cos sin)
             float abar[4][3];
             {
-                uint32_t ah[2][2][4], al[2][2][4];
+                const float f0 = (float)(1 << t), f1 = 16.0f * f0;
+                uint32_t ah[2][2][4], al[2][2][4];              // [m-tile][k-step]
 #pragma unroll
                 for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-                    for (int ks = 0; ks < 2; ++ks) frag::a_from_c(gb[mt][ks], ah[mt][ks], al[mt][ks]);
-                const float f0 = (float)(1 << t), f1 = 16.0f * f0;
+                    for (int ks = 0; ks < 2; ++ks) a_from_c(gb[mt][ks], ah[mt][ks], al[mt][ks]);
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                    f2 eb[2][2][2];                              // [m-tile][octave half f]: (cos, sin) adjoints of rows g, g + 8
+                    mma3_quad<true>(eb[0][0], eb[0][1], eb[1][0], eb[1][1], ah[0][0], al[0][0], ah[1][0], al[1][0],
+                                    fragL[(kR0 + 2 * c) * 32], fragL[(kR0 + 2 * c + 1) * 32]);
+                    mma3_quad<false>(eb[0][0], eb[0][1], eb[1][0], eb[1][1], ah[0][1], al[0][1], ah[1][1], al[1][1],
+                                     fragL[(kR0 + 6 + 2 * c) * 32], fragL[(kR0 + 6 + 2 * c + 1) * 32]);
 #pragma unroll
-                    for (int f = 0; f < 2; ++f) {
-                        const int nt = 2 * c + f;
-                        const float4 w0 = fragL[(frag::kR0 + nt) * 32], w1 = fragL[(frag::kR0 + 6 + nt) * 32];
-                        const float fk = f ? f1 : f0;
+                    for (int mt = 0; mt < 2; ++mt) {
+                        float acc0 = 0.0f, acc1 = 0.0f;
 #pragma unroll
-                        for (int mt = 0; mt < 2; ++mt) {
-                            float eb[4] = {0.0f, 0.0f, 0.0f, 0.0f};      // (cos, sin) adjoints of rows g, g+8
-                            frag::mma3(eb, ah[mt][0], al[mt][0], w0);
-                            frag::mma3(eb, ah[mt][1], al[mt][1], w1);
-                            acc[2 * mt] += fk * (eb[1] * e.cs[2 * mt][c][f] - eb[0] * e.sn[2 * mt][c][f]);
-                            acc[2 * mt + 1] += fk * (eb[3] * e.cs[2 * mt + 1][c][f] - eb[2] * e.sn[2 * mt + 1][c][f]);
+                        for (int f = 0; f < 2; ++f) {
+                            const float fk = f ? f1 : f0;
+                            const f2 cs = e.cs[mt][c][f], sn = e.sn[mt][c][f];
+                            acc0 = fmaf(fk, fmaf(eb[mt][f][0].y, cs.x, -eb[mt][f][0].x * sn.x), acc0);
+                            acc1 = fmaf(fk, fmaf(eb[mt][f][1].y, cs.y, -eb[mt][f][1].x * sn.y), acc1);
                         }
+                        const f2 a2 = quad_sum2(make_float2(acc0, acc1));
+                        abar[2 * mt][c] = a2.x;
+                        abar[2 * mt + 1][c] = a2.y;
                     }
-#pragma unroll
-                    for (int s = 0; s < 4; ++s) abar[s][c] = frag::quad_sum(acc[s]);
                 }
             }
             // ------------------------------------------------------------ 4. lane == sample
-            const float o = frag::rows_to_lanes(out, lane);
+            const float o = rows_to_lanes(out, lane);
             float ga[3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 const float v[4] = {abar[0][c], abar[1][c], abar[2][c], abar[3][c]};
-                ga[c] = frag::rows_to_lanes(v, lane);
+                ga[c] = rows_to_lanes(v, lane);
             }
             const float res = sigmoidf_(o - 1.0f);
             const float sp = res * (1.0f - res) * pi_scale;

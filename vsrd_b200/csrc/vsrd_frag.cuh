@@ -28,6 +28,19 @@
 namespace vsrd {
 namespace frag {
 
+// ---- packed fp32 pairs (Blackwell FFMA2 / FMUL2 / FADD2) --------------------------------------
+// sm_100 issues one two-wide fp32 FMA per warp instruction (fma.rn.f32x2); a scalar or an immediate
+// broadcasts for free (`R.F32` operand form).  The field kernels are issue-bound on fp32 element-wise
+// work between the MMAs (profiles/r01_v5_*: 61 % FADD/FMUL/FFMA), so every per-channel formula is
+// written on the accumulator register pairs (c0, c1) / (c2, c3) of the C layout.
+using f2 = float2;
+__device__ __forceinline__ f2 bc(float a) { return make_float2(a, a); }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) { return __ffma2_rn(b, bc(-1.0f), a); }   // a - b, one rounding
+__device__ __forceinline__ float hsum(f2 a) { return a.x + a.y; }
+
 // ---- shared-memory image of one instance's weights -------------------------------------------
 // float4 {b0_hi, b1_hi, b0_lo, b1_lo} per (fragment, lane); fragment order:
 constexpr int kF0 = 0;              // layer 0 forward:   [ks 0..5][nt 0..1]     b0 = W0[8nt+g][8ks+2t], b1 = W0[8nt+g][8ks+2t+1]
@@ -48,25 +61,76 @@ __device__ __forceinline__ void split(float x, uint32_t& hi, uint32_t& lo) {
     lo = __float_as_uint(x - __uint_as_float(hi));    // remainder; the MMA reads its top 19 bits
 }
 
-__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+// An accumulator tile is two register pairs: d[0] = (c0, c1) (row g), d[1] = (c2, c3) (row g + 8).
+__device__ __forceinline__ void mma_tf32(f2 (&d)[2], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "+f"(d[0].x), "+f"(d[0].y), "+f"(d[1].x), "+f"(d[1].y)
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
 // d += A * B with A = ah + al, B = bh + bl (the lo*lo term is below fp32 rounding)
-__device__ __forceinline__ void mma3(float (&d)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], const float4& b) {
+__device__ __forceinline__ void mma3(f2 (&d)[2], const uint32_t (&ah)[4], const uint32_t (&al)[4], const float4& b) {
     mma_tf32(d, al, __float_as_uint(b.x), __float_as_uint(b.y));
     mma_tf32(d, ah, __float_as_uint(b.z), __float_as_uint(b.w));
     mma_tf32(d, ah, __float_as_uint(b.x), __float_as_uint(b.y));
 }
 
+// The same with a zero accumulator on input (first k-step of a product without bias): the C operand is
+// the zero register, so no accumulator clearing is issued.
+__device__ __forceinline__ void mma_tf32_zero(f2 (&d)[2], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+                 : "=f"(d[0].x), "=f"(d[0].y), "=f"(d[1].x), "=f"(d[1].y)
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(0.0f));
+}
+__device__ __forceinline__ void mma3_zero(f2 (&d)[2], const uint32_t (&ah)[4], const uint32_t (&al)[4], const float4& b) {
+    mma_tf32_zero(d, al, __float_as_uint(b.x), __float_as_uint(b.y));
+    mma_tf32(d, ah, __float_as_uint(b.z), __float_as_uint(b.w));
+    mma_tf32(d, ah, __float_as_uint(b.x), __float_as_uint(b.y));
+}
+
+// One k-step of FOUR accumulator tiles at once: x0, x1 share the A operand X (n-tiles w0, w1), y0, y1
+// share Y.  The three 3xTF32 passes are issued pass-major, so two MMAs into the same accumulator are
+// always three independent MMAs apart: a back-to-back chain stalls on the tensor pipe's result latency
+// (profiles/r01_v5_*: HMMA = 6 % of the instructions but 22 % of the stall samples, "wait").
+template <bool kZero>
+__device__ __forceinline__ void mma3_quad(f2 (&x0)[2], f2 (&x1)[2], f2 (&y0)[2], f2 (&y1)[2],
+                                          const uint32_t (&xh)[4], const uint32_t (&xl)[4],
+                                          const uint32_t (&yh)[4], const uint32_t (&yl)[4],
+                                          const float4& w0, const float4& w1) {
+    const uint32_t w0h0 = __float_as_uint(w0.x), w0h1 = __float_as_uint(w0.y), w0l0 = __float_as_uint(w0.z), w0l1 = __float_as_uint(w0.w);
+    const uint32_t w1h0 = __float_as_uint(w1.x), w1h1 = __float_as_uint(w1.y), w1l0 = __float_as_uint(w1.z), w1l1 = __float_as_uint(w1.w);
+    if (kZero) {
+        mma_tf32_zero(x0, xl, w0h0, w0h1); mma_tf32_zero(x1, xl, w1h0, w1h1);
+        mma_tf32_zero(y0, yl, w0h0, w0h1); mma_tf32_zero(y1, yl, w1h0, w1h1);
+    } else {
+        mma_tf32(x0, xl, w0h0, w0h1); mma_tf32(x1, xl, w1h0, w1h1);
+        mma_tf32(y0, yl, w0h0, w0h1); mma_tf32(y1, yl, w1h0, w1h1);
+    }
+    mma_tf32(x0, xh, w0l0, w0l1); mma_tf32(x1, xh, w1l0, w1l1);
+    mma_tf32(y0, yh, w0l0, w0l1); mma_tf32(y1, yh, w1l0, w1l1);
+    mma_tf32(x0, xh, w0h0, w0h1); mma_tf32(x1, xh, w1h0, w1h1);
+    mma_tf32(y0, yh, w0h0, w0h1); mma_tf32(y1, yh, w1h0, w1h1);
+}
+
 // A fragment (hi, lo) of k-step `nt` from an activation tile held in C layout.
-__device__ __forceinline__ void a_from_c(const float (&c)[4], uint32_t (&ah)[4], uint32_t (&al)[4]) {
-    split(c[0], ah[0], al[0]);
-    split(c[2], ah[1], al[1]);
-    split(c[1], ah[2], al[2]);
-    split(c[3], ah[3], al[3]);
+__device__ __forceinline__ void a_from_c(const f2 (&c)[2], uint32_t (&ah)[4], uint32_t (&al)[4]) {
+    split(c[0].x, ah[0], al[0]);
+    split(c[1].x, ah[1], al[1]);
+    split(c[0].y, ah[2], al[2]);
+    split(c[1].y, ah[3], al[3]);
+}
+
+// A fragment from two register pairs that already are (row g, row g + 8) pairs: lo = x - hi packed.
+//   p01 -> (a0, a1) = k-slot t of rows g, g + 8;  p23 -> (a2, a3) = k-slot t + 4
+__device__ __forceinline__ void a_from_row_pairs(f2 p01, f2 p23, uint32_t (&ah)[4], uint32_t (&al)[4]) {
+    f2 h01, h23;
+    ah[0] = __float_as_uint(p01.x) & 0xffffe000u; ah[1] = __float_as_uint(p01.y) & 0xffffe000u;
+    ah[2] = __float_as_uint(p23.x) & 0xffffe000u; ah[3] = __float_as_uint(p23.y) & 0xffffe000u;
+    h01.x = __uint_as_float(ah[0]); h01.y = __uint_as_float(ah[1]);
+    h23.x = __uint_as_float(ah[2]); h23.y = __uint_as_float(ah[3]);
+    const f2 l01 = sub2(p01, h01), l23 = sub2(p23, h23);
+    al[0] = __float_as_uint(l01.x); al[1] = __float_as_uint(l01.y);
+    al[2] = __float_as_uint(l23.x); al[3] = __float_as_uint(l23.y);
 }
 
 // ---- sample-contracted products (weight gradients) ---------------------------------------------
@@ -84,9 +148,18 @@ __device__ __forceinline__ uint32_t movmatrix_trans(uint32_t x) {
 // (x0, x1) -> packed bf16 pairs {lo half = x0, hi half = x1}: rounded value and rounded remainder.
 __device__ __forceinline__ void pack_bf16_split(float x0, float x1, uint32_t& hi, uint32_t& lo) {
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+    f2 h;
+    h.x = __uint_as_float(hi << 16);
+    h.y = __uint_as_float(hi & 0xffff0000u);
+    const f2 rem = sub2(make_float2(x0, x1), h);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(rem.y), "f"(rem.x));
+}
+__device__ __forceinline__ void pack_bf16_split_scalar(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
     const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(x1 - h1), "f"(x0 - h0));
 }
+__device__ __forceinline__ void pack_transposed(f2 x, uint32_t& hi, uint32_t& lo);
 
 // Pair (x0, x1) = C-layout elements (sample g, channels 2t, 2t+1) of an 8x8 block -> transposed operand
 // register (samples 2t, 2t+1; channel g), hi and lo parts.
@@ -97,34 +170,50 @@ __device__ __forceinline__ void pack_transposed(float x0, float x1, uint32_t& hi
     lo = movmatrix_trans(l);
 }
 
-__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+__device__ __forceinline__ void pack_transposed(f2 x, uint32_t& hi, uint32_t& lo) { pack_transposed(x.x, x.y, hi, lo); }
+
+__device__ __forceinline__ void mma_bf16(f2 (&d)[2], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "+f"(d[0].x), "+f"(d[0].y), "+f"(d[1].x), "+f"(d[1].y)
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
 // A operand (16 outputs x 16 samples of one m-tile) of the weight-gradient product from the adjoint's
 // two C tiles c[nt][q] (nt = output half): rows = outputs, k = samples.
-__device__ __forceinline__ void wgrad_a_operand(const float (&c)[2][4], uint32_t (&ah)[4], uint32_t (&al)[4]) {
-    pack_transposed(c[0][0], c[0][1], ah[0], al[0]);   // outputs 0-7,  samples 0-7
-    pack_transposed(c[1][0], c[1][1], ah[1], al[1]);   // outputs 8-15, samples 0-7
-    pack_transposed(c[0][2], c[0][3], ah[2], al[2]);   // outputs 0-7,  samples 8-15
-    pack_transposed(c[1][2], c[1][3], ah[3], al[3]);   // outputs 8-15, samples 8-15
+__device__ __forceinline__ void wgrad_a_operand(const f2 (&c)[2][2], uint32_t (&ah)[4], uint32_t (&al)[4]) {
+    pack_transposed(c[0][0], ah[0], al[0]);   // outputs 0-7,  samples 0-7
+    pack_transposed(c[1][0], ah[1], al[1]);   // outputs 8-15, samples 0-7
+    pack_transposed(c[0][1], ah[2], al[2]);   // outputs 0-7,  samples 8-15
+    pack_transposed(c[1][1], ah[3], al[3]);   // outputs 8-15, samples 8-15
 }
 
 // D (16 outputs x 8 inputs) += A (adjoint) x B, B = one C tile (16 samples x 8 input channels).
-__device__ __forceinline__ void wgrad_tile(float (&D)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
-                                           float b0, float b1, float b2, float b3) {
+// lo = channels (2t, 2t+1) of the samples in rows g, hi = the same channels in rows g + 8.
+__device__ __forceinline__ void wgrad_tile(f2 (&D)[2], const uint32_t (&ah)[4], const uint32_t (&al)[4], f2 lo_rows, f2 hi_rows) {
     uint32_t bh0, bl0, bh1, bl1;
-    pack_transposed(b0, b1, bh0, bl0);
-    pack_transposed(b2, b3, bh1, bl1);
+    pack_transposed(lo_rows, bh0, bl0);
+    pack_transposed(hi_rows, bh1, bl1);
+    mma_bf16(D, ah, bl0, bl1);
+    mma_bf16(D, al, bh0, bh1);
+    mma_bf16(D, ah, bh0, bh1);
+}
+
+// The same for a B tile whose elements are four unrelated registers (b0, b1: channels 2t, 2t+1 of row g;
+// b2, b3: of row g + 8).
+__device__ __forceinline__ void wgrad_tile_scalar(f2 (&D)[2], const uint32_t (&ah)[4], const uint32_t (&al)[4],
+                                                  float b0, float b1, float b2, float b3) {
+    uint32_t h, l, bh0, bl0, bh1, bl1;
+    pack_bf16_split_scalar(b0, b1, h, l);
+    bh0 = movmatrix_trans(h); bl0 = movmatrix_trans(l);
+    pack_bf16_split_scalar(b2, b3, h, l);
+    bh1 = movmatrix_trans(h); bl1 = movmatrix_trans(l);
     mma_bf16(D, ah, bl0, bl1);
     mma_bf16(D, al, bh0, bh1);
     mma_bf16(D, ah, bh0, bh1);
 }
 
 // D += A x ones: every column holds the sum over the 16 samples (bias gradient).
-__device__ __forceinline__ void wgrad_bias(float (&D)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4]) {
+__device__ __forceinline__ void wgrad_bias(f2 (&D)[2], const uint32_t (&ah)[4], const uint32_t (&al)[4]) {
     constexpr uint32_t kOnes = 0x3f803f80u;
     mma_bf16(D, al, kOnes, kOnes);
     mma_bf16(D, ah, kOnes, kOnes);
@@ -174,6 +263,15 @@ __device__ __forceinline__ float quad_sum(float v) {
     return v;
 }
 
+// two independent quad sums at once: (x, y) -> (sum over the quad of x, of y)
+__device__ __forceinline__ f2 quad_sum2(f2 v) {
+    f2 o;
+    o.x = __shfl_xor_sync(kFull, v.x, 1); o.y = __shfl_xor_sync(kFull, v.y, 1);
+    v = add2(v, o);
+    o.x = __shfl_xor_sync(kFull, v.x, 2); o.y = __shfl_xor_sync(kFull, v.y, 2);
+    return add2(v, o);
+}
+
 // sin / cos with a three-term Cody-Waite reduction (|x| < ~1e4) and the single-precision minimax
 // polynomials on [-pi/4, pi/4]; absolute error ~1e-7, no slow path, no local memory.
 __host__ __device__ __forceinline__ void sincos_cw(float x, float& s, float& c) {
@@ -210,6 +308,85 @@ __device__ __forceinline__ void gelu_terms_fast(float z, float& Phi, float& phi)
     const float tail = 0.5f * poly * t * E;
     Phi = z >= 0.0f ? 1.0f - tail : tail;
     phi = kInvSqrt2Pi * E;
+}
+
+// The same for a channel pair.  zz = z^2 is returned for gelu'' = phi (2 - z^2).  The polynomial
+// coefficients carry the factor 1/2 of the tail; Phi = 1/2 + copysign(1/2 - tail, z).
+__device__ __forceinline__ void gelu_terms2(f2 z, f2& Phi, f2& phi, f2& zz) {
+    zz = mul2(z, z);
+    const f2 arg = mul2(zz, bc(-0.72134752044448170368f));
+    f2 E, t;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(E.x) : "f"(arg.x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(E.y) : "f"(arg.y));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.x) : "f"(fmaf(0.3275911f * kInvSqrt2, fabsf(z.x), 1.0f)));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.y) : "f"(fmaf(0.3275911f * kInvSqrt2, fabsf(z.y), 1.0f)));
+    f2 poly = fma2(bc(0.5f * 1.061405429f), t, bc(0.5f * -1.453152027f));
+    poly = fma2(poly, t, bc(0.5f * 1.421413741f));
+    poly = fma2(poly, t, bc(0.5f * -0.284496736f));
+    poly = fma2(poly, t, bc(0.5f * 0.254829592f));
+    const f2 tail = mul2(mul2(poly, t), E);
+    f2 q = fma2(tail, bc(-1.0f), bc(0.5f));                    // 1/2 - tail >= 0
+    q.x = __uint_as_float(__float_as_uint(q.x) | (__float_as_uint(z.x) & 0x80000000u));
+    q.y = __uint_as_float(__float_as_uint(q.y) | (__float_as_uint(z.y) & 0x80000000u));
+    Phi = add2(q, bc(0.5f));
+    phi = mul2(E, bc(kInvSqrt2Pi));
+}
+
+// sincos_cw on a pair of arguments.
+__device__ __forceinline__ void sincos_cw2(f2 x, f2& s, f2& c) {
+    const f2 kx = mul2(x, bc(0.63661977236758134308f));
+    f2 kf;
+    kf.x = rintf(kx.x); kf.y = rintf(kx.y);
+    f2 r = fma2(kf, bc(-1.5707962513e+00f), x);
+    r = fma2(kf, bc(-7.5497894159e-08f), r);
+    r = fma2(kf, bc(-5.3903029534e-15f), r);
+    const int q0 = (int)kf.x, q1 = (int)kf.y;
+    const f2 r2 = mul2(r, r);
+    f2 sp = fma2(r2, bc(-1.9515295891e-4f), bc(8.3321608736e-3f));
+    sp = fma2(sp, r2, bc(-1.6666654611e-1f));
+    sp = fma2(mul2(sp, r2), r, r);
+    f2 cp = fma2(r2, bc(2.443315711809948e-5f), bc(-1.388731625493765e-3f));
+    cp = fma2(cp, r2, bc(4.166664568298827e-2f));
+    cp = fma2(cp, r2, bc(-0.5f));
+    cp = fma2(cp, r2, bc(1.0f));
+    {
+        const float ss = (q0 & 1) ? cp.x : sp.x, cc = (q0 & 1) ? sp.x : cp.x;
+        s.x = (q0 & 2) ? -ss : ss;
+        c.x = ((q0 + 1) & 2) ? -cc : cc;
+    }
+    {
+        const float ss = (q1 & 1) ? cp.y : sp.y, cc = (q1 & 1) ? sp.y : cp.y;
+        s.y = (q1 & 2) ? -ss : ss;
+        c.y = ((q1 + 1) & 2) ? -cc : cc;
+    }
+}
+
+// Positional encoding of the warp tile in A-operand form: pairs run over the two rows (g, g + 8) of an
+// m-tile, so cs[mt][c][f] / sn[mt][c][f] ARE the register pairs (a0, a1) / (a2, a3) of k-step 2c + f.
+// Lane t owns frequencies k = t (f = 0) and k = t + 4 (f = 1) of every coordinate c.
+struct Encoding2 {
+    f2 cs[2][3][2];
+    f2 sn[2][3][2];
+};
+
+// a[mt][c] = PE argument fl(pi * u_c) of rows (g, g + 8) of m-tile mt.
+__device__ __forceinline__ void encode2(const f2 (&a)[2][3], int t, Encoding2& e) {
+    const float f = (float)(1 << t);
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            f2 sn, cs;
+            sincos_cw2(mul2(a[mt][c], bc(f)), sn, cs);     // f * a is exact: matches fl(2^k * fl(pi * u))
+            e.cs[mt][c][0] = cs; e.sn[mt][c][0] = sn;
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {                  // four octaves up by the double-angle recurrence
+                const f2 s2 = mul2(add2(sn, sn), cs);
+                cs = mul2(sub2(cs, sn), add2(cs, sn));
+                sn = s2;
+            }
+            e.cs[mt][c][1] = cs; e.sn[mt][c][1] = sn;
+        }
 }
 
 // Per-lane view of the positional encoding of its 4 rows: lane t owns the (cos, sin) pairs of
