@@ -51,20 +51,31 @@ __global__ void __launch_bounds__(kThreads) field_forward_kernel(SceneDev scene,
 //   4. lane == sample: residual = sigmoid(out - 1), chain rule through |p_x|, rotate the gradient to the
 //      world frame, one coalesced float4 store
 // =============================================================================================
-constexpr int kFwdWarps = 12;
-constexpr int kFwdThreads = kFwdWarps * 32;
-constexpr int kFwdStashPairs = 4 * 16 * 32;      // per warp, float2: [layer][z pairs 8 | g1/sigma pairs 8][lane]
-constexpr size_t kFwdSmemBytes = frag::kWeightBytes + (size_t)kFwdWarps * kFwdStashPairs * sizeof(float2);
+// MT = m-tiles (16 rows) per warp tile; one CTA per SM.  Measured on B200 (profiles/r01_v6_*): 12 warps x 2
+// m-tiles (168 registers) 0.321 ms, 16 warps x 1 m-tile (128 registers) 0.335 ms, 20 x 1 (96 registers,
+// spills) 0.342 ms for the fine pass -- throughput follows the number of m-tiles in flight, which the
+// register file bounds, not the warp count.  MT = 2 ships; MT = 1 stays selectable (VSRD_FWD_MT=1).
+template <int MT>
+struct FwdCfg {
+    static constexpr int kWarps = MT == 2 ? 12 : 16;
+    static constexpr int kThreads = kWarps * 32;
+    static constexpr int kRows = 16 * MT;
+    static constexpr int kStashPairs = 4 * 8 * MT * 32;     // per warp, float2: [layer][z pairs 4 MT | g1/sigma pairs 4 MT][lane]
+    static constexpr size_t kSmemBytes = frag::kWeightBytes + (size_t)kWarps * kStashPairs * sizeof(float2);
+};
 
-__global__ void __launch_bounds__(kFwdThreads, 1) field_forward_mma_kernel(
+template <int MT>
+__global__ void __launch_bounds__(FwdCfg<MT>::kThreads, 1) field_forward_mma_kernel(
         SceneDev scene, RaysDev rays, float4* __restrict__ field, int tiles_per_inst) {
     using namespace frag;
+    using Cfg = FwdCfg<MT>;
+    constexpr int kRows = Cfg::kRows, kSlots = 2 * MT, kLayerPairs = 4 * MT;   // pair rows of z (then as many of g1/sigma) per layer
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4* sF = reinterpret_cast<float4*>(smem_raw);
     float* sTail = reinterpret_cast<float*>(sF + kFragFloat4);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int t = lane & 3;
-    float2* stash = reinterpret_cast<float2*>(sTail + kTailFloats) + (size_t)warp * kFwdStashPairs + lane;
+    float2* stash = reinterpret_cast<float2*>(sTail + kTailFloats) + (size_t)warp * Cfg::kStashPairs + lane;
     const float4* fragL = sF + lane;
 
     const int total = rays.R * rays.M;
@@ -86,36 +97,37 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_forward_mma_kernel(
         const float b4 = sTail[kTailB4];
 
 #pragma unroll 1
-        for (long long tile = seg + warp; tile < seg_end; tile += kFwdWarps) {
-            const int base = (int)(tile - (long long)inst * tiles_per_inst) * 32;
-            // ------------------------------------------------------------ 1. lane == sample
-            const int idx = min(base + lane, total - 1);
+        for (long long tile = seg + warp; tile < seg_end; tile += Cfg::kWarps) {
+            const int base = (int)(tile - (long long)inst * tiles_per_inst) * kRows;
+            // ------------------------------------------------------------ 1. lane == sample (lanes < kRows)
+            const int row = lane & (kRows - 1);
+            const int idx = min(base + row, total - 1);
             const int r = idx / rays.M;
             const int j = idx - r * rays.M;
             float x[3];
             sample_position(rays, r, j, x);
             BoxEval b;
             box_eval(x, I, b);
-            f2 arow[2][3];                                 // PE arguments of rows (g, g + 8) of each m-tile
+            f2 arow[MT][3];                                // PE arguments of rows (g, g + 8) of each m-tile
             {
                 const float m[3] = {fabsf(b.p[0]), b.p[1], b.p[2]};
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    float v[4];
-                    lanes_to_rows(kPiF * (m[c] / scene.scale), lane, v);
-                    arow[0][c] = make_float2(v[0], v[1]);
-                    arow[1][c] = make_float2(v[2], v[3]);
+                    f2 v[MT];
+                    lanes_to_row_pairs<MT>(kPiF * (m[c] / scene.scale), lane, v);
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) arow[mt][c] = v[mt];
                 }
             }
             // ------------------------------------------------------------ 2. forward sweep
-            Encoding2 e;
-            encode2(arow, t, e);
-            f2 h[2][2][2];                                 // [m-tile][n-tile][row g | row g + 8]
+            EncodingT<MT> e;
+            encode2<MT>(arow, t, e);
+            f2 h[MT][2][2];                                // [m-tile][n-tile][row g | row g + 8]
 #pragma unroll
             for (int nt = 0; nt < 2; ++nt) {
                 const f2 bias = make_float2(sTail[8 * nt + 2 * t], sTail[8 * nt + 2 * t + 1]);
 #pragma unroll
-                for (int mt = 0; mt < 2; ++mt) { h[mt][nt][0] = bias; h[mt][nt][1] = bias; }
+                for (int mt = 0; mt < MT; ++mt) { h[mt][nt][0] = bias; h[mt][nt][1] = bias; }
             }
 #pragma unroll
             for (int c = 0; c < 3; ++c)
@@ -123,18 +135,18 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_forward_mma_kernel(
                 for (int f = 0; f < 2; ++f) {
                     const int ks = 2 * c + f;
                     const float4 w0 = fragL[(kF0 + 2 * ks) * 32], w1 = fragL[(kF0 + 2 * ks + 1) * 32];
-                    uint32_t ah[2][4], al[2][4];
-                    a_from_row_pairs(e.cs[0][c][f], e.sn[0][c][f], ah[0], al[0]);
-                    a_from_row_pairs(e.cs[1][c][f], e.sn[1][c][f], ah[1], al[1]);
-                    mma3_quad<false>(h[0][0], h[0][1], h[1][0], h[1][1], ah[0], al[0], ah[1], al[1], w0, w1);
+                    uint32_t ah[MT][4], al[MT][4];
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) a_from_row_pairs(e.cs[mt][c][f], e.sn[mt][c][f], ah[mt], al[mt]);
+                    mma3_step<false, MT>(h, ah, al, w0, w1);
                 }
-            float out[4];
+            float out[kSlots];
 #pragma unroll 1
             for (int l = 1; l <= 4; ++l) {
-                float2* st = stash + (l - 1) * 16 * 32;
+                float2* st = stash + (l - 1) * 2 * kLayerPairs * 32;
                 // LayerNorm (no affine, eps 1e-5) + GELU per row slot (slot s = 2 mt + half)
 #pragma unroll
-                for (int s = 0; s < 4; ++s) {
+                for (int s = 0; s < kSlots; ++s) {
                     f2& p0 = h[s >> 1][0][s & 1];
                     f2& p1 = h[s >> 1][1][s & 1];
                     const float mean = quad_sum(hsum(add2(p0, p1))) * (1.0f / kHid);
@@ -147,96 +159,94 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_forward_mma_kernel(
                     gelu_terms2(p1, Phi1, phi1, zz);
                     st[(2 * s) * 32] = p0;
                     st[(2 * s + 1) * 32] = p1;
-                    st[(8 + 2 * s) * 32] = mul2(fma2(p0, phi0, Phi0), bc(rs));      // gelu'(z) / sigma
-                    st[(8 + 2 * s + 1) * 32] = mul2(fma2(p1, phi1, Phi1), bc(rs));
+                    st[(kLayerPairs + 2 * s) * 32] = mul2(fma2(p0, phi0, Phi0), bc(rs));      // gelu'(z) / sigma
+                    st[(kLayerPairs + 2 * s + 1) * 32] = mul2(fma2(p1, phi1, Phi1), bc(rs));
                     p0 = mul2(p0, Phi0); p1 = mul2(p1, Phi1);
                 }
                 if (l < 4) {
-                    f2 hn[2][2][2];
+                    f2 hn[MT][2][2];
 #pragma unroll
                     for (int nt = 0; nt < 2; ++nt) {
                         const f2 bias = make_float2(sTail[16 * l + 8 * nt + 2 * t], sTail[16 * l + 8 * nt + 2 * t + 1]);
 #pragma unroll
-                        for (int mt = 0; mt < 2; ++mt) { hn[mt][nt][0] = bias; hn[mt][nt][1] = bias; }
+                        for (int mt = 0; mt < MT; ++mt) { hn[mt][nt][0] = bias; hn[mt][nt][1] = bias; }
                     }
                     const float4* fl = fragL + (kF1 + 4 * (l - 1)) * 32;
 #pragma unroll
                     for (int ks = 0; ks < 2; ++ks) {
                         const float4 w0 = fl[(2 * ks) * 32], w1 = fl[(2 * ks + 1) * 32];
-                        uint32_t ah[2][4], al[2][4];
-                        a_from_c(h[0][ks], ah[0], al[0]);
-                        a_from_c(h[1][ks], ah[1], al[1]);
-                        mma3_quad<false>(hn[0][0], hn[0][1], hn[1][0], hn[1][1], ah[0], al[0], ah[1], al[1], w0, w1);
+                        uint32_t ah[MT][4], al[MT][4];
+#pragma unroll
+                        for (int mt = 0; mt < MT; ++mt) a_from_c(h[mt][ks], ah[mt], al[mt]);
+                        mma3_step<false, MT>(hn, ah, al, w0, w1);
                     }
 #pragma unroll
-                    for (int mt = 0; mt < 2; ++mt)
+                    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
                         for (int nt = 0; nt < 2; ++nt) { h[mt][nt][0] = hn[mt][nt][0]; h[mt][nt][1] = hn[mt][nt][1]; }
                 } else {
 #pragma unroll
-                    for (int s = 0; s < 4; ++s)
+                    for (int s = 0; s < kSlots; ++s)
                         out[s] = quad_sum(hsum(fma2(w4p0, h[s >> 1][0][s & 1], mul2(w4p1, h[s >> 1][1][s & 1])))) + b4;
                 }
             }
             // ------------------------------------------------------------ 3. reverse sweep: d out / d a
             // gb: adjoint of the GELU outputs of layer l (C layout); starts as the last layer's weights
-            f2 gb[2][2][2];
+            f2 gb[MT][2][2];
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt) {
+            for (int mt = 0; mt < MT; ++mt) {
                 gb[mt][0][0] = w4p0; gb[mt][0][1] = w4p0;
                 gb[mt][1][0] = w4p1; gb[mt][1][1] = w4p1;
             }
 #pragma unroll 1
             for (int l = 4; l >= 1; --l) {
-                const float2* st = stash + (l - 1) * 16 * 32;
+                const float2* st = stash + (l - 1) * 2 * kLayerPairs * 32;
                 // hbar = zb - mean(zb) - z mean(z zb),  zb = gbar * gelu'(z) / sigma
 #pragma unroll
-                for (int s = 0; s < 4; ++s) {
+                for (int s = 0; s < kSlots; ++s) {
                     f2& g0 = gb[s >> 1][0][s & 1];
                     f2& g1 = gb[s >> 1][1][s & 1];
                     const f2 z0 = st[(2 * s) * 32], z1 = st[(2 * s + 1) * 32];
-                    const f2 zb0 = mul2(st[(8 + 2 * s) * 32], g0), zb1 = mul2(st[(8 + 2 * s + 1) * 32], g1);
+                    const f2 zb0 = mul2(st[(kLayerPairs + 2 * s) * 32], g0), zb1 = mul2(st[(kLayerPairs + 2 * s + 1) * 32], g1);
                     const f2 m = quad_sum2(make_float2(hsum(add2(zb0, zb1)), hsum(fma2(z0, zb0, mul2(z1, zb1)))));
                     const float m1 = m.x * (-1.0f / kHid), m2 = m.y * (-1.0f / kHid);
                     g0 = fma2(z0, bc(m2), add2(zb0, bc(m1)));
                     g1 = fma2(z1, bc(m2), add2(zb1, bc(m1)));
                 }
                 if (l > 1) {        // gbar_{l-1} = W_{l-1}^T hbar  (hidden layer l-1 maps gelu(z_{l-1}) to h_l)
-                    f2 gn[2][2][2];
+                    f2 gn[MT][2][2];
                     const float4* fl = fragL + (kR1 + 4 * (l - 2)) * 32;
 #pragma unroll
                     for (int ks = 0; ks < 2; ++ks) {
                         const float4 w0 = fl[(2 * ks) * 32], w1 = fl[(2 * ks + 1) * 32];
-                        uint32_t ah[2][4], al[2][4];
-                        a_from_c(gb[0][ks], ah[0], al[0]);
-                        a_from_c(gb[1][ks], ah[1], al[1]);
-                        if (ks == 0) mma3_quad<true>(gn[0][0], gn[0][1], gn[1][0], gn[1][1], ah[0], al[0], ah[1], al[1], w0, w1);
-                        else mma3_quad<false>(gn[0][0], gn[0][1], gn[1][0], gn[1][1], ah[0], al[0], ah[1], al[1], w0, w1);
+                        uint32_t ah[MT][4], al[MT][4];
+#pragma unroll
+                        for (int mt = 0; mt < MT; ++mt) a_from_c(gb[mt][ks], ah[mt], al[mt]);
+                        if (ks == 0) mma3_step<true, MT>(gn, ah, al, w0, w1);
+                        else mma3_step<false, MT>(gn, ah, al, w0, w1);
                     }
 #pragma unroll
-                    for (int mt = 0; mt < 2; ++mt)
+                    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
                         for (int nt = 0; nt < 2; ++nt) { gb[mt][nt][0] = gn[mt][nt][0]; gb[mt][nt][1] = gn[mt][nt][1]; }
                 }
             }
             // layer 0 transposed + positional-encoding adjoint: abar_c = sum_k 2^k (ebar_sin cos - ebar_cos sin)
-            float abar[4][3];
+            float abar[kSlots][3];
             {
                 const float f0 = (float)(1 << t), f1 = 16.0f * f0;
-                uint32_t ah[2][2][4], al[2][2][4];              // [m-tile][k-step]
+                uint32_t ah[2][MT][4], al[2][MT][4];            // [k-step][m-tile]
 #pragma unroll
-                for (int mt = 0; mt < 2; ++mt)
+                for (int ks = 0; ks < 2; ++ks)
 #pragma unroll
-                    for (int ks = 0; ks < 2; ++ks) a_from_c(gb[mt][ks], ah[mt][ks], al[mt][ks]);
+                    for (int mt = 0; mt < MT; ++mt) a_from_c(gb[mt][ks], ah[ks][mt], al[ks][mt]);
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    f2 eb[2][2][2];                              // [m-tile][octave half f]: (cos, sin) adjoints of rows g, g + 8
-                    mma3_quad<true>(eb[0][0], eb[0][1], eb[1][0], eb[1][1], ah[0][0], al[0][0], ah[1][0], al[1][0],
-                                    fragL[(kR0 + 2 * c) * 32], fragL[(kR0 + 2 * c + 1) * 32]);
-                    mma3_quad<false>(eb[0][0], eb[0][1], eb[1][0], eb[1][1], ah[0][1], al[0][1], ah[1][1], al[1][1],
-                                     fragL[(kR0 + 6 + 2 * c) * 32], fragL[(kR0 + 6 + 2 * c + 1) * 32]);
+                    f2 eb[MT][2][2];                             // [m-tile][octave half f]: (cos, sin) adjoints of rows g, g + 8
+                    mma3_step<true, MT>(eb, ah[0], al[0], fragL[(kR0 + 2 * c) * 32], fragL[(kR0 + 2 * c + 1) * 32]);
+                    mma3_step<false, MT>(eb, ah[1], al[1], fragL[(kR0 + 6 + 2 * c) * 32], fragL[(kR0 + 6 + 2 * c + 1) * 32]);
 #pragma unroll
-                    for (int mt = 0; mt < 2; ++mt) {
+                    for (int mt = 0; mt < MT; ++mt) {
                         float acc0 = 0.0f, acc1 = 0.0f;
 #pragma unroll
                         for (int f = 0; f < 2; ++f) {
@@ -252,19 +262,21 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_forward_mma_kernel(
                 }
             }
             // ------------------------------------------------------------ 4. lane == sample
-            const float o = rows_to_lanes(out, lane);
+            const float o = row_slots_to_lanes<MT>(out, lane);
             float ga[3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                const float v[4] = {abar[0][c], abar[1][c], abar[2][c], abar[3][c]};
-                ga[c] = rows_to_lanes(v, lane);
+                float v[kSlots];
+#pragma unroll
+                for (int s = 0; s < kSlots; ++s) v[s] = abar[s][c];
+                ga[c] = row_slots_to_lanes<MT>(v, lane);
             }
             const float res = sigmoidf_(o - 1.0f);
             const float sp = res * (1.0f - res) * pi_scale;
             const float gp0 = b.gp[0] + sp * b.s[0] * ga[0];
             const float gp1 = b.gp[1] + sp * ga[1];
             const float gp2 = b.gp[2] + sp * ga[2];
-            if (base + lane < total) {
+            if (lane < kRows && base + lane < total) {
                 field[(size_t)inst * total + base + lane] = make_float4(
                     b.value + res,
                     I.R[0] * gp0 + I.R[1] * gp1 + I.R[2] * gp2,
@@ -278,6 +290,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_forward_mma_kernel(
 }
 
 static int g_fwd_sms = 0;
+static int g_fwd_mt = 2;      // m-tiles per warp tile (VSRD_FWD_MT=1 selects the 16-row variant)
 
 // 0 = tensor-core kernel (default), 1 = SIMT cross-check (VSRD_FIELD_IMPL=simt, read per call)
 static int forward_impl() {
@@ -291,11 +304,25 @@ static int forward_setup() {
     if (cudaGetDevice(&dev) != cudaSuccess) return fail("vsrd_b200: no CUDA device%s");
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return fail("vsrd_b200: cudaGetDeviceProperties failed%s");
-    if (cudaFuncSetAttribute(field_forward_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)kFwdSmemBytes) != cudaSuccess)
+    if (cudaFuncSetAttribute(field_forward_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)FwdCfg<1>::kSmemBytes) != cudaSuccess ||
+        cudaFuncSetAttribute(field_forward_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)FwdCfg<2>::kSmemBytes) != cudaSuccess)
         return fail("vsrd_b200: cannot reserve %s of shared memory for field_forward_mma_kernel (built for sm_100a)", "217 KB");
+    const char* mt = getenv("VSRD_FWD_MT");
+    if (mt && (mt[0] == '1' || mt[0] == '2')) g_fwd_mt = mt[0] - '0';
     g_fwd_sms = prop.multiProcessorCount;
     return 0;
+}
+
+template <int MT>
+static void launch_forward_mma(const SceneDev& s, const RaysDev& r, float4* field, size_t total, cudaStream_t st) {
+    using Cfg = FwdCfg<MT>;
+    const int tiles_per_inst = (int)((total + Cfg::kRows - 1) / Cfg::kRows);
+    const long long all_tiles = (long long)s.N * tiles_per_inst;
+    const long long want = (all_tiles + Cfg::kWarps - 1) / Cfg::kWarps;
+    const int grid = (int)(want < g_fwd_sms ? want : g_fwd_sms);
+    field_forward_mma_kernel<MT><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(s, r, field, tiles_per_inst);
 }
 
 }  // namespace vsrd
@@ -314,11 +341,8 @@ int vsrd_field_forward(const VsrdScene* scene, const VsrdRays* rays, float* fiel
     if (forward_setup()) return 1;
     cudaStream_t st = (cudaStream_t)stream;
     if (s.W && forward_impl() == 0) {
-        const int tiles_per_inst = (int)((total + 31) / 32);
-        const long long all_tiles = (long long)s.N * tiles_per_inst;
-        const long long want = (all_tiles + kFwdWarps - 1) / kFwdWarps;
-        const int grid = (int)(want < g_fwd_sms ? want : g_fwd_sms);
-        field_forward_mma_kernel<<<grid, kFwdThreads, kFwdSmemBytes, st>>>(s, r, (float4*)field, tiles_per_inst);
+        if (g_fwd_mt == 2) launch_forward_mma<2>(s, r, (float4*)field, total, st);
+        else launch_forward_mma<1>(s, r, (float4*)field, total, st);
     } else {
         const dim3 grid((unsigned)((total + kThreads - 1) / kThreads), (unsigned)s.N);
         if (s.W) field_forward_kernel<true><<<grid, kThreads, 0, st>>>(s, r, (float4*)field);

@@ -112,6 +112,26 @@ __device__ __forceinline__ void mma3_quad(f2 (&x0)[2], f2 (&x1)[2], f2 (&y0)[2],
     mma_tf32(y0, yh, w0h0, w0h1); mma_tf32(y1, yh, w1h0, w1h1);
 }
 
+// Two accumulator tiles sharing one A operand (one m-tile per warp), pass-major.
+template <bool kZero>
+__device__ __forceinline__ void mma3_pair(f2 (&x0)[2], f2 (&x1)[2], const uint32_t (&xh)[4], const uint32_t (&xl)[4],
+                                          const float4& w0, const float4& w1) {
+    const uint32_t w0h0 = __float_as_uint(w0.x), w0h1 = __float_as_uint(w0.y), w0l0 = __float_as_uint(w0.z), w0l1 = __float_as_uint(w0.w);
+    const uint32_t w1h0 = __float_as_uint(w1.x), w1h1 = __float_as_uint(w1.y), w1l0 = __float_as_uint(w1.z), w1l1 = __float_as_uint(w1.w);
+    if (kZero) { mma_tf32_zero(x0, xl, w0h0, w0h1); mma_tf32_zero(x1, xl, w1h0, w1h1); }
+    else { mma_tf32(x0, xl, w0h0, w0h1); mma_tf32(x1, xl, w1h0, w1h1); }
+    mma_tf32(x0, xh, w0l0, w0l1); mma_tf32(x1, xh, w1l0, w1l1);
+    mma_tf32(x0, xh, w0h0, w0h1); mma_tf32(x1, xh, w1h0, w1h1);
+}
+
+// All accumulators [MT][2 n-tiles] of one k-step.
+template <bool kZero, int MT>
+__device__ __forceinline__ void mma3_step(f2 (&acc)[MT][2][2], const uint32_t (&ah)[MT][4], const uint32_t (&al)[MT][4],
+                                          const float4& w0, const float4& w1) {
+    if constexpr (MT == 2) mma3_quad<kZero>(acc[0][0], acc[0][1], acc[1][0], acc[1][1], ah[0], al[0], ah[1], al[1], w0, w1);
+    else mma3_pair<kZero>(acc[0][0], acc[0][1], ah[0], al[0], w0, w1);
+}
+
 // A fragment (hi, lo) of k-step `nt` from an activation tile held in C layout.
 __device__ __forceinline__ void a_from_c(const f2 (&c)[2], uint32_t (&ah)[4], uint32_t (&al)[4]) {
     split(c[0].x, ah[0], al[0]);
@@ -364,16 +384,19 @@ __device__ __forceinline__ void sincos_cw2(f2 x, f2& s, f2& c) {
 // Positional encoding of the warp tile in A-operand form: pairs run over the two rows (g, g + 8) of an
 // m-tile, so cs[mt][c][f] / sn[mt][c][f] ARE the register pairs (a0, a1) / (a2, a3) of k-step 2c + f.
 // Lane t owns frequencies k = t (f = 0) and k = t + 4 (f = 1) of every coordinate c.
-struct Encoding2 {
-    f2 cs[2][3][2];
-    f2 sn[2][3][2];
+template <int MT>
+struct EncodingT {
+    f2 cs[MT][3][2];
+    f2 sn[MT][3][2];
 };
+using Encoding2 = EncodingT<2>;
 
 // a[mt][c] = PE argument fl(pi * u_c) of rows (g, g + 8) of m-tile mt.
-__device__ __forceinline__ void encode2(const f2 (&a)[2][3], int t, Encoding2& e) {
+template <int MT>
+__device__ __forceinline__ void encode2(const f2 (&a)[MT][3], int t, EncodingT<MT>& e) {
     const float f = (float)(1 << t);
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
+    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             f2 sn, cs;
@@ -422,6 +445,26 @@ __device__ __forceinline__ float rows_to_lanes(const float (&v)[4], int lane) {
     const int t = lane & 3;
     const float mine = t == 0 ? v[0] : (t == 1 ? v[1] : (t == 2 ? v[2] : v[3]));
     return __shfl_sync(kFull, mine, 4 * (lane & 7) + (lane >> 3));
+}
+
+// Tiles of 16 * MT rows: row r (= lane, r < 16 MT) lives in quad (r & 7) as slot (r >> 3); pairs are
+// (slot 2 mt, slot 2 mt + 1) = rows (g, g + 8) of m-tile mt.
+template <int MT>
+__device__ __forceinline__ void lanes_to_row_pairs(float x, int lane, f2 (&v)[MT]) {
+    const int g = lane >> 2;
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+        v[mt].x = __shfl_sync(kFull, x, 16 * mt + g);
+        v[mt].y = __shfl_sync(kFull, x, 16 * mt + 8 + g);
+    }
+}
+template <int MT>
+__device__ __forceinline__ float row_slots_to_lanes(const float (&v)[2 * MT], int lane) {
+    const int t = lane & 3;
+    float mine = v[0];
+#pragma unroll
+    for (int s = 1; s < 2 * MT; ++s) mine = (t == s) ? v[s] : mine;
+    return __shfl_sync(kFull, mine, 4 * (lane & 7) + ((lane >> 3) & (2 * MT - 1)));
 }
 
 // The inverse: lane == row holds x; returns x of the 4 rows this lane owns in the fragment layout.
