@@ -34,6 +34,30 @@ extern "C" {
 #define VSRD_MAX_INSTANCES 32
 #define VSRD_MAX_INTERVALS 512
 
+/* Device-resident per-step scalars.  scripts/main.py:420-431 re-derives the union temperature, the SDF
+ * standard deviation and the cosine ratio on the host every step; keeping them (and the sampler seed)
+ * in device memory lets one captured CUDA graph be replayed for every optimisation step.  Wherever a
+ * call accepts a `step_state` DEVICE pointer, a non-NULL value overrides the by-value scalars. */
+typedef struct VsrdStepState {
+    float temperature;            /* sdf_union_temperature                                    */
+    float std_deviation;          /* sdf_std_deviation                                        */
+    float cosine_ratio;           /* step / num_steps                                         */
+    float eikonal_weight;         /* loss weight, 0 while step < warmup_steps (main.py:677)   */
+    uint64_t seed;                /* counter-based generator key of this step                 */
+    int64_t step;
+} VsrdStepState;
+
+/* Host-side description of the schedule (config.json:226-238, optimization.num_steps/warmup_steps). */
+typedef struct VsrdSchedule {
+    int64_t num_steps;
+    int64_t warmup_steps;
+    float max_temperature, min_temperature;
+    float max_std_deviation, min_std_deviation;
+    float eikonal_weight;
+    float _pad;
+    uint64_t seed;
+} VsrdSchedule;
+
 /* Decoded per-frame parameters: what scripts/main.py:530-618 closes over when it composes
  * soft_union(translation(rotation(instance_field(box [+ residual])))). */
 typedef struct VsrdScene {
@@ -45,6 +69,8 @@ typedef struct VsrdScene {
     const float* mlp_weights;     /* [N,NW]  hyper_distance_field(embeddings) or NULL (warm-up)*/
     float temperature;            /* sdf_union_temperature (main.py:422-426)                  */
     float scale;                  /* max(distance_range) (main.py:441)                        */
+    const VsrdStepState* step_state; /* DEVICE pointer or NULL: overrides temperature, std_deviation,
+                                        cosine_ratio and the eikonal weight of the calls below   */
 } VsrdScene;
 
 typedef struct VsrdRays {
@@ -71,6 +97,15 @@ typedef struct VsrdLoss {
     float eikonal_weight;         /* 0 during warm-up                                           */
 } VsrdLoss;
 
+/* The V views of a target frame (target + sources, main.py:339-367). */
+typedef struct VsrdViews {
+    int32_t num_views;            /* V */
+    int32_t target_view;          /* index of relative frame 0 (matching uses this view only)   */
+    int32_t height, width;        /* image size for clip_boxes_to_image                         */
+    const float* extrinsics;      /* [V,4,4] world -> camera                                    */
+    const float* intrinsics;      /* [V,3,3]                                                    */
+} VsrdViews;
+
 int vsrd_version(void);
 const char* vsrd_last_error(void);
 
@@ -91,15 +126,17 @@ int vsrd_gather_rays(const float* inv_projection, const float* camera_positions,
 
 /* ---- a9: quadrature_sampler (vsrd/rendering/samplers.py:5-8) ----------------------------
  * bins[S+1]; jitter[R][S] in [0,1) or NULL to draw from the counter-based generator (seed).
+ * `step_state` (DEVICE pointer or NULL) supplies the seed instead of the by-value one.
  * out distances[R][S]. */
-int vsrd_place_coarse(const float* bins, const float* jitter, uint64_t seed, int num_rays, int num_samples,
-                      float* distances, void* stream);
+int vsrd_place_coarse(const float* bins, const float* jitter, uint64_t seed, const VsrdStepState* step_state,
+                      int num_rays, int num_samples, float* distances, void* stream);
 
 /* ---- a10: inverse_transform_sampler + concat + sort (samplers.py:11-36, renderers.py:196-210)
  * coarse_distances[R][S], coarse_weights[R][S-1]; sorted_uniforms[R][S] or NULL (generator);
  * out distances[R][2S], ascending. */
 int vsrd_place_fine(const float* coarse_distances, const float* coarse_weights, const float* sorted_uniforms,
-                    uint64_t seed, int num_rays, int num_samples, float* distances, void* stream);
+                    uint64_t seed, const VsrdStepState* step_state, int num_rays, int num_samples,
+                    float* distances, void* stream);
 
 /* ---- a5-a8: per-(sample, instance) field: box SDF + residual MLP, value and spatial gradient.
  * out field[N][R*M] as float4 (d_i, dd_i/dx, dd_i/dy, dd_i/dz). */
@@ -130,6 +167,57 @@ int vsrd_composite_backward(const VsrdScene* scene, const VsrdRays* rays, const 
 int vsrd_field_backward(const VsrdScene* scene, const VsrdRays* rays, const float* adjoint, float* partials,
                         float* grad_locations, float* grad_rotations, float* grad_half_extents,
                         float* grad_mlp_weights, void* stream);
+
+/* ---- a14 + a15: multi-view box projection, matching and projection losses, forward and adjoint in
+ * ONE launch (scripts/main.py:339-415; operations/geometric_operations.py:343-389 project_box_3d and
+ * clip_lines_to_front; torchvision clip_boxes_to_image / distance_box_iou / distance_box_iou_loss;
+ * scipy linear_sum_assignment; nn.functional.smooth_l1_loss).
+ *   world_boxes [N,8,3]        detector corners (box_parameters.py:73-91)
+ *   gt_boxes_2d [V,N,4]        x1 y1 x2 y2 per view in TARGET instance order, or NULL: projection only
+ *   visible     [V,N] uint8    source-view visibility of each target instance (main.py:248-251), NULL = all
+ *   fixed_gt_indices [N]       NULL: solve the assignment on -DIoU of the target view; else use these
+ * out boxes_2d [V,N,4] (clipped to the image); gt_indices [N] int64 (ground-truth index matched to
+ * prediction k; pd_indices are 0..N-1 as scipy returns them for a square cost); losses[2] =
+ * (iou_projection_loss, l1_projection_loss) as means over the visible matched pairs;
+ * grad_world_boxes [2,N,8,3] = d losses[k] / d world_boxes (NULL to skip the adjoint).
+ * scratch: vsrd_projection_scratch_floats(V, N) floats. */
+size_t vsrd_projection_scratch_floats(int num_views, int num_instances);
+int vsrd_projection_step(const VsrdViews* views, int num_instances, const float* world_boxes,
+                         const float* gt_boxes_2d, const uint8_t* visible, const int64_t* fixed_gt_indices,
+                         float* boxes_2d, int64_t* gt_indices, float* losses, float* grad_world_boxes,
+                         float* scratch, void* stream);
+
+/* ---- a2: ray selection (scripts/main.py:620-627: torch.multinomial(max_n soft_masks, num_rays, no
+ * replacement) over all V*H*W pixels, every step).  The weights do not change within a frame, so the
+ * max over instances and its inclusive CDF (double) are built once per frame:
+ *   soft_masks [P,N] (P = V*H*W, instance-minor as main.py:300-315 stacks them) -> cdf [P] double;
+ *   scratch: vsrd_ray_cdf_scratch_doubles(P) doubles. */
+size_t vsrd_ray_cdf_scratch_doubles(int64_t num_pixels);
+int vsrd_ray_cdf_build(const float* soft_masks, int64_t num_pixels, int num_instances, double* cdf, double* scratch,
+                       void* stream);
+/* Per step: draws pixels i.i.d. from the CDF and rejects repeats in draw order, which IS sequential
+ * sampling without replacement.  uniforms [max_draws] double in [0,1) or NULL (counter-based generator
+ * keyed by `seed`, or by step_state->seed when step_state is a non-NULL DEVICE pointer).
+ * out pixel_indices [R] int64 in acceptance order; status[0] (device int32, may be NULL) = number of
+ * rays that could NOT be drawn (0 on success; >0 when the uniforms ran out or fewer than R pixels have
+ * non-zero weight, where torch.multinomial raises). */
+int vsrd_select_rays(const double* cdf, int64_t num_pixels, const double* uniforms, int max_draws, uint64_t seed,
+                     const VsrdStepState* step_state, int num_rays, int64_t* pixel_indices, int32_t* status, void* stream);
+/* targets[r][k] = soft_masks[pixel_indices[r]][gt_indices[k]] (main.py:656; gt_indices NULL = identity). */
+int vsrd_gather_targets(const float* soft_masks, const int64_t* pixel_indices, const int64_t* gt_indices,
+                        int num_rays, int num_instances, float* targets, void* stream);
+
+/* ---- soft masks of the synthetic frames (transforms/geometric_transforms.py:267-309 SoftRasterizer):
+ * sigmoid(signed pixel distance to the instance polygon / temperature); polygons [V,N,max_vertices,2]
+ * (x = column, y = row), polygon_sizes [V,N] int32 (< 3: instance absent, mask 0);
+ * out soft_masks [V,H,W,N]. */
+int vsrd_soft_masks(const float* polygons, const int32_t* polygon_sizes, int num_views, int num_instances,
+                    int max_vertices, int height, int width, float temperature, float* soft_masks, void* stream);
+
+/* ---- schedule (scripts/main.py:420-431, 677): set_step >= 0 jumps to that step, < 0 advances by one;
+ * recomputes temperature / std_deviation (cosine annealing), cosine_ratio, the eikonal switch and the
+ * per-step seed in DEVICE memory. */
+int vsrd_step_state_update(VsrdStepState* step_state, const VsrdSchedule* schedule, int64_t set_step, void* stream);
 
 #ifdef __cplusplus
 }

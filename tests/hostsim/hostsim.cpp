@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../vsrd_b200/csrc/vsrd_math.cuh"
+#include "../../vsrd_b200/csrc/vsrd_frame_math.cuh"
 
 using namespace vsrd;
 
@@ -152,6 +153,55 @@ void hs_composite_backward(const float* t, const float* dirs, const float* F, in
             union_backward(load, wbar, store, N, T, us[j], dbar_adj, gbar);
         }
     }
+}
+
+// ---- frame-level rows (vsrd_frame_math.cuh): serial stand-in for projection_step_kernel with the
+// assignment supplied by the caller (the warp-parallel Hungarian solver only exists on the device).
+void hs_projection_step(const float* E, const float* K, const float* world, const float* gt, const uint8_t* visible,
+                        const int64_t* gt_idx, int V, int N, float height, float width,
+                        float* boxes, float* cost, float* losses, float* grad_world /*[2,N,24]*/) {
+    const float eps = 1e-6f;
+    std::vector<BoxProjection> bp((size_t)V * N);
+    for (int v = 0; v < V; ++v)
+        for (int n = 0; n < N; ++n) {
+            project_box(E + 16 * v, K + 9 * v, world + 24 * n, height, width, eps, bp[v * N + n]);
+            for (int k = 0; k < 4; ++k) boxes[(v * N + n) * 4 + k] = bp[v * N + n].box[k];
+        }
+    if (!gt) return;
+    if (cost)   // target view passed as view 0 of `cost` by the caller's choice of pointer offsets
+        for (int a = 0; a < N; ++a)
+            for (int b = 0; b < N; ++b) cost[a * N + b] = -diou_pair(boxes + 4 * a, gt + 4 * b);
+    float iou = 0.0f, l1 = 0.0f, count = 0.0f;
+    std::vector<float> gbox((size_t)V * N * 8, 0.0f);
+    for (int v = 0; v < V; ++v)
+        for (int k = 0; k < N; ++k) {
+            const int g = (int)gt_idx[k];
+            if (visible && !visible[v * N + g]) continue;
+            iou += diou_loss_pair(boxes + (v * N + k) * 4, gt + (v * N + g) * 4, &gbox[(v * N + k) * 8]);
+            l1 += smooth_l1_pair(boxes + (v * N + k) * 4, gt + (v * N + g) * 4, &gbox[(v * N + k) * 8 + 4]);
+            count += 1.0f;
+        }
+    losses[0] = iou / count;
+    losses[1] = l1 / (4.0f * count);
+    for (int i = 0; i < 2 * N * 24; ++i) grad_world[i] = 0.0f;
+    for (int v = 0; v < V; ++v)
+        for (int n = 0; n < N; ++n)
+            for (int which = 0; which < 2; ++which) {
+                float g[4];
+                const float scale = which ? 1.0f / (4.0f * count) : 1.0f / count;
+                for (int c = 0; c < 4; ++c) g[c] = gbox[(v * N + n) * 8 + 4 * which + c] * scale;
+                project_box_backward(E + 16 * v, K + 9 * v, bp[v * N + n], height, width, eps, g,
+                                     grad_world + (which * N + n) * 24);
+            }
+}
+
+void hs_soft_mask(const float* polygon, int count, int H, int W, float temperature, float* signed_distance, float* mask) {
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) {
+            const float d = polygon_signed_distance(polygon, count, (float)x, (float)y);
+            signed_distance[y * W + x] = d;
+            mask[y * W + x] = sigmoidf_(d / temperature);
+        }
 }
 
 }  // extern "C"

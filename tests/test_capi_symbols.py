@@ -29,7 +29,8 @@ def test_header_declares_expected_entry_points():
     names = _declared_functions()
     assert "vsrd_field_forward" in names and "vsrd_field_backward" in names
     assert "vsrd_composite_forward" in names and "vsrd_composite_backward" in names
-    assert len(names) >= 11
+    assert len(names) >= 19
+    assert {'vsrd_projection_step', 'vsrd_select_rays', 'vsrd_ray_cdf_build', 'vsrd_step_state_update'} <= set(names)
 
 
 def test_library_exports_every_declared_symbol(lib):
@@ -47,8 +48,11 @@ def test_version_and_error_string_callable_without_gpu(lib):
 
 def test_struct_layout_matches_header():
     from vsrd_b200 import _lib
-    # VsrdScene: 2 x int32, 4 pointers, 2 floats -> 48 bytes on LP64; VsrdRays: 2 x int32 + 3 pointers
-    assert ctypes.sizeof(_lib.VsrdScene) == 48
+    # VsrdScene: 2 x int32, 4 pointers, 2 floats, 1 pointer -> 56 bytes on LP64; VsrdRays: 2 x int32 + 3 pointers
+    assert ctypes.sizeof(_lib.VsrdScene) == 56
+    assert ctypes.sizeof(_lib.VsrdStepState) == 32
+    assert ctypes.sizeof(_lib.VsrdSchedule) == 48
+    assert ctypes.sizeof(_lib.VsrdViews) == 32
     assert ctypes.sizeof(_lib.VsrdRays) == 32
     assert ctypes.sizeof(_lib.VsrdRenderParams) == 16
     assert ctypes.sizeof(_lib.VsrdLoss) == 16
@@ -62,7 +66,7 @@ def test_struct_layout_matches_header():
 def test_argument_errors_are_reported_without_gpu(lib):
     """Validation happens before any CUDA call, so the error convention is testable on CPU."""
     from vsrd_b200 import _lib
-    scene = _lib.VsrdScene(0, 0, None, None, None, None, 1.0, 100.0)
+    scene = _lib.VsrdScene(0, 0, None, None, None, None, 1.0, 100.0, None)
     rays = _lib.VsrdRays(1, 1, None, None, None)
     status = lib.vsrd_field_forward(ctypes.byref(scene), ctypes.byref(rays), None, None)
     assert status != 0

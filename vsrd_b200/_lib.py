@@ -29,6 +29,44 @@ class VsrdScene(ctypes.Structure):
         ("mlp_weights", ctypes.c_void_p),
         ("temperature", ctypes.c_float),
         ("scale", ctypes.c_float),
+        ("step_state", ctypes.c_void_p),
+    ]
+
+
+class VsrdStepState(ctypes.Structure):
+    """Device-resident per-step scalars (this mirror is used for sizes/offsets and host read-back)."""
+    _fields_ = [
+        ("temperature", ctypes.c_float),
+        ("std_deviation", ctypes.c_float),
+        ("cosine_ratio", ctypes.c_float),
+        ("eikonal_weight", ctypes.c_float),
+        ("seed", ctypes.c_uint64),
+        ("step", ctypes.c_int64),
+    ]
+
+
+class VsrdSchedule(ctypes.Structure):
+    _fields_ = [
+        ("num_steps", ctypes.c_int64),
+        ("warmup_steps", ctypes.c_int64),
+        ("max_temperature", ctypes.c_float),
+        ("min_temperature", ctypes.c_float),
+        ("max_std_deviation", ctypes.c_float),
+        ("min_std_deviation", ctypes.c_float),
+        ("eikonal_weight", ctypes.c_float),
+        ("_pad", ctypes.c_float),
+        ("seed", ctypes.c_uint64),
+    ]
+
+
+class VsrdViews(ctypes.Structure):
+    _fields_ = [
+        ("num_views", ctypes.c_int32),
+        ("target_view", ctypes.c_int32),
+        ("height", ctypes.c_int32),
+        ("width", ctypes.c_int32),
+        ("extrinsics", ctypes.c_void_p),
+        ("intrinsics", ctypes.c_void_p),
     ]
 
 
@@ -69,14 +107,22 @@ SIGNATURES = {
     "vsrd_backward_blocks_per_instance": (_I, [_I, _I, _I]),
     "vsrd_ray_directions": (_I, [_V, _I, _I, _I, _V, _V]),
     "vsrd_gather_rays": (_I, [_V, _V, _V, _I, _I, _I, _I, _V, _V, _V]),
-    "vsrd_place_coarse": (_I, [_V, _V, ctypes.c_uint64, _I, _I, _V, _V]),
-    "vsrd_place_fine": (_I, [_V, _V, _V, ctypes.c_uint64, _I, _I, _V, _V]),
+    "vsrd_place_coarse": (_I, [_V, _V, ctypes.c_uint64, _V, _I, _I, _V, _V]),
+    "vsrd_place_fine": (_I, [_V, _V, _V, ctypes.c_uint64, _V, _I, _I, _V, _V]),
     "vsrd_field_forward": (_I, [_P(VsrdScene), _P(VsrdRays), _V, _V]),
     "vsrd_composite_forward": (_I, [_P(VsrdScene), _P(VsrdRays), _P(VsrdRenderParams), _V, _V, _V, _V,
                                     _P(VsrdLoss), _V, _V]),
     "vsrd_composite_backward": (_I, [_P(VsrdScene), _P(VsrdRays), _P(VsrdRenderParams), _V, _V, _V, _V,
                                      _P(VsrdLoss), _V, _V, _V]),
     "vsrd_field_backward": (_I, [_P(VsrdScene), _P(VsrdRays), _V, _V, _V, _V, _V, _V, _V]),
+    "vsrd_projection_scratch_floats": (ctypes.c_size_t, [_I, _I]),
+    "vsrd_projection_step": (_I, [_P(VsrdViews), _I, _V, _V, _V, _V, _V, _V, _V, _V, _V, _V]),
+    "vsrd_ray_cdf_scratch_doubles": (ctypes.c_size_t, [ctypes.c_int64]),
+    "vsrd_ray_cdf_build": (_I, [_V, ctypes.c_int64, _I, _V, _V, _V]),
+    "vsrd_select_rays": (_I, [_V, ctypes.c_int64, _V, _I, ctypes.c_uint64, _V, _I, _V, _V, _V]),
+    "vsrd_gather_targets": (_I, [_V, _V, _V, _I, _I, _V, _V]),
+    "vsrd_soft_masks": (_I, [_V, _V, _I, _I, _I, _I, _I, ctypes.c_float, _V, _V]),
+    "vsrd_step_state_update": (_I, [_V, _P(VsrdSchedule), ctypes.c_int64, _V]),
 }
 
 _lib = None

@@ -37,6 +37,7 @@ struct SceneDev {
     const float* W;
     float T;
     float scale;
+    const VsrdStepState* state;   // device-resident schedule overriding T (and the render scalars) or NULL
 };
 
 struct RaysDev {
@@ -79,9 +80,9 @@ inline int check_scene(const VsrdScene* s, SceneDev& d) {
     VSRD_CHECK_ARG(s != nullptr, "scene is NULL");
     VSRD_CHECK_ARG(s->num_instances >= 1 && s->num_instances <= VSRD_MAX_INSTANCES, "num_instances must be in [1, 32]");
     VSRD_CHECK_ARG(s->locations && s->rotations && s->half_extents, "scene pointers must not be NULL");
-    VSRD_CHECK_ARG(s->temperature > 0.0f, "temperature must be positive");
+    VSRD_CHECK_ARG(s->step_state != nullptr || s->temperature > 0.0f, "temperature must be positive");
     VSRD_CHECK_ARG(s->scale > 0.0f, "scale must be positive");
-    d = SceneDev{s->num_instances, s->locations, s->rotations, s->half_extents, s->mlp_weights, s->temperature, s->scale};
+    d = SceneDev{s->num_instances, s->locations, s->rotations, s->half_extents, s->mlp_weights, s->temperature, s->scale, s->step_state};
     return 0;
 }
 

@@ -73,7 +73,8 @@ __device__ __forceinline__ float uniform01(uint64_t seed, uint32_t stream, uint3
 // a9: stratified placement
 // =============================================================================================
 __global__ void place_coarse_kernel(const float* __restrict__ bins, const float* __restrict__ jitter, uint64_t seed,
-                                    int R, int S, float* __restrict__ out) {
+                                    const VsrdStepState* __restrict__ state, int R, int S, float* __restrict__ out) {
+    if (state != nullptr) seed = state->seed;
     const size_t total = (size_t)R * S;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         const int j = (int)(idx % S);
@@ -99,8 +100,9 @@ __device__ __forceinline__ int upper_bound_f(const float* a, int n, float v) {  
 
 __global__ void __launch_bounds__(kThreads) place_fine_kernel(
         const float* __restrict__ coarse_t, const float* __restrict__ coarse_w, const float* __restrict__ uniforms,
-        uint64_t seed, int R, int S, float* __restrict__ out) {
+        uint64_t seed, const VsrdStepState* __restrict__ state, int R, int S, float* __restrict__ out) {
     extern __shared__ float smem[];
+    if (state != nullptr) seed = state->seed;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r = blockIdx.x * kWarps + warp;
     if (r >= R) return;
@@ -217,7 +219,11 @@ __global__ void __launch_bounds__(VSRD_MAX_INTERVALS) composite_forward_kernel(
     const int r = blockIdx.x;
     const int N = scene.N, M = rays.M;
     const size_t stride = (size_t)rays.R * M;
-    const float T = scene.T;
+    float T = scene.T;
+    if (scene.state != nullptr) {     // device-resident schedule (graph replay across optimisation steps)
+        T = scene.state->temperature; sigma = scene.state->std_deviation; rho = scene.state->cosine_ratio;
+        loss.eik_w = scene.state->eikonal_weight;
+    }
     const int j = threadIdx.x;
     const bool valid = j < M;
     const size_t idx = (size_t)r * M + (valid ? j : 0);
@@ -295,7 +301,11 @@ __global__ void __launch_bounds__(VSRD_MAX_INTERVALS) composite_backward_kernel(
     const int r = blockIdx.x;
     const int N = scene.N, M = rays.M;
     const size_t stride = (size_t)rays.R * M;
-    const float T = scene.T;
+    float T = scene.T;
+    if (scene.state != nullptr) {     // device-resident schedule (graph replay across optimisation steps)
+        T = scene.state->temperature; sigma = scene.state->std_deviation; rho = scene.state->cosine_ratio;
+        loss.eik_w = scene.state->eikonal_weight;
+    }
     const bool fused = loss.targets != nullptr;
     const float eik_scale = fused ? loss.eik_w * 2.0f / ((float)rays.R * (float)M) : 0.0f;
 
@@ -410,28 +420,29 @@ int vsrd_gather_rays(const float* inv_projection, const float* camera_positions,
     return 0;
 }
 
-int vsrd_place_coarse(const float* bins, const float* jitter, uint64_t seed, int num_rays, int num_samples,
-                      float* distances, void* stream) {
+int vsrd_place_coarse(const float* bins, const float* jitter, uint64_t seed, const VsrdStepState* step_state,
+                      int num_rays, int num_samples, float* distances, void* stream) {
     VSRD_CHECK_ARG(bins && distances, "NULL pointer");
     VSRD_CHECK_ARG(num_rays >= 0 && num_samples >= 1, "bad size");
     const size_t total = (size_t)num_rays * num_samples;
     if (total == 0) return 0;
     if (render_setup()) return 1;
     const size_t want = (total + 255) / 256, cap = (size_t)g_num_sms_render * 16;
-    place_coarse_kernel<<<(int)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(bins, jitter, seed, num_rays, num_samples, distances);
+    place_coarse_kernel<<<(int)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(bins, jitter, seed, step_state, num_rays, num_samples, distances);
     VSRD_CHECK_LAUNCH();
     return 0;
 }
 
 int vsrd_place_fine(const float* coarse_distances, const float* coarse_weights, const float* sorted_uniforms,
-                    uint64_t seed, int num_rays, int num_samples, float* distances, void* stream) {
+                    uint64_t seed, const VsrdStepState* step_state, int num_rays, int num_samples,
+                    float* distances, void* stream) {
     VSRD_CHECK_ARG(coarse_distances && coarse_weights && distances, "NULL pointer");
     VSRD_CHECK_ARG(num_rays >= 0, "bad size");
     VSRD_CHECK_ARG(num_samples >= 2 && 2 * num_samples - 1 <= VSRD_MAX_INTERVALS, "num_samples must be in [2, 256]");
     if (num_rays == 0) return 0;
     const size_t smem = (size_t)kWarps * 4 * num_samples * sizeof(float);
     place_fine_kernel<<<(num_rays + kWarps - 1) / kWarps, kThreads, smem, (cudaStream_t)stream>>>(
-        coarse_distances, coarse_weights, sorted_uniforms, seed, num_rays, num_samples, distances);
+        coarse_distances, coarse_weights, sorted_uniforms, seed, step_state, num_rays, num_samples, distances);
     VSRD_CHECK_LAUNCH();
     return 0;
 }
@@ -442,7 +453,7 @@ int vsrd_composite_forward(const VsrdScene* scene, const VsrdRays* rays, const V
     SceneDev s; RaysDev r;
     if (check_scene(scene, s) || check_rays(rays, r)) return 1;
     VSRD_CHECK_ARG(params != nullptr, "params is NULL");
-    VSRD_CHECK_ARG(params->std_deviation > 0.0f, "std_deviation must be positive");
+    VSRD_CHECK_ARG(s.state != nullptr || params->std_deviation > 0.0f, "std_deviation must be positive");
     VSRD_CHECK_ARG(field && labels && gradients && weights, "NULL pointer");
     if (r.R == 0) return 0;
     LossDev l{nullptr, 0.0f, 0.0f};
@@ -469,7 +480,7 @@ int vsrd_composite_backward(const VsrdScene* scene, const VsrdRays* rays, const 
     SceneDev s; RaysDev r;
     if (check_scene(scene, s) || check_rays(rays, r)) return 1;
     VSRD_CHECK_ARG(params != nullptr, "params is NULL");
-    VSRD_CHECK_ARG(params->std_deviation > 0.0f, "std_deviation must be positive");
+    VSRD_CHECK_ARG(s.state != nullptr || params->std_deviation > 0.0f, "std_deviation must be positive");
     VSRD_CHECK_ARG(field && adjoint, "NULL pointer");
     if (r.R == 0) return 0;
     LossDev l{nullptr, 0.0f, 0.0f};

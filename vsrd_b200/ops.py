@@ -12,7 +12,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import VsrdLoss, VsrdRays, VsrdRenderParams, VsrdScene
+from ._lib import VsrdLoss, VsrdRays, VsrdRenderParams, VsrdSchedule, VsrdScene, VsrdStepState, VsrdViews
 
 MLP_WEIGHTS = _lib.MLP_WEIGHTS
 GRAD_STRIDE = _lib.GRAD_STRIDE
@@ -39,7 +39,7 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 class SceneArgs:
     """Keeps the tensors alive and exposes the C struct."""
 
-    def __init__(self, locations, rotations, half_extents, mlp_weights, temperature, scale=100.0):
+    def __init__(self, locations, rotations, half_extents, mlp_weights, temperature, scale=100.0, step_state=None):
         self.locations = _f32(locations, "locations").reshape(-1, 3)
         n = self.locations.shape[0]
         self.rotations = _f32(rotations, "rotations").reshape(n, 3, 3)
@@ -56,8 +56,10 @@ class SceneArgs:
         self.num_instances = n
         self.temperature = float(temperature)
         self.scale = float(scale)
+        self.step_state = step_state          # StepState or None: device-resident schedule overrides the scalars
         self.struct = VsrdScene(n, 0, _ptr(self.locations), _ptr(self.rotations), _ptr(self.half_extents),
-                                _ptr(self.mlp_weights), self.temperature, self.scale)
+                                _ptr(self.mlp_weights), self.temperature, self.scale,
+                                None if step_state is None else step_state.ptr)
 
 
 class RayArgs:
@@ -74,6 +76,10 @@ class RayArgs:
         if self.num_intervals > _lib.MAX_INTERVALS:
             raise RuntimeError(f"vsrd_b200: at most {_lib.MAX_INTERVALS} intervals per ray, got {self.num_intervals}")
         self.struct = VsrdRays(r, self.num_intervals, _ptr(self.origins), _ptr(self.directions), _ptr(self.distances))
+
+
+def _state_ptr(step_state) -> Optional[int]:
+    return None if step_state is None else step_state.ptr
 
 
 def _params(std_deviation, cosine_ratio, epsilon) -> VsrdRenderParams:
@@ -114,17 +120,20 @@ def gather_rays(inv_projection, camera_positions, pixel_indices, height, width) 
 
 # ---- a9 / a10 ---------------------------------------------------------------------------------
 
-def place_coarse(bins: torch.Tensor, num_rays: int, jitter: Optional[torch.Tensor] = None, seed: int = 0) -> torch.Tensor:
+def place_coarse(bins: torch.Tensor, num_rays: int, jitter: Optional[torch.Tensor] = None, seed: int = 0,
+                 step_state=None) -> torch.Tensor:
     bins = _f32(bins, "bins").reshape(-1)
     s = bins.numel() - 1
     if jitter is not None:
         jitter = _f32(jitter, "jitter").reshape(num_rays, s)
     out = torch.empty(num_rays, s, device=bins.device, dtype=torch.float32)
-    _lib.check(_lib.load().vsrd_place_coarse(_ptr(bins), _ptr(jitter), seed & (2 ** 64 - 1), num_rays, s, _ptr(out), _stream()))
+    _lib.check(_lib.load().vsrd_place_coarse(_ptr(bins), _ptr(jitter), seed & (2 ** 64 - 1), _state_ptr(step_state),
+                                             num_rays, s, _ptr(out), _stream()))
     return out
 
 
-def place_fine(coarse_distances, coarse_weights, sorted_uniforms: Optional[torch.Tensor] = None, seed: int = 0) -> torch.Tensor:
+def place_fine(coarse_distances, coarse_weights, sorted_uniforms: Optional[torch.Tensor] = None, seed: int = 0,
+               step_state=None) -> torch.Tensor:
     t = _f32(coarse_distances, "coarse_distances")
     w = _f32(coarse_weights, "coarse_weights")
     r, s = t.shape
@@ -133,7 +142,8 @@ def place_fine(coarse_distances, coarse_weights, sorted_uniforms: Optional[torch
     if sorted_uniforms is not None:
         sorted_uniforms = _f32(sorted_uniforms, "sorted_uniforms").reshape(r, s)
     out = torch.empty(r, 2 * s, device=t.device, dtype=torch.float32)
-    _lib.check(_lib.load().vsrd_place_fine(_ptr(t), _ptr(w), _ptr(sorted_uniforms), seed & (2 ** 64 - 1), r, s, _ptr(out), _stream()))
+    _lib.check(_lib.load().vsrd_place_fine(_ptr(t), _ptr(w), _ptr(sorted_uniforms), seed & (2 ** 64 - 1),
+                                           _state_ptr(step_state), r, s, _ptr(out), _stream()))
     return out
 
 
@@ -204,3 +214,140 @@ def field_backward(scene: SceneArgs, rays: RayArgs, adjoint: torch.Tensor):
         ctypes.byref(scene.struct), ctypes.byref(rays.struct), _ptr(adjoint), _ptr(partials),
         _ptr(g_loc), _ptr(g_rot), _ptr(g_dim), _ptr(g_w), _stream()))
     return g_loc, g_rot, g_dim, g_w
+
+
+# ---- device-resident schedule -------------------------------------------------------------------
+
+class StepState:
+    """`VsrdStepState` in device memory plus the host-side `VsrdSchedule` that drives it
+    (scripts/main.py:420-431, 677).  `advance()` / `set_step()` enqueue a one-thread kernel, so they can
+    be captured into the same CUDA graph as the step they parameterise."""
+
+    def __init__(self, *, num_steps: int, warmup_steps: int = 0, temperature=(1.0, 0.1), std_deviation=(1.0, 0.1),
+                 eikonal_weight: float = 0.01, seed: int = 0, device="cuda"):
+        self.schedule = VsrdSchedule(int(num_steps), int(warmup_steps), float(temperature[0]), float(temperature[1]),
+                                     float(std_deviation[0]), float(std_deviation[1]), float(eikonal_weight), 0.0,
+                                     int(seed) & (2 ** 64 - 1))
+        self.buffer = torch.zeros(ctypes.sizeof(VsrdStepState), dtype=torch.uint8, device=device)
+        self.set_step(0)
+
+    @property
+    def ptr(self) -> int:
+        return self.buffer.data_ptr()
+
+    def set_step(self, step: int) -> None:
+        _lib.check(_lib.load().vsrd_step_state_update(self.ptr, ctypes.byref(self.schedule), int(step), _stream()))
+
+    def advance(self) -> None:
+        _lib.check(_lib.load().vsrd_step_state_update(self.ptr, ctypes.byref(self.schedule), -1, _stream()))
+
+    def read(self) -> dict:
+        """Host copy (synchronises); for tests and logging only."""
+        raw = bytes(self.buffer.cpu().numpy().tobytes())
+        st = VsrdStepState.from_buffer_copy(raw)
+        return dict(temperature=st.temperature, std_deviation=st.std_deviation, cosine_ratio=st.cosine_ratio,
+                    eikonal_weight=st.eikonal_weight, seed=st.seed, step=st.step)
+
+
+# ---- a14 / a15: projection, matching, projection losses -----------------------------------------
+
+class ViewArgs:
+    def __init__(self, extrinsics, intrinsics, image_size, target_view: int):
+        self.extrinsics = _f32(extrinsics, "extrinsic_matrices").reshape(-1, 4, 4)
+        v = self.extrinsics.shape[0]
+        self.intrinsics = _f32(intrinsics, "intrinsic_matrices").reshape(v, 3, 3)
+        self.num_views, self.target_view = v, int(target_view)
+        self.height, self.width = int(image_size[0]), int(image_size[1])
+        self.struct = VsrdViews(v, self.target_view, self.height, self.width, _ptr(self.extrinsics), _ptr(self.intrinsics))
+
+
+def projection_step(views: ViewArgs, world_boxes, gt_boxes_2d=None, visible=None, fixed_gt_indices=None,
+                    need_grad: bool = True):
+    """world_boxes [N,8,3] -> boxes_2d [V,N,4]; with gt_boxes_2d [V,N,4] also (gt_indices [N] int64,
+    losses [2], grad_world_boxes [2,N,8,3] or None)."""
+    wb = _f32(world_boxes, "world_boxes").reshape(-1, 8, 3)
+    n, v, dev = wb.shape[0], views.num_views, wb.device
+    boxes = torch.empty(v, n, 4, device=dev, dtype=torch.float32)
+    if gt_boxes_2d is None:
+        _lib.check(_lib.load().vsrd_projection_step(ctypes.byref(views.struct), n, _ptr(wb), None, None, None,
+                                                    _ptr(boxes), None, None, None, None, _stream()))
+        return boxes
+    gt = _f32(gt_boxes_2d, "gt_boxes_2d").reshape(v, n, 4)
+    if visible is not None:
+        if visible.dtype not in (torch.uint8, torch.bool) or not visible.is_cuda:
+            raise RuntimeError("vsrd_b200: visible must be a CUDA bool/uint8 tensor")
+        visible = visible.to(torch.uint8).contiguous().reshape(v, n)
+    if fixed_gt_indices is not None:
+        if fixed_gt_indices.dtype != torch.int64 or not fixed_gt_indices.is_cuda:
+            raise RuntimeError("vsrd_b200: fixed_gt_indices must be a CUDA int64 tensor")
+        fixed_gt_indices = fixed_gt_indices.contiguous().reshape(n)
+    gt_indices = torch.empty(n, device=dev, dtype=torch.int64)
+    losses = torch.empty(2, device=dev, dtype=torch.float32)
+    grad = torch.empty(2, n, 8, 3, device=dev, dtype=torch.float32) if need_grad else None
+    scratch = torch.empty(_lib.load().vsrd_projection_scratch_floats(v, n), device=dev, dtype=torch.float32)
+    _lib.check(_lib.load().vsrd_projection_step(
+        ctypes.byref(views.struct), n, _ptr(wb), _ptr(gt), _ptr(visible), _ptr(fixed_gt_indices),
+        _ptr(boxes), _ptr(gt_indices), _ptr(losses), _ptr(grad), _ptr(scratch), _stream()))
+    return boxes, gt_indices, losses, grad
+
+
+# ---- a2: ray selection ---------------------------------------------------------------------------
+
+def ray_cdf_build(soft_masks: torch.Tensor) -> torch.Tensor:
+    """soft_masks [..., N] (flattened to [P,N]) -> inclusive CDF [P] (float64) of max_n soft_masks."""
+    m = _f32(soft_masks, "soft_masks")
+    n = m.shape[-1]
+    m = m.reshape(-1, n)
+    p = m.shape[0]
+    cdf = torch.empty(p, device=m.device, dtype=torch.float64)
+    scratch = torch.empty(_lib.load().vsrd_ray_cdf_scratch_doubles(p), device=m.device, dtype=torch.float64)
+    _lib.check(_lib.load().vsrd_ray_cdf_build(_ptr(m), p, n, _ptr(cdf), _ptr(scratch), _stream()))
+    return cdf
+
+
+def select_rays(cdf: torch.Tensor, num_rays: int, uniforms: Optional[torch.Tensor] = None, seed: int = 0,
+                step_state=None, status: Optional[torch.Tensor] = None):
+    """Weighted draw of `num_rays` distinct pixels (scripts/main.py:620-627).  Returns (indices [R] int64,
+    status [1] int32 on the device: 0 = ok, else the number of rays that could not be drawn)."""
+    if not cdf.is_cuda or cdf.dtype != torch.float64:
+        raise RuntimeError("vsrd_b200: cdf must be a CUDA float64 tensor (ops.ray_cdf_build)")
+    cdf = cdf.contiguous()
+    draws = 0
+    if uniforms is not None:
+        if not uniforms.is_cuda or uniforms.dtype != torch.float64:
+            raise RuntimeError("vsrd_b200: uniforms must be a CUDA float64 tensor")
+        uniforms = uniforms.contiguous().reshape(-1)
+        draws = uniforms.numel()
+    out = torch.empty(num_rays, device=cdf.device, dtype=torch.int64)
+    if status is None:
+        status = torch.zeros(1, device=cdf.device, dtype=torch.int32)
+    _lib.check(_lib.load().vsrd_select_rays(_ptr(cdf), cdf.numel(), _ptr(uniforms), draws, seed & (2 ** 64 - 1),
+                                            _state_ptr(step_state), num_rays, _ptr(out), _ptr(status), _stream()))
+    return out, status
+
+
+def gather_targets(soft_masks: torch.Tensor, pixel_indices: torch.Tensor, gt_indices: Optional[torch.Tensor] = None):
+    m = _f32(soft_masks, "soft_masks")
+    n = m.shape[-1]
+    m = m.reshape(-1, n)
+    if pixel_indices.dtype != torch.int64 or not pixel_indices.is_cuda:
+        raise RuntimeError("vsrd_b200: pixel_indices must be a CUDA int64 tensor")
+    pix = pixel_indices.contiguous().reshape(-1)
+    if gt_indices is not None:
+        gt_indices = gt_indices.contiguous().reshape(n)
+    out = torch.empty(pix.numel(), n, device=m.device, dtype=torch.float32)
+    _lib.check(_lib.load().vsrd_gather_targets(_ptr(m), _ptr(pix), _ptr(gt_indices), pix.numel(), n, _ptr(out), _stream()))
+    return out
+
+
+def soft_masks(polygons: torch.Tensor, polygon_sizes: torch.Tensor, image_size, temperature: float = 10.0):
+    """polygons [V,N,PV,2] (x, y pixel coordinates), polygon_sizes [V,N] int32 -> soft masks [V,H,W,N]."""
+    poly = _f32(polygons, "polygons")
+    v, n, pv, _ = poly.shape
+    if polygon_sizes.dtype != torch.int32 or not polygon_sizes.is_cuda:
+        raise RuntimeError("vsrd_b200: polygon_sizes must be a CUDA int32 tensor")
+    sizes = polygon_sizes.contiguous().reshape(v, n)
+    h, w = int(image_size[0]), int(image_size[1])
+    out = torch.empty(v, h, w, n, device=poly.device, dtype=torch.float32)
+    _lib.check(_lib.load().vsrd_soft_masks(_ptr(poly), _ptr(sizes), v, n, pv, h, w, float(temperature), _ptr(out), _stream()))
+    return out
