@@ -22,9 +22,9 @@ class _RenderPass(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, locations, rotations, half_extents, mlp_weights, origins, directions, distances,
-                temperature, scale, std_deviation, cosine_ratio, epsilon):
+                temperature, scale, std_deviation, cosine_ratio, epsilon, step_state=None):
         scene = SceneArgs(locations.detach(), rotations.detach(), half_extents.detach(),
-                          None if mlp_weights is None else mlp_weights.detach(), temperature, scale)
+                          None if mlp_weights is None else mlp_weights.detach(), temperature, scale, step_state)
         rays = RayArgs(origins.detach(), directions.detach(), distances.detach())
         field = ops.field_forward(scene, rays)
         labels, grads, weights, _ = ops.composite_forward(scene, rays, field, std_deviation, cosine_ratio, epsilon)
@@ -40,22 +40,23 @@ class _RenderPass(torch.autograd.Function):
                                          grad_labels=grad_labels, grad_gradients=grad_gradients,
                                          grad_weights=grad_weights)
         g_loc, g_rot, g_dim, g_w = ops.field_backward(ctx.scene, ctx.rays, adjoint)
-        return g_loc, g_rot, g_dim, (g_w if ctx.has_mlp else None), None, None, None, None, None, None, None, None
+        return g_loc, g_rot, g_dim, (g_w if ctx.has_mlp else None), None, None, None, None, None, None, None, None, None
 
 
 def render_pass(locations, rotations, half_extents, mlp_weights, ray_positions, ray_directions, distances, *,
                 temperature: float, std_deviation: float, cosine_ratio: float = 1.0, epsilon: float = 1e-6,
-                scale: float = 100.0):
+                scale: float = 100.0, step_state=None):
     """Union field + SDF->opacity + compositing at the given sample distances.
 
     locations [N,3], rotations [N,3,3], half_extents [N,3], mlp_weights [N,1617] or None,
     ray_positions [R,3] (or [3]), ray_directions [R,3], distances [R,M+1] (ascending, detached).
     Returns labels [R,N], gradients [R,M,3] (un-normalised union gradient), weights [R,M];
-    differentiable w.r.t. the first four arguments.
+    differentiable w.r.t. the first four arguments.  `step_state` (ops.StepState) makes the kernels read
+    temperature / std_deviation / cosine_ratio from device memory instead (CUDA-graph replay across steps).
     """
     return _RenderPass.apply(locations, rotations, half_extents, mlp_weights, ray_positions, ray_directions,
                              distances, float(temperature), float(scale), float(std_deviation),
-                             float(cosine_ratio), float(epsilon))
+                             float(cosine_ratio), float(epsilon), step_state)
 
 
 def distance_bins(distance_range: Sequence[float], num_samples: int, device) -> torch.Tensor:
@@ -95,9 +96,10 @@ class _FusedRenderLoss(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, locations, rotations, half_extents, mlp_weights, origins, directions, distances, targets,
-                temperature, scale, std_deviation, cosine_ratio, epsilon, silhouette_weight, eikonal_weight):
+                temperature, scale, std_deviation, cosine_ratio, epsilon, silhouette_weight, eikonal_weight,
+                step_state=None):
         scene = SceneArgs(locations.detach(), rotations.detach(), half_extents.detach(),
-                          None if mlp_weights is None else mlp_weights.detach(), temperature, scale)
+                          None if mlp_weights is None else mlp_weights.detach(), temperature, scale, step_state)
         rays = RayArgs(origins.detach(), directions.detach(), distances.detach())
         field = ops.field_forward(scene, rays)
         labels, _, _, loss_parts = ops.composite_forward(
@@ -118,37 +120,39 @@ class _FusedRenderLoss(torch.autograd.Function):
         g_loc, g_rot, g_dim, g_w = ops.field_backward(ctx.scene, ctx.rays, adjoint)
         scale = grad_loss
         return (g_loc * scale, g_rot * scale, g_dim * scale, (g_w * scale if ctx.has_mlp else None),
-                None, None, None, None, None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None, None, None, None, None)
 
 
 def fused_render_loss(locations, rotations, half_extents, mlp_weights, ray_positions, ray_directions, distances,
                       targets, *, temperature: float, std_deviation: float, cosine_ratio: float = 1.0,
                       epsilon: float = 1e-6, scale: float = 100.0, silhouette_weight: float = 1.0,
-                      eikonal_weight: float = 0.01):
+                      eikonal_weight: float = 0.01, step_state=None):
     """loss = silhouette_weight * mean BCE(clamp(labels, 1e-6, 1-1e-6), targets)
             + eikonal_weight * mean((|grad| - 1)^2), computed inside the compositing kernel.
     Returns (loss, labels [R,N], loss_parts [2])."""
     return _FusedRenderLoss.apply(locations, rotations, half_extents, mlp_weights, ray_positions, ray_directions,
                                   distances, targets, float(temperature), float(scale), float(std_deviation),
-                                  float(cosine_ratio), float(epsilon), float(silhouette_weight), float(eikonal_weight))
+                                  float(cosine_ratio), float(epsilon), float(silhouette_weight), float(eikonal_weight),
+                                  step_state)
 
 
 def render_step(locations, rotations, half_extents, mlp_weights, ray_positions, ray_directions, targets, *,
                 bins: torch.Tensor, temperature: float, std_deviation: float, cosine_ratio: float,
                 epsilon: float = 1e-6, scale: float = 100.0, silhouette_weight: float = 1.0,
-                eikonal_weight: Optional[float] = None, jitter=None, sorted_uniforms=None, seed: int = 0):
+                eikonal_weight: Optional[float] = None, jitter=None, sorted_uniforms=None, seed: int = 0,
+                step_state=None):
     """One renderer step of the optimisation loop (scripts/main.py:629-687): coarse pass, resampling,
     fine pass and the fused loss.  Returns (loss, labels, loss_parts)."""
     if eikonal_weight is None:
         eikonal_weight = 0.01 if mlp_weights is not None else 0.0   # main.py:677: only with the residual field
     num_rays = ray_directions.reshape(-1, 3).shape[0]
     kw = dict(temperature=temperature, std_deviation=std_deviation, cosine_ratio=cosine_ratio,
-              epsilon=epsilon, scale=scale)
+              epsilon=epsilon, scale=scale, step_state=step_state)
     with torch.no_grad():
-        coarse = ops.place_coarse(bins, num_rays, jitter, seed)
+        coarse = ops.place_coarse(bins, num_rays, jitter, seed, step_state)
         _, _, coarse_w = render_pass(locations, rotations, half_extents, mlp_weights, ray_positions,
                                      ray_directions, coarse, **kw)
-        fine = ops.place_fine(coarse, coarse_w, sorted_uniforms, seed)
+        fine = ops.place_fine(coarse, coarse_w, sorted_uniforms, seed, step_state)
     return fused_render_loss(locations, rotations, half_extents, mlp_weights, ray_positions, ray_directions,
                              fine, targets, silhouette_weight=silhouette_weight,
                              eikonal_weight=eikonal_weight, **kw)
