@@ -1,0 +1,88 @@
+"""Frame-parallel driver on CPU: the partitioner against torch's DistributedSampler (what the reference's
+DistributedDataLoader uses, vsrd/distributed/loader.py:6-9) and the final label gather on a 2-rank gloo world."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+from torch.utils.data.distributed import DistributedSampler
+
+from vsrd_b200 import sequence
+
+
+@pytest.mark.parametrize("num_frames,world", [(10, 2), (2562, 8), (7, 4), (3, 8), (1, 1), (64, 8)])
+@pytest.mark.parametrize("shuffle", [True, False])
+def test_partition_matches_distributed_sampler(num_frames, world, shuffle):
+    dataset = list(range(num_frames))
+    seen = []
+    for rank in range(world):
+        ref = list(DistributedSampler(dataset, num_replicas=world, rank=rank, shuffle=shuffle, seed=0))
+        got = sequence.partition_frames(num_frames, rank, world, seed=0, shuffle=shuffle)
+        assert got == ref
+        seen += sequence.partition_frames(num_frames, rank, world, seed=0, shuffle=shuffle, drop_duplicates=True)
+    assert sorted(seen) == dataset            # without the wrap-around repeats: every frame exactly once
+
+
+def test_partition_edge_cases():
+    assert sequence.partition_frames(0, 0, 4) == []
+    with pytest.raises(ValueError):
+        sequence.partition_frames(4, 4, 4)
+    # survey probe: 10 frames on 2 ranks
+    assert sequence.partition_frames(10, 0, 2) == [4, 7, 3, 0, 6]
+    assert sequence.partition_frames(10, 1, 2) == [1, 5, 9, 8, 2]
+
+
+def test_label_frames_skips_done_and_validates():
+    calls = []
+
+    def label_one(fid):
+        calls.append(fid)
+        return dict(boxes_3d=torch.full((2, 8, 3), float(fid)))
+
+    done = {3: dict(boxes_3d=torch.zeros(1, 8, 3))}
+    out = sequence.label_frames([1, 3, 5], label_one, done=done)
+    assert calls == [1, 5] and sorted(out) == [1, 3, 5]
+    with pytest.raises(RuntimeError):
+        sequence.label_frames([0], lambda f: dict(boxes_3d=torch.zeros(2, 4, 3)))
+    assert {k: v.shape for k, v in sequence.gather_labels(out).items()} == {1: (2, 8, 3), 3: (1, 8, 3), 5: (2, 8, 3)}
+
+
+def _fake_boxes(fid):
+    n = 1 + fid % 5                               # ragged instance counts
+    g = torch.Generator().manual_seed(fid)
+    return torch.rand(n, 8, 3, generator=g) * 50.0
+
+
+def _worker(rank, world, port, num_frames, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        labelled = []
+
+        def label_one(fid):
+            labelled.append(fid)
+            return dict(boxes_3d=_fake_boxes(fid))
+
+        merged = sequence.label_sequence(num_frames, label_one, seed=0)
+        ret[rank] = (labelled, {k: v.clone() for k, v in merged.items()})
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("num_frames", [7, 1])
+def test_two_rank_gloo_label_gather(num_frames):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    manager = mp.Manager()
+    ret = manager.dict()
+    mp.spawn(_worker, args=(2, port, num_frames, ret), nprocs=2, join=True)
+    (l0, m0), (l1, m1) = ret[0], ret[1]
+    assert sorted(l0 + l1) == list(range(num_frames))                  # each frame labelled exactly once
+    assert l0 == sequence.partition_frames(num_frames, 0, 2, drop_duplicates=True)
+    for merged in (m0, m1):                                            # every rank holds every frame's boxes
+        assert sorted(merged) == list(range(num_frames))
+        for fid, boxes in merged.items():
+            assert torch.equal(boxes, _fake_boxes(fid))

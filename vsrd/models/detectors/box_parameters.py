@@ -15,6 +15,18 @@ _CORNERS = (
 )
 
 
+_corner_cache = {}
+
+
+def _corner_signs(like):
+    """The corner sign table on `like`'s device/dtype, uploaded once (a host->device copy per call would
+    break CUDA-graph capture of the optimisation step)."""
+    key = (like.device, like.dtype)
+    if key not in _corner_cache:
+        _corner_cache[key] = torch.tensor(_CORNERS, device=like.device, dtype=like.dtype)
+    return _corner_cache[key]
+
+
 def rotation_matrix_y(cos, sin):
     zero, one = torch.zeros_like(cos), torch.ones_like(cos)
     rows = [
@@ -60,7 +72,7 @@ class BoxParameters3D(nn.Module):
 
     @staticmethod
     def decode_box_3d(locations, dimensions, orientations):
-        corners = dimensions.new_tensor(_CORNERS) * dimensions.unsqueeze(-2)
+        corners = _corner_signs(dimensions) * dimensions.unsqueeze(-2)
         return corners @ orientations.transpose(-2, -1) + locations.unsqueeze(-2)
 
     @staticmethod

@@ -1,0 +1,262 @@
+"""Per-frame auto-labeling loop on the B200 kernels: what `scripts/main.py:train()` does for ONE target
+frame (main.py:106-865), device-resident.
+
+The reference runs, per optimisation step, ~21 k ATen calls, 136 Python projection calls, a scipy
+assignment on the host and a 9 M-way multinomial.  Here one step is
+
+    schedule (1 thread)  ->  BoxParameters3D decode (PyTorch, [N,.] tensors)  ->  projection + matching +
+    projection losses (1 launch)  ->  ray draw + target gather + ray generation (3 launches)  ->
+    hypernetwork (PyTorch/cuBLAS, after warm-up)  ->  coarse pass, resampling, fine pass with the fused
+    silhouette/eikonal loss (6 launches)  ->  autograd backward (compositing + field adjoint kernels, then
+    PyTorch through the decode / hypernetwork)  ->  Adam
+
+with no host synchronisation, so the whole step (forward, backward, optimizer) is captured once into a
+CUDA graph per phase (warm-up: box only; main: box + residual field) and replayed for the remaining
+steps.  Every per-step scalar (annealed temperature / std deviation, cosine ratio, eikonal switch,
+sampler seed, learning-rate decay) lives in device memory (`ops.StepState`).
+
+Losses and weights: main.py:653-687, 391-415, 855 and config.json:120-127; optimizer and scheduler:
+config.json:177-215 (Adam, five groups, ExponentialLR with gamma = 0.01 ** (1 / num_steps)).
+"""
+from __future__ import annotations
+
+import dataclasses
+import math
+from typing import Dict, Optional
+
+import torch
+
+from . import functional as F
+from . import ops
+
+LOSS_WEIGHTS = dict(silhouette_loss=1.0, eikonal_loss=0.01, iou_projection_loss=0.1, l1_projection_loss=1.0)
+LEARNING_RATES = dict(locations=1e-2, dimensions=1e-2, orientations=1e-2, embeddings=1e-3, hyper_distance_field=1e-4)
+
+
+@dataclasses.dataclass
+class FrameInputs:
+    """Device tensors of one target frame, as main.py:204-316 stacks them."""
+    soft_masks: torch.Tensor        # [V,H,W,N] float32, instance-minor, target instance order
+    boxes_2d: torch.Tensor          # [V,N,4] x1 y1 x2 y2
+    visible: torch.Tensor           # [V,N] bool
+    extrinsics: torch.Tensor        # [V,4,4] world -> camera
+    intrinsics: torch.Tensor        # [V,3,3]
+    target_view: int
+
+    @property
+    def image_size(self):
+        return int(self.soft_masks.shape[1]), int(self.soft_masks.shape[2])
+
+    @property
+    def num_instances(self):
+        return int(self.soft_masks.shape[-1])
+
+
+def synthetic_frame_inputs(frame, device, temperature: float = 10.0) -> FrameInputs:
+    """Supervision of a `synthetic.SyntheticFrame`, rasterised on the device (soft_masks kernel)."""
+    from . import synthetic
+    sup = synthetic.frame_supervision(frame)
+    masks = ops.soft_masks(sup.polygons.to(device), sup.polygon_sizes.to(device), frame.image_size, temperature)
+    return FrameInputs(masks, sup.boxes_2d.to(device), sup.visible.to(device), frame.extrinsics.to(device),
+                       frame.intrinsics.to(device), sup.target_view)
+
+
+class _ProjectionLosses(torch.autograd.Function):
+    """a14 + a15 (main.py:339-415) as one launch; the kernel returns d losses / d corners with the forward."""
+
+    @staticmethod
+    def forward(ctx, world_boxes, views, gt_boxes_2d, visible):
+        _, gt_indices, losses, grad = ops.projection_step(views, world_boxes.detach(), gt_boxes_2d, visible)
+        ctx.save_for_backward(grad)
+        ctx.mark_non_differentiable(gt_indices)
+        return losses, gt_indices
+
+    @staticmethod
+    def backward(ctx, grad_losses, _):
+        grad, = ctx.saved_tensors
+        return (grad * grad_losses.reshape(2, 1, 1, 1)).sum(dim=0), None, None, None
+
+
+class FrameLabeler:
+    """Optimises the boxes (and residual fields) of one target frame.
+
+        labeler = FrameLabeler(inputs, num_steps=3000, warmup_steps=1000)
+        result = labeler.run()            # dict(boxes_3d [N,8,3], locations, dimensions, orientations, losses)
+
+    `rays` selects where a step's ray batch comes from:
+      "draw"     weighted draw without replacement on the device (main.py:620-627) + target gather (the product path);
+      "indices"  `step(pixel_indices)` — the caller injects the pixel indices (parity tests), targets gathered on device;
+      "batches"  `step(pixel_indices, targets)` — indices and silhouette targets copied from (pinned) host memory every
+                 step (bench.py's end-to-end leg).
+    `inject_samples=True` additionally takes the stratified jitter [R,S] and sorted importance uniforms [R,S] of each
+    step from the caller instead of the counter-based generator (parity tests against the CPU oracle)."""
+
+    def __init__(self, inputs: FrameInputs, *, num_steps: int = 3000, warmup_steps: int = 1000, num_rays: int = 1000,
+                 num_samples: int = 100, distance_range=(0.0, 100.0), seed: int = 0, loss_weights: Optional[Dict] = None,
+                 learning_rates: Optional[Dict] = None, temperature=(1.0, 0.1), std_deviation=(1.0, 0.1),
+                 use_graph: bool = True, rays: str = "draw", inject_samples: bool = False, initial_parameters=None,
+                 model_seed: Optional[int] = None):
+        import vsrd
+        dev = inputs.soft_masks.device
+        if dev.type != "cuda":
+            raise RuntimeError("vsrd_b200: FrameLabeler needs CUDA tensors (there is no CPU path)")
+        self.device, self.inputs = dev, inputs
+        self.num_steps, self.warmup_steps = int(num_steps), int(warmup_steps)
+        self.num_rays, self.num_samples = int(num_rays), int(num_samples)
+        self.weights = dict(LOSS_WEIGHTS, **(loss_weights or {}))
+        if rays not in ("draw", "indices", "batches"):
+            raise ValueError(f"rays must be 'draw', 'indices' or 'batches', got {rays!r}")
+        self.use_graph, self.rays, self.inject_samples = bool(use_graph), rays, bool(inject_samples)
+        h, w = inputs.image_size
+        n = inputs.num_instances
+        self.height, self.width, self.num_instances = h, w, n
+
+        # ---- per-frame constants
+        inv_e = torch.linalg.inv(inputs.extrinsics.double())
+        inv_k = torch.linalg.inv(inputs.intrinsics.double())
+        self.inv_projection = (inv_e[:, :3, :3] @ inv_k).float().contiguous()       # rendering/utils.py:8-17
+        self.camera_positions = inv_e[:, :3, 3].float().contiguous()
+        self.views = ops.ViewArgs(inputs.extrinsics, inputs.intrinsics, (h, w), inputs.target_view)
+        self.gt_boxes = inputs.boxes_2d.float().contiguous()
+        self.visible = inputs.visible.to(torch.uint8).contiguous()
+        self.bins = F.distance_bins(distance_range, num_samples, dev)
+        self.scale = float(max(distance_range))
+        self.cdf = ops.ray_cdf_build(inputs.soft_masks) if rays == "draw" else None      # once per frame
+        self.state = ops.StepState(num_steps=num_steps, warmup_steps=warmup_steps, temperature=temperature,
+                                   std_deviation=std_deviation, eikonal_weight=self.weights["eikonal_loss"],
+                                   seed=seed, device=dev)
+        self._step_view = self.state.buffer[24:32].view(torch.int64)                  # VsrdStepState.step
+
+        # ---- fresh models per frame (main.py:174-199)
+        if model_seed is not None:
+            torch.manual_seed(model_seed)
+        self.detector = vsrd.models.BoxParameters3D(batch_size=1, num_instances=n).to(dev)
+        self.hyper = vsrd.models.HyperDistanceField(in_channels=48, out_channels_list=[16, 16, 16, 16],
+                                                    hyper_in_channels=256, hyper_out_channels_list=[256] * 4).to(dev)
+        if initial_parameters is not None:
+            with torch.no_grad():
+                for name, value in initial_parameters.items():
+                    getattr(self.detector, name).copy_(value.reshape(getattr(self.detector, name).shape))
+        lrs = dict(LEARNING_RATES, **(learning_rates or {}))
+        self._base_lrs = [lrs["locations"], lrs["dimensions"], lrs["orientations"], lrs["embeddings"], lrs["hyper_distance_field"]]
+        groups = [
+            dict(params=[self.detector.locations]), dict(params=[self.detector.dimensions]),
+            dict(params=[self.detector.orientations]), dict(params=[self.detector.embeddings]),
+            dict(params=list(self.hyper.parameters())),
+        ]
+        for g, lr in zip(groups, self._base_lrs):
+            g["lr"] = torch.tensor(lr, dtype=torch.float32, device=dev)                # tensor lr: updated in-graph
+        self.optimizer = torch.optim.Adam(groups, lr=1e-2, capturable=True, fused=True)
+        self._log_gamma = math.log(0.01) / float(num_steps)                            # ExponentialLR, config.json:211-215
+
+        # ---- static I/O of the step
+        self.pixel_indices = torch.zeros(self.num_rays, dtype=torch.int64, device=dev)
+        self.targets = torch.zeros(self.num_rays, n, dtype=torch.float32, device=dev)
+        self.jitter = torch.zeros(self.num_rays, self.num_samples, device=dev) if inject_samples else None
+        self.sorted_uniforms = torch.zeros(self.num_rays, self.num_samples, device=dev) if inject_samples else None
+        self.draw_failures = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.losses = torch.zeros(5, dtype=torch.float32, device=dev)    # total, silhouette, eikonal, iou, l1 (weighted)
+        self.step_index = 0
+        # all of the frame's work is enqueued on its own stream, after the set-up above
+        self.stream = torch.cuda.Stream(device=dev)
+        self.stream.wait_stream(torch.cuda.current_stream())
+        self._graphs: Dict[bool, torch.cuda.CUDAGraph] = {}
+        self._eager_done: Dict[bool, int] = {False: 0, True: 0}
+
+    # ---- one optimisation step (main.py:328-865), enqueued on the current stream (= self.stream) ----
+    def _step_body(self, residual: bool) -> None:
+        st = self.state
+        # learning rates of this step: lr0 * gamma^step (scheduler.step() follows optimizer.step(), main.py:863-865)
+        decay = torch.exp(self._step_view.double() * self._log_gamma).float()
+        for group, base in zip(self.optimizer.param_groups, self._base_lrs):
+            group["lr"].copy_(decay[0] * base)
+        self.optimizer.zero_grad(set_to_none=True)
+
+        world = self.detector()
+        boxes_3d = world["boxes_3d"][0]
+        proj, gt_indices = _ProjectionLosses.apply(boxes_3d, self.views, self.gt_boxes, self.visible)
+
+        if self.rays == "draw":
+            pix, status = ops.select_rays(self.cdf, self.num_rays, step_state=st)
+            self.draw_failures.add_(status)
+            self.pixel_indices.copy_(pix)
+        if self.rays != "batches":
+            self.targets.copy_(ops.gather_targets(self.inputs.soft_masks, self.pixel_indices, gt_indices))
+        origins, directions = ops.gather_rays(self.inv_projection, self.camera_positions, self.pixel_indices,
+                                              self.height, self.width)
+        mlp_weights = self.hyper(world["embeddings"])[0] if residual else None
+        render_loss, _, parts = F.render_step(
+            world["locations"][0], world["orientations"][0], world["dimensions"][0], mlp_weights,
+            origins, directions, self.targets, bins=self.bins, temperature=1.0, std_deviation=1.0, cosine_ratio=0.0,
+            scale=self.scale, silhouette_weight=self.weights["silhouette_loss"],
+            eikonal_weight=self.weights["eikonal_loss"] if residual else 0.0, step_state=st,
+            jitter=self.jitter, sorted_uniforms=self.sorted_uniforms)
+        w_iou, w_l1 = self.weights["iou_projection_loss"], self.weights["l1_projection_loss"]
+        loss = render_loss + w_iou * proj[0] + w_l1 * proj[1]
+        loss.backward()
+        self.optimizer.step()
+        with torch.no_grad():
+            self.losses.copy_(torch.stack([loss.detach(), parts[0], parts[1], w_iou * proj[0].detach(), w_l1 * proj[1].detach()]))
+        st.advance()
+
+    def _capture(self, residual: bool) -> None:
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=self.stream):
+            self._step_body(residual)
+        self._graphs[residual] = graph
+
+    def step(self, pixel_indices: Optional[torch.Tensor] = None, targets: Optional[torch.Tensor] = None,
+             jitter: Optional[torch.Tensor] = None, sorted_uniforms: Optional[torch.Tensor] = None) -> None:
+        """Enqueues optimisation step `self.step_index` on the labeler's own stream (asynchronous: several
+        labelers can be stepped round-robin so their frames overlap on one GPU).  Injected inputs (see `rays`,
+        `inject_samples`) are copied from the given (pinned host or device) tensors into the step's static
+        buffers first."""
+        if self.step_index >= self.num_steps:
+            raise RuntimeError("vsrd_b200: FrameLabeler.step() called after the last optimisation step")
+        if self.rays != "draw" and (pixel_indices is None or (self.rays == "batches" and targets is None)):
+            raise RuntimeError(f"vsrd_b200: rays={self.rays!r} needs the ray batch of every step")
+        if self.inject_samples and (jitter is None or sorted_uniforms is None):
+            raise RuntimeError("vsrd_b200: inject_samples=True needs jitter and sorted_uniforms for every step")
+        residual = self.step_index >= self.warmup_steps
+        with torch.cuda.stream(self.stream):
+            if self.rays != "draw":
+                self.pixel_indices.copy_(pixel_indices.reshape(-1), non_blocking=True)
+                if self.rays == "batches":
+                    self.targets.copy_(targets, non_blocking=True)
+            if self.inject_samples:
+                self.jitter.copy_(jitter.reshape(self.jitter.shape), non_blocking=True)
+                self.sorted_uniforms.copy_(sorted_uniforms.reshape(self.sorted_uniforms.shape), non_blocking=True)
+            if self.use_graph and residual not in self._graphs and self._eager_done[residual] >= 3:
+                self._capture(residual)
+            if self.use_graph and residual in self._graphs:
+                self._graphs[residual].replay()
+            else:
+                # without graphs, or for the first steps of each phase (allocator / cuBLAS warm-up before capture)
+                self._step_body(residual)
+                self._eager_done[residual] += 1
+        self.step_index += 1
+
+    def synchronize(self) -> None:
+        self.stream.synchronize()
+
+    # ---- results -----------------------------------------------------------------------------------
+    @torch.no_grad()
+    def boxes(self) -> Dict[str, torch.Tensor]:
+        """Decoded boxes after the steps enqueued so far (waits for the labeler's stream)."""
+        torch.cuda.current_stream().wait_stream(self.stream)
+        world = self.detector()
+        return dict(boxes_3d=world["boxes_3d"][0], locations=world["locations"][0],
+                    dimensions=world["dimensions"][0], orientations=world["orientations"][0])
+
+    def run(self) -> Dict[str, torch.Tensor]:
+        if self.rays != "draw" or self.inject_samples:
+            raise RuntimeError("vsrd_b200: run() draws its own rays and samples; drive step(...) yourself when injecting them")
+        while self.step_index < self.num_steps:
+            self.step()
+        out = self.boxes()
+        out["losses"] = self.losses.clone()
+        failures = int(self.draw_failures)           # the only host sync of the frame
+        if failures:
+            raise RuntimeError(f"vsrd_b200: {failures} rays could not be drawn (fewer weighted pixels than num_rays; "
+                               "torch.multinomial raises in the reference, main.py:620-627)")
+        return out

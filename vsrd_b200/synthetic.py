@@ -136,3 +136,83 @@ def perturbed_raw_parameters(frame: SyntheticFrame, seed: int = 0, position_nois
     raw_dim = torch.zeros(n, 3)
     raw_ori = torch.stack([torch.cos(yaw), torch.sin(yaw)], dim=-1)
     return raw_loc, raw_dim, raw_ori
+
+
+# ------------------------------------------------------------------------------------------------
+# Per-frame supervision of a synthetic frame: what KITTI360Dataset + the mask transforms hand to
+# scripts/main.py: soft masks, 2D boxes and source-view visibility.
+# ------------------------------------------------------------------------------------------------
+_CORNER_SIGNS = torch.tensor([
+    (-1.0, -1.0, +1.0), (+1.0, -1.0, +1.0), (+1.0, -1.0, -1.0), (-1.0, -1.0, -1.0),
+    (-1.0, +1.0, +1.0), (+1.0, +1.0, +1.0), (+1.0, +1.0, -1.0), (-1.0, +1.0, -1.0),
+])
+MAX_POLYGON_VERTICES = 8
+
+
+def gt_corners(frame: SyntheticFrame) -> torch.Tensor:
+    """Ground-truth corners [N,8,3] in the corner order of box_parameters.py:77-86."""
+    local = _CORNER_SIGNS[None] * frame.gt_half_extents[:, None]
+    return local @ frame.gt_rotations.transpose(-2, -1) + frame.gt_locations[:, None]
+
+
+def _convex_hull(points):
+    """Andrew's monotone chain on a handful of 2D points (list of (x, y)); counter-clockwise hull."""
+    pts = sorted(set(points))
+    if len(pts) < 3:
+        return pts
+
+    def cross(o, a, b):
+        return (a[0] - o[0]) * (b[1] - o[1]) - (a[1] - o[1]) * (b[0] - o[0])
+
+    lower, upper = [], []
+    for p in pts:
+        while len(lower) >= 2 and cross(lower[-2], lower[-1], p) <= 0:
+            lower.pop()
+        lower.append(p)
+    for p in reversed(pts):
+        while len(upper) >= 2 and cross(upper[-2], upper[-1], p) <= 0:
+            upper.pop()
+        upper.append(p)
+    return lower[:-1] + upper[:-1]
+
+
+@dataclasses.dataclass
+class FrameSupervision:
+    polygons: torch.Tensor        # [V,N,8,2] silhouette polygons (x, y) of the GT boxes, zero padded
+    polygon_sizes: torch.Tensor   # [V,N] int32, 0 where the instance is not visible in the view
+    boxes_2d: torch.Tensor        # [V,N,4] x1 y1 x2 y2 (bounding box of the visible polygon, clipped to the image)
+    visible: torch.Tensor         # [V,N] bool
+    target_view: int
+
+
+def frame_supervision(frame: SyntheticFrame, min_depth: float = 1.0) -> FrameSupervision:
+    """Projects the GT boxes into every view: the instance silhouette is the convex hull of its 8
+    projected corners.  An instance is visible in a view when all corners are in front of the camera
+    and its box overlaps the image."""
+    h, w = frame.image_size
+    v, n = frame.num_views, frame.num_instances
+    corners = gt_corners(frame)                                                    # [N,8,3]
+    cam = torch.einsum("vmk,nck->vncm", frame.extrinsics[:, :3, :3], corners) + frame.extrinsics[:, None, None, :3, 3]
+    uvw = torch.einsum("vmk,vnck->vncm", frame.intrinsics, cam)
+    uv = uvw[..., :2] / uvw[..., 2:].clamp_min(1e-6)
+    polygons = torch.zeros(v, n, MAX_POLYGON_VERTICES, 2)
+    sizes = torch.zeros(v, n, dtype=torch.int32)
+    boxes = torch.zeros(v, n, 4)
+    visible = torch.zeros(v, n, dtype=torch.bool)
+    for vi in range(v):
+        for ni in range(n):
+            if float(cam[vi, ni, :, 2].min()) < min_depth:
+                continue
+            hull = _convex_hull([(float(x), float(y)) for x, y in uv[vi, ni].tolist()])
+            if len(hull) < 3:
+                continue
+            p = torch.tensor(hull)
+            x1, y1 = float(p[:, 0].min()), float(p[:, 1].min())
+            x2, y2 = float(p[:, 0].max()), float(p[:, 1].max())
+            if x2 <= 0 or y2 <= 0 or x1 >= w or y1 >= h:
+                continue
+            polygons[vi, ni, :len(hull)] = p
+            sizes[vi, ni] = len(hull)
+            boxes[vi, ni] = torch.tensor([max(x1, 0.0), max(y1, 0.0), min(x2, float(w)), min(y2, float(h))])
+            visible[vi, ni] = True
+    return FrameSupervision(polygons, sizes, boxes, visible, target_view=v // 2)
