@@ -11,9 +11,12 @@ Unit of work: ray-samples = R * ((S-1) + (2S-1)) per step.
 
   value       device-resident inputs, raw kernel sequence replayed as a CUDA graph, CUDA-event timed,
               L2 flushed between steps, max over ranks.
-  e2e         same metric through the public drop-in API (vsrd.models + vsrd.rendering closures as
-              scripts/main.py composes them, autograd backward, Adam step) with the step's inputs
-              coming from pinned host memory and the loss read back to the host every step.
+  e2e         same metric through the public API a labeling job calls (vsrd_b200.frame.FrameLabeler.step: the
+              whole scripts/main.py optimisation step -- decode, projection/matching losses, hypernetwork,
+              two-pass render, loss, backward, Adam -- replayed as one CUDA graph), the step's ray batch coming
+              from pinned host memory and the losses read back to the host every step.
+  eager_api   (informational) the drop-in vsrd.* API composed from main.py's closures every step, no graph.
+  frames      whole frames labelled per hour (3000 steps each, rays drawn on the device, 2 frames in flight).
   roofline    dominant kernel (field backward) against the FP32-FMA peak.
   cpu_baseline  oracle port (the reference's PyTorch algorithm) on the host cores, bounded sample.
 
@@ -53,6 +56,8 @@ def parse_args():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--cpu-sample-rays", type=int, default=250)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--frames", type=int, default=2, help="whole frames labelled (in flight together) for frames/hour; 0 = skip")
+    ap.add_argument("--frame-steps", type=int, default=3000)
     return ap.parse_args()
 
 
@@ -71,14 +76,17 @@ def workload_name(args):
 # CPU reference arm (oracle port) -- also used for cpu_baseline
 # ------------------------------------------------------------------------------------------------
 def cpu_reference_run(args, steps, warmup, num_rays):
-    """Times the oracle (oracle/vsrd_oracle.py: the reference's PyTorch algorithm) on the host cores:
-    detector decode + hypernetwork + two-pass renderer + BCE/eikonal + backward to the leaf parameters."""
+    """Times the oracle (oracle/vsrd_oracle.py + frame_oracle.py: the reference's PyTorch algorithm) on the host
+    cores: detector decode + multi-view projection / matching / projection losses + hypernetwork + two-pass
+    renderer + BCE/eikonal + backward + Adam -- the same optimisation step the native e2e leg runs."""
+    from oracle import frame_oracle
     from oracle import vsrd_oracle as oracle
     from vsrd_b200 import synthetic
 
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     frame = synthetic.make_frame(args.instances, args.views, seed=0)
+    sup = synthetic.frame_supervision(frame)
     gen = torch.Generator().manual_seed(0)
     inv_proj, cam = frame.inverse_projections()
     raw_loc, raw_dim, raw_ori = synthetic.perturbed_raw_parameters(frame, seed=0)
@@ -86,6 +94,9 @@ def cpu_reference_run(args, steps, warmup, num_rays):
     emb = torch.rand(256, generator=gen).repeat(args.instances, 1).requires_grad_(True)
     torch.manual_seed(0)
     hyper = oracle.HyperNetwork()
+    optimizer = torch.optim.Adam([dict(params=[leaves[0]], lr=1e-2), dict(params=[leaves[1]], lr=1e-2),
+                                  dict(params=[leaves[2]], lr=1e-2), dict(params=[emb], lr=1e-3),
+                                  dict(params=list(hyper.parameters()), lr=1e-4)], lr=1e-2)
     sched = schedule_at()
     h, w = frame.image_size
     times = []
@@ -98,15 +109,18 @@ def cpu_reference_run(args, steps, warmup, num_rays):
         o = cam[view]
         targets = torch.rand(num_rays, args.instances, generator=gen)
         t0 = time.perf_counter()
+        optimizer.zero_grad(set_to_none=True)
         loc, dim, rot = oracle.decode_box_parameters(*leaves)
+        _, _, iou, l1 = frame_oracle.projection_step(oracle.box_corners(loc, dim, rot), frame.extrinsics, frame.intrinsics,
+                                                     (h, w), sup.boxes_2d, sup.visible, sup.target_view)
         scene = oracle.Scene(loc, rot, dim, hyper(emb), sched["temperature"])
         loss, _ = oracle.render_loss(scene, o, d, targets, num_samples=args.samples, distance_range=[0.0, 100.0],
                                      sdf_std_deviation=sched["std_deviation"], cosine_ratio=sched["cosine_ratio"])
+        loss = loss + 0.1 * iou + 1.0 * l1
         loss.backward()
+        optimizer.step()
         float(loss)
         dt = time.perf_counter() - t0
-        for p in [*leaves, emb, *hyper.parameters()]:
-            p.grad = None
         if it >= warmup:
             times.append(dt)
     per_step = sum(times) / len(times)
@@ -376,6 +390,47 @@ def run_native(args):
     per_kernel = {k: statistics.median(v) for k, v in per_kernel.items()}
 
     # ---------------- end-to-end leg through the public API ----------------
+    # vsrd_b200.frame.FrameLabeler = scripts/main.py's optimisation step for one frame (decode, projection +
+    # matching + projection losses, hypernetwork, two-pass render, silhouette/eikonal loss, backward, Adam, LR
+    # decay), replayed as one CUDA graph.  Every step: the ray batch (pixel indices + silhouette targets) comes
+    # from pinned host memory and the step's losses are read back to the host.
+    from vsrd_b200.frame import FrameLabeler, synthetic_frame_inputs
+    inputs = synthetic_frame_inputs(frame, device)
+    from vsrd_b200 import synthetic as _syn
+    raw_loc, raw_dim, raw_ori = _syn.perturbed_raw_parameters(frame, seed=rank)
+    labeler = FrameLabeler(inputs, num_steps=3000, warmup_steps=1000, num_rays=args.rays, num_samples=args.samples,
+                           rays="batches", use_graph=use_graph, seed=rank, model_seed=rank,
+                           initial_parameters=dict(locations=raw_loc.to(device), dimensions=raw_dim.to(device),
+                                                   orientations=raw_ori.to(device)))
+    start_step = 1500 - (K + W) // 2                      # mid-schedule, residual field on (as the device leg)
+    labeler.state.set_step(start_step)
+    labeler.step_index = start_step
+    pool_pin, targets_pin = pool.pin_memory(), targets.pin_memory()
+    loss_pin = torch.zeros(5, dtype=torch.float32).pin_memory()
+
+    def e2e_step(k):
+        labeler.step(pool_pin[k], targets_pin[k])                        # H2D copies + graph replay on the labeler's stream
+        with torch.cuda.stream(labeler.stream):
+            loss_pin.copy_(labeler.losses, non_blocking=True)            # D2H: the step's losses
+        labeler.stream.synchronize()
+        return float(loss_pin[0])
+
+    for k in range(W):
+        e2e_step(k)
+    barrier()
+    e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(labeler.stream):
+        e_start.record()
+    for k in range(K):
+        last = e2e_step(W + k)
+    with torch.cuda.stream(labeler.stream):
+        e_end.record()
+    barrier()
+    e2e_ms = e_start.elapsed_time(e_end)
+    if not math.isfinite(last):
+        raise RuntimeError("bench.py: non-finite loss from the end-to-end leg")
+
+    # ---------------- eager drop-in API leg (informational): main.py's closures -> vsrd.rendering ----------------
     config = vsrd.utils.Dict.apply(dict(volume_rendering=dict(distance_range=[0.0, 100.0], num_fine_samples=args.samples)))
     params = [
         dict(params=[detector.locations], lr=1e-2), dict(params=[detector.dimensions], lr=1e-2),
@@ -383,38 +438,64 @@ def run_native(args):
         dict(params=list(hyper.parameters()), lr=1e-4),
     ]
     optimizer = torch.optim.Adam(params, lr=1e-2)
-    pool_pin, targets_pin = pool.pin_memory(), targets.pin_memory()
     inv_proj_dev, cam_dev = inv_proj.to(device), cam.to(device)
     h, w = frame.image_size
 
-    def e2e_step(k):
-        pix = pool_pin[k].to(device, non_blocking=True)                  # H2D: ray selection of this step
-        tgt = targets_pin[k].to(device, non_blocking=True)               # H2D: silhouette targets
+    def api_step(k):
+        pix = pool_pin[k].to(device, non_blocking=True)
+        tgt = targets_pin[k].to(device, non_blocking=True)
         rays_o, rays_d = ops.gather_rays(inv_proj_dev, cam_dev, pix, h, w)
         optimizer.zero_grad(set_to_none=True)
         loss = main_style_step(vsrd, (detector, hyper, encoder), config, rays_o, rays_d, tgt, sched, args.instances)
         loss.backward()
         optimizer.step()
-        return float(loss)                                               # D2H: the step's loss
+        return float(loss)
 
-    for k in range(W):
-        e2e_step(k)
-    barrier()
-    e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e_start.record()
-    for k in range(K):
-        last = e2e_step(W + k)
-    e_end.record()
-    barrier()
-    e2e_ms = e_start.elapsed_time(e_end)
-    if not math.isfinite(last):
-        raise RuntimeError("bench.py: non-finite loss from the end-to-end leg")
+    api_steps = min(K, 20)
+    for k in range(3):
+        api_step(k)
+    torch.cuda.synchronize()
+    a_start, a_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a_start.record()
+    for k in range(api_steps):
+        api_step(3 + k)
+    a_end.record()
+    torch.cuda.synchronize()
+    api_ms = a_start.elapsed_time(a_end) / api_steps
+
+    # ---------------- whole frames: FrameLabeler.run() with on-device ray draws, 2 frames in flight ----------------
+    frames_info = None
+    if args.frames > 0:
+        torch.cuda.synchronize()
+        t_frames = time.perf_counter()
+        labelers = []
+        for f in range(args.frames):
+            fr = _syn.make_frame(args.instances, args.views, seed=1000 + rank * args.frames + f)
+            raw = _syn.perturbed_raw_parameters(fr, seed=f)
+            labelers.append(FrameLabeler(synthetic_frame_inputs(fr, device), num_steps=args.frame_steps,
+                                         warmup_steps=args.frame_steps // 3, num_rays=args.rays, num_samples=args.samples,
+                                         seed=f, initial_parameters=dict(locations=raw[0].to(device), dimensions=raw[1].to(device),
+                                                                         orientations=raw[2].to(device))))
+        for _ in range(args.frame_steps):
+            for lab in labelers:                                          # round-robin: the frames overlap on the GPU
+                lab.step()
+        boxes = [lab.boxes()["boxes_3d"].cpu() for lab in labelers]
+        torch.cuda.synchronize()
+        frame_s = time.perf_counter() - t_frames
+        if not all(bool(torch.isfinite(b).all()) for b in boxes):
+            raise RuntimeError("bench.py: non-finite boxes from the frame leg")
+        frames_info = dict(frames=args.frames, steps_per_frame=args.frame_steps, in_flight=args.frames, seconds=frame_s)
 
     # ---------------- reduce over ranks ----------------
-    t = torch.tensor([dev_ms, e2e_ms], device=device, dtype=torch.float64)
+    t = torch.tensor([dev_ms, e2e_ms, frames_info["seconds"] if frames_info else 0.0], device=device, dtype=torch.float64)
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
     dev_ms, e2e_ms = float(t[0]), float(t[1])
+    if frames_info:
+        frames_info["seconds"] = float(t[2])
+        frames_info["frames_per_hour"] = world * frames_info["frames"] * 3600.0 / frames_info["seconds"]
+        frames_info["note"] = ("whole-job frames/hour incl. per-frame set-up (soft masks, CDF, models, graph capture); "
+                               "3000 steps/frame as configs/kitti_360, logging/checkpoint paths off")
 
     if rank == 0:
         peaks = {}
@@ -445,8 +526,13 @@ def run_native(args):
             "e2e": {"value": world * units * K / (e2e_ms * 1e-3), "unit": "ray-samples/s",
                     "ms_per_step": e2e_ms / K,
                     "h2d_bytes_per_step": int(pool[0].numel() * 8 + targets[0].numel() * 4),
-                    "d2h_bytes_per_step": 4,
-                    "api": "vsrd.models + vsrd.rendering.hierarchical_volumetric_rendering (main.py closures) + autograd + Adam"},
+                    "d2h_bytes_per_step": 20,
+                    "api": "vsrd_b200.frame.FrameLabeler.step(pixel_indices, targets): decode + projection/matching losses + "
+                           "hypernetwork + two-pass render + loss + backward + Adam as one CUDA graph"},
+            "eager_api": {"ms_per_step": api_ms, "value": units / (api_ms * 1e-3), "unit": "ray-samples/s (per GPU)",
+                          "api": "vsrd.models + vsrd.rendering.hierarchical_volumetric_rendering composed from main.py's "
+                                 "closures every step + autograd + Adam (no graph: Python dispatch bound)"},
+            "frames": frames_info,
             "gpu_launches": SilhouetteStep.KERNELS_PER_STEP * K,
             "roofline": {"bound": "fp32_fma", "kernel": "field_backward_kernel<residual>", "achieved": achieved,
                          "peak": fma_peak_tflops, "unit": "TFLOP/s",
