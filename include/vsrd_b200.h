@@ -214,6 +214,26 @@ int vsrd_gather_targets(const float* soft_masks, const int64_t* pixel_indices, c
 int vsrd_soft_masks(const float* polygons, const int32_t* polygon_sizes, int num_views, int num_instances,
                     int max_vertices, int height, int width, float temperature, float* soft_masks, void* stream);
 
+/* ---- inference / logging renderers (scripts/main.py:1011-1041): the per-instance field at ARBITRARY points,
+ * the soft union there, and one iteration of vsrd.rendering.sphere_tracing (rendering/renderers.py:21-76).
+ * surface_normal (renderers.py:79-113) is the normalised union gradient these return.
+ *   points [P,3] -> field [N][P] float4 (d_i, grad d_i): the same kernels as vsrd_field_forward. */
+int vsrd_field_points(const VsrdScene* scene, const float* points, int num_points, float* field, void* stream);
+/* soft union (scripts/main.py:477-492) of field [N][P]: union_out [P] float4 (d, grad d) and/or
+ * weights [P,N] (softmin weights = soft instance labels); either output may be NULL. */
+int vsrd_union_points(const VsrdScene* scene, const float* field, int num_points, float* union_out, float* weights,
+                      void* stream);
+/* One sphere-tracing iteration (renderers.py:45-55) given union_out [P] float4 evaluated at `positions`:
+ *   positions += directions * d where foreground & ~converged;  foreground &= |positions| < bounding_radius
+ *   (bounding_radius <= 0: no bound);  converged = |d| < convergence_criteria.
+ * directions [P,3] (directions_per_ray != 0) or one shared [3]; foreground / converged [P] uint8 in/out.
+ * active [>= iteration + 1] int32, zero-initialised: active[iteration] receives the number of rays still
+ * foreground and not converged; an iteration whose predecessor counted 0 is a no-op, which reproduces the
+ * reference's global `break` (renderers.py:55) without a host round trip per iteration. */
+int vsrd_sphere_trace_step(const float* union_out, const float* directions, int directions_per_ray, int num_rays,
+                           float convergence_criteria, float bounding_radius, float* positions, uint8_t* foreground,
+                           uint8_t* converged, int32_t* active, int iteration, void* stream);
+
 /* ---- schedule (scripts/main.py:420-431, 677): set_step >= 0 jumps to that step, < 0 advances by one;
  * recomputes temperature / std_deviation (cosine annealing), cosine_ratio, the eikonal switch and the
  * per-step seed in DEVICE memory. */

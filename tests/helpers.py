@@ -34,3 +34,13 @@ def render_kwargs(g):
 
 def rel_l2(a, b):
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+SURFACE_CASES = ["box_f32", "residual_f32", "late_f32"]
+
+
+def load_surface_golden(case):
+    """tests/golden/surface.npz (reference sphere_tracing / surface_normal outputs) for one render case."""
+    data = np.load(os.path.join(GOLDEN_DIR, "surface.npz"))
+    prefix = case + "."
+    return {k[len(prefix):]: torch.from_numpy(data[k]) for k in data.files if k.startswith(prefix)}

@@ -63,3 +63,29 @@ def test_units_match_reference():
     keys = sorted(net.state_dict().keys())
     assert keys == list(u["hyper_state_keys"])
     assert [net.state_dict()[k].numel() for k in keys] == list(u["hyper_state_numel"])
+
+
+@pytest.mark.parametrize("case", ["box_f32", "residual_f32", "late_f32"])
+def test_surface_renderers_match_reference(case):
+    """oracle/surface_oracle.py against the reference's own sphere_tracing / surface_normal outputs."""
+    from oracle import surface_oracle as so
+    from tests.helpers import load_surface_golden
+    g = load_surface_golden(case)
+    scene = scene_from_golden(load_golden(case))
+    it, crit = int(g["num_iterations"]), float(g["criteria"])
+    d, labels = scene.field()(g["points"])
+    torch.testing.assert_close(d, g["point_distances"], rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(labels, g["point_labels"], rtol=1e-6, atol=1e-6)
+    runs = [
+        ("positions", "converged", dict(ray_positions=g["camera_position"], num_iterations=it, bounding_radius=100.0, initialization=False)),
+        ("positions_cap", "converged_cap", dict(ray_positions=g["camera_position"], num_iterations=7, bounding_radius=100.0, initialization=False)),
+        ("positions_init", "converged_init", dict(ray_positions=g["far_camera"], num_iterations=it, bounding_radius=40.0, initialization=True)),
+        ("positions_newton", "converged_newton", dict(ray_positions=g["camera_position"], num_iterations=it, bounding_radius=100.0,
+                                                      initialization=False, differentiable=True)),
+    ]
+    for pk, ck, kw in runs:
+        pos, conv = so.sphere_tracing(scene, ray_directions=g["ray_directions"], convergence_criteria=crit, **kw)
+        assert torch.equal(conv, g[ck]), (pk, int((conv != g[ck]).sum()))
+        torch.testing.assert_close(pos.detach(), g[pk], rtol=1e-6, atol=1e-5, msg=lambda m, k=pk: f"{k}: {m}")
+    torch.testing.assert_close(so.surface_normal(scene, g["positions"]), g["normals"], rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(so.surface_normal(scene, g["positions"], 1e-2), g["normals_fd"], rtol=1e-4, atol=1e-4)

@@ -165,3 +165,37 @@ def hierarchical_volumetric_rendering(
     out_weights = weights.t().reshape(m, *lead, 1)
     features = (labels.reshape(*lead, -1),) if field.returns_features else ()
     return (*features, out_grads, out_dist, out_weights)
+
+
+def sphere_intersection(ray_positions, ray_directions, bounding_radius):
+    """rendering/renderers.py:10-18 (plain tensor algebra, runs before the loop)."""
+    from vsrd_b200 import surface
+    return surface.sphere_intersection(ray_positions, ray_directions, bounding_radius)
+
+
+def sphere_tracing(
+    distance_field,
+    ray_positions,
+    ray_directions,
+    num_iterations,
+    convergence_criteria,
+    foreground_masks=None,
+    bounding_radius=None,
+    initialization=True,
+    differentiable=False,
+):
+    """`vsrd.rendering.sphere_tracing` (rendering/renderers.py:21-76) for the union field scripts/main.py
+    composes (`compose(soft_distance_field, itemgetter(0))`, main.py:1030): returns
+    `(ray_positions [..., 3], convergence_masks [..., 1])`.  The iteration loop runs on the device."""
+    from vsrd_b200 import surface
+    field = match_union_field(distance_field)
+    return surface.sphere_trace(field, ray_positions, ray_directions, num_iterations, convergence_criteria,
+                                foreground_masks=foreground_masks, bounding_radius=bounding_radius,
+                                initialization=initialization, differentiable=differentiable)
+
+
+def surface_normal(distance_field, surface_positions, finite_difference_epsilon=None):
+    """`vsrd.rendering.surface_normal` (rendering/renderers.py:79-113): unit normals of the union field."""
+    from vsrd_b200 import surface
+    field = match_union_field(distance_field)
+    return surface.surface_normals(field, surface_positions, finite_difference_epsilon)

@@ -122,6 +122,9 @@ SIGNATURES = {
     "vsrd_select_rays": (_I, [_V, ctypes.c_int64, _V, _I, ctypes.c_uint64, _V, _I, _V, _V, _V]),
     "vsrd_gather_targets": (_I, [_V, _V, _V, _I, _I, _V, _V]),
     "vsrd_soft_masks": (_I, [_V, _V, _I, _I, _I, _I, _I, ctypes.c_float, _V, _V]),
+    "vsrd_field_points": (_I, [_P(VsrdScene), _V, _I, _V, _V]),
+    "vsrd_union_points": (_I, [_P(VsrdScene), _V, _I, _V, _V, _V]),
+    "vsrd_sphere_trace_step": (_I, [_V, _V, _I, _I, ctypes.c_float, ctypes.c_float, _V, _V, _V, _V, _I, _V]),
     "vsrd_step_state_update": (_I, [_V, _P(VsrdSchedule), ctypes.c_int64, _V]),
 }
 

@@ -67,7 +67,14 @@ __device__ __forceinline__ void stage_weights(const float* __restrict__ W, float
 
 // Sample position exactly as the reference forms it: o + d * ((t0 + t1) / 2), no FMA contraction
 // (renderers.py:213-216).
+// POINTS mode (vsrd_field_points: sphere tracing / surface normals, renderers.py:21-113): dist == NULL, M = 1
+// and `origins` holds the evaluation points themselves.
 __device__ __forceinline__ void sample_position(const RaysDev& rays, int r, int j, float x[3]) {
+    if (rays.dist == nullptr) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) x[c] = __ldg(rays.origins + 3 * ((size_t)r * rays.M + j) + c);
+        return;
+    }
     const float t0 = __ldg(rays.dist + (size_t)r * (rays.M + 1) + j);
     const float t1 = __ldg(rays.dist + (size_t)r * (rays.M + 1) + j + 1);
     const float mid = __fadd_rn(t0, t1) / 2.0f;

@@ -331,9 +331,7 @@ using namespace vsrd;
 
 extern "C" {
 
-int vsrd_field_forward(const VsrdScene* scene, const VsrdRays* rays, float* field, void* stream) {
-    SceneDev s; RaysDev r;
-    if (check_scene(scene, s) || check_rays(rays, r)) return 1;
+static int launch_field(const SceneDev& s, const RaysDev& r, float* field, void* stream) {
     VSRD_CHECK_ARG(field != nullptr, "field is NULL");
     const size_t total = (size_t)r.R * r.M;
     if (total == 0) return 0;
@@ -350,6 +348,21 @@ int vsrd_field_forward(const VsrdScene* scene, const VsrdRays* rays, float* fiel
     }
     VSRD_CHECK_LAUNCH();
     return 0;
+}
+
+int vsrd_field_forward(const VsrdScene* scene, const VsrdRays* rays, float* field, void* stream) {
+    SceneDev s; RaysDev r;
+    if (check_scene(scene, s) || check_rays(rays, r)) return 1;
+    return launch_field(s, r, field, stream);
+}
+
+int vsrd_field_points(const VsrdScene* scene, const float* points, int num_points, float* field, void* stream) {
+    SceneDev s;
+    if (check_scene(scene, s)) return 1;
+    VSRD_CHECK_ARG(num_points >= 0, "num_points must be non-negative");
+    VSRD_CHECK_ARG(num_points == 0 || points != nullptr, "points is NULL");
+    const RaysDev r{num_points, 1, points, nullptr, nullptr};     // points mode of sample_position()
+    return launch_field(s, r, field, stream);
 }
 
 }  // extern "C"

@@ -351,3 +351,42 @@ def soft_masks(polygons: torch.Tensor, polygon_sizes: torch.Tensor, image_size, 
     out = torch.empty(v, h, w, n, device=poly.device, dtype=torch.float32)
     _lib.check(_lib.load().vsrd_soft_masks(_ptr(poly), _ptr(sizes), v, n, pv, h, w, float(temperature), _ptr(out), _stream()))
     return out
+
+
+# ---- inference / logging renderers -------------------------------------------
+
+def field_points(scene: SceneArgs, points: torch.Tensor) -> torch.Tensor:
+    """Per-instance field (d_i, grad d_i) at arbitrary points [P,3] -> [N,P,4]."""
+    pts = _f32(points, "points").reshape(-1, 3)
+    field = torch.empty(scene.num_instances, pts.shape[0], 4, device=pts.device, dtype=torch.float32)
+    _lib.check(_lib.load().vsrd_field_points(ctypes.byref(scene.struct), _ptr(pts), pts.shape[0], _ptr(field), _stream()))
+    return field
+
+
+def union_points(scene: SceneArgs, field: torch.Tensor, want_weights: bool = False):
+    """Soft union (main.py:477-492) of field [N,P,4] -> union [P,4] (d, grad d) and, optionally, the softmin
+    weights [P,N] (the soft instance labels)."""
+    f = _f32(field, "field")
+    n, p = scene.num_instances, f.shape[1]
+    if tuple(f.shape) != (n, p, 4):
+        raise RuntimeError(f"vsrd_b200: field must be [{n}, P, 4], got {tuple(f.shape)}")
+    out = torch.empty(p, 4, device=f.device, dtype=torch.float32)
+    weights = torch.empty(p, n, device=f.device, dtype=torch.float32) if want_weights else None
+    _lib.check(_lib.load().vsrd_union_points(ctypes.byref(scene.struct), _ptr(f), p, _ptr(out), _ptr(weights), _stream()))
+    return out, weights
+
+
+def sphere_trace_step(union_out, directions, positions, foreground, converged, active, iteration: int,
+                      convergence_criteria: float, bounding_radius: Optional[float]) -> None:
+    """One iteration of sphere_tracing (renderers.py:45-55), in place on positions / foreground / converged."""
+    p = positions.shape[0]
+    if directions.shape[0] not in (1, p):
+        raise RuntimeError("vsrd_b200: directions must be [P,3] or [1,3]")
+    for t, name, dt in ((foreground, "foreground", torch.uint8), (converged, "converged", torch.uint8), (active, "active", torch.int32)):
+        if t.dtype != dt or not t.is_cuda or not t.is_contiguous():
+            raise RuntimeError(f"vsrd_b200: {name} must be a contiguous CUDA {dt} tensor")
+    if iteration >= active.numel():
+        raise RuntimeError("vsrd_b200: `active` holds fewer counters than iterations")
+    _lib.check(_lib.load().vsrd_sphere_trace_step(
+        _ptr(union_out), _ptr(directions), int(directions.shape[0] == p and p > 0), p, float(convergence_criteria),
+        float(bounding_radius or 0.0), _ptr(positions), _ptr(foreground), _ptr(converged), _ptr(active), int(iteration), _stream()))
