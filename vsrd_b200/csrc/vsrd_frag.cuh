@@ -56,8 +56,14 @@ constexpr int kTailB4 = 80;
 constexpr int kTailFloats = 96;
 constexpr size_t kWeightBytes = (size_t)kFragFloat4 * 16 + kTailFloats * 4;
 
+// The TF32 mask lives in constant memory on purpose: with an immediate, ptxas proves that the tensor core
+// ignores the low 13 bits, drops the AND and then has to MOV the raw (register-pair allocated) activations
+// into a contiguous A-operand quad before every HMMA (13 % of the executed instructions were such MOVs,
+// profiles/r01_v8_*).  A constant-bank operand keeps the LOP3, which writes the operand quad directly.
+static __constant__ uint32_t kTf32Mask = 0xffffe000u;
+
 __device__ __forceinline__ void split(float x, uint32_t& hi, uint32_t& lo) {
-    hi = __float_as_uint(x) & 0xffffe000u;            // exact TF32 (truncated)
+    hi = __float_as_uint(x) & kTf32Mask;              // exact TF32 (truncated)
     lo = __float_as_uint(x - __uint_as_float(hi));    // remainder; the MMA reads its top 19 bits
 }
 
@@ -144,8 +150,9 @@ __device__ __forceinline__ void a_from_c(const f2 (&c)[2], uint32_t (&ah)[4], ui
 //   p01 -> (a0, a1) = k-slot t of rows g, g + 8;  p23 -> (a2, a3) = k-slot t + 4
 __device__ __forceinline__ void a_from_row_pairs(f2 p01, f2 p23, uint32_t (&ah)[4], uint32_t (&al)[4]) {
     f2 h01, h23;
-    ah[0] = __float_as_uint(p01.x) & 0xffffe000u; ah[1] = __float_as_uint(p01.y) & 0xffffe000u;
-    ah[2] = __float_as_uint(p23.x) & 0xffffe000u; ah[3] = __float_as_uint(p23.y) & 0xffffe000u;
+    const uint32_t mask = kTf32Mask;
+    ah[0] = __float_as_uint(p01.x) & mask; ah[1] = __float_as_uint(p01.y) & mask;
+    ah[2] = __float_as_uint(p23.x) & mask; ah[3] = __float_as_uint(p23.y) & mask;
     h01.x = __uint_as_float(ah[0]); h01.y = __uint_as_float(ah[1]);
     h23.x = __uint_as_float(ah[2]); h23.y = __uint_as_float(ah[3]);
     const f2 l01 = sub2(p01, h01), l23 = sub2(p23, h23);
