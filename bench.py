@@ -58,6 +58,8 @@ def parse_args():
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--frames", type=int, default=2, help="whole frames labelled (in flight together) for frames/hour; 0 = skip")
     ap.add_argument("--frame-steps", type=int, default=3000)
+    ap.add_argument("--compare-torch-models", action="store_true",
+                    help="also time the end-to-end step with the models as nn.Modules under autograd (informational)")
     return ap.parse_args()
 
 
@@ -430,6 +432,36 @@ def run_native(args):
     if not math.isfinite(last):
         raise RuntimeError("bench.py: non-finite loss from the end-to-end leg")
 
+    # informational: the same step with the models as nn.Modules under autograd + torch.optim.Adam (~150 more launches)
+    torch_models_ms = None
+    if args.compare_torch_models:
+        lab2 = FrameLabeler(inputs, num_steps=3000, warmup_steps=1000, num_rays=args.rays, num_samples=args.samples,
+                            rays="batches", use_graph=use_graph, seed=rank, model_seed=rank, models="torch",
+                            initial_parameters=dict(locations=raw_loc.to(device), dimensions=raw_dim.to(device),
+                                                    orientations=raw_ori.to(device)))
+        lab2.state.set_step(start_step)
+        lab2.step_index = start_step
+
+        def torch_step(k):
+            lab2.step(pool_pin[k], targets_pin[k])
+            with torch.cuda.stream(lab2.stream):
+                loss_pin.copy_(lab2.losses, non_blocking=True)
+            lab2.stream.synchronize()
+
+        for k in range(W + 2):
+            torch_step(k % total)
+        t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(lab2.stream):
+            t_start.record()
+        reps2 = min(K, 20)
+        for k in range(reps2):
+            torch_step((W + k) % total)
+        with torch.cuda.stream(lab2.stream):
+            t_end.record()
+        torch.cuda.synchronize()
+        torch_models_ms = t_start.elapsed_time(t_end) / reps2
+        del lab2
+
     # ---------------- eager drop-in API leg (informational): main.py's closures -> vsrd.rendering ----------------
     config = vsrd.utils.Dict.apply(dict(volume_rendering=dict(distance_range=[0.0, 100.0], num_fine_samples=args.samples)))
     params = [
@@ -528,7 +560,9 @@ def run_native(args):
                     "h2d_bytes_per_step": int(pool[0].numel() * 8 + targets[0].numel() * 4),
                     "d2h_bytes_per_step": 20,
                     "api": "vsrd_b200.frame.FrameLabeler.step(pixel_indices, targets): decode + projection/matching losses + "
-                           "hypernetwork + two-pass render + loss + backward + Adam as one CUDA graph"},
+                           "hypernetwork + two-pass render + loss + backward + Adam as one CUDA graph; models, their "
+                           "backward and Adam are the vsrd_model.cu launches (no autograd)",
+                    "ms_per_step_autograd_models": torch_models_ms},
             "eager_api": {"ms_per_step": api_ms, "value": units / (api_ms * 1e-3), "unit": "ray-samples/s (per GPU)",
                           "api": "vsrd.models + vsrd.rendering.hierarchical_volumetric_rendering composed from main.py's "
                                  "closures every step + autograd + Adam (no graph: Python dispatch bound)"},

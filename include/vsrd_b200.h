@@ -234,6 +234,90 @@ int vsrd_sphere_trace_step(const float* union_out, const float* directions, int 
                            float convergence_criteria, float bounding_radius, float* positions, uint8_t* foreground,
                            uint8_t* converged, int32_t* active, int iteration, void* stream);
 
+/* ---- a3 / a4 / a16: the per-frame models and their optimiser (scripts/main.py:174-199, 330-332, 527, 859-865).
+ * In the reference these are nn.Modules stepped by autograd + torch.optim.Adam: ~150 launches of 2-5 us per
+ * optimisation step on [N,.] tensors.  The entry points below run them as a dozen latency-bound launches. */
+#define VSRD_HYPER_WIDTH 256        /* hyper_in_channels == hyper_out_channels_list[i] (config.json:142-162) */
+#define VSRD_HYPER_MAX_LAYERS 5
+#define VSRD_MAX_PARAM_GROUPS 8
+
+/* One weight-normed Linear of HyperDistanceField.hypernetwork (models/fields/hyper_distance_field.py:30-55)
+ * and the LayerNorm that follows it (NULL for the output layer).  State-dict names in parentheses. */
+typedef struct VsrdHyperLayer {
+    const float* weight_v;        /* [out,in]  (hypernetwork.L.0.weight_v)                       */
+    const float* weight_g;        /* [out]     (hypernetwork.L.0.weight_g, stored [out,1])       */
+    const float* bias;            /* [out]     (hypernetwork.L.0.bias)                           */
+    const float* ln_weight;       /* [out]     (hypernetwork.L.1.weight) or NULL                 */
+    const float* ln_bias;         /* [out]     (hypernetwork.L.1.bias) or NULL                   */
+    int32_t in_features, out_features;
+} VsrdHyperLayer;
+typedef struct VsrdHyperNet {
+    int32_t num_layers;           /* 5 in configs/kitti_360: 4 hidden + the 1617-wide output layer */
+    int32_t _pad;
+    VsrdHyperLayer layers[VSRD_HYPER_MAX_LAYERS];
+} VsrdHyperNet;
+typedef struct VsrdHyperLayerGrads {
+    float* weight_v; float* weight_g; float* bias; float* ln_weight; float* ln_bias;
+} VsrdHyperLayerGrads;
+typedef struct VsrdHyperNetGrads {
+    int32_t num_layers;
+    int32_t _pad;
+    VsrdHyperLayerGrads layers[VSRD_HYPER_MAX_LAYERS];
+} VsrdHyperNetGrads;
+
+/* HyperDistanceField.forward (hyper_distance_field.py:75-77): embeddings [N,256] -> mlp_weights [N,out_last].
+ * activations [num_layers-1][N][256] receives the pre-LayerNorm outputs of the hidden Linears (kept for the
+ * backward). */
+int vsrd_hyper_forward(const VsrdHyperNet* net, const float* embeddings, int num_instances,
+                       float* activations, float* mlp_weights, void* stream);
+/* Its backward (what autograd replays for main.py:859): grad_mlp_weights [N,out_last] -> every gradient in `grads`
+ * and grad_embeddings [N,256] (all overwritten).  scratch: vsrd_hyper_scratch_floats(N) floats. */
+size_t vsrd_hyper_scratch_floats(int num_instances);
+int vsrd_hyper_backward(const VsrdHyperNet* net, const VsrdHyperNetGrads* grads, const float* embeddings,
+                        int num_instances, const float* activations, const float* grad_mlp_weights,
+                        float* grad_embeddings, float* scratch, void* stream);
+
+/* BoxParameters3D buffers `location_range` / `dimension_range` (box_parameters.py:19-30). */
+typedef struct VsrdBoxRanges {
+    float location_min[3], location_max[3];
+    float dimension_min[3], dimension_max[3];
+} VsrdBoxRanges;
+/* BoxParameters3D.forward (box_parameters.py:60-91, 124-146): raw locations [N,3], dimensions [N,3],
+ * orientations [N,2] -> locations [N,3] = lerp(range, sigmoid(raw)), half_extents [N,3] likewise,
+ * rotations [N,3,3] = rotation_matrix_y(normalize(raw)), boxes_3d [N,8,3] corners. */
+int vsrd_decode_boxes(const VsrdBoxRanges* ranges, const float* raw_locations, const float* raw_dimensions,
+                      const float* raw_orientations, int num_instances, float* locations, float* half_extents,
+                      float* rotations, float* boxes_3d, void* stream);
+/* Its backward.  Inputs: gradients w.r.t. the decoded locations / half extents / rotations (from
+ * vsrd_field_backward) and, optionally, grad_boxes_3d [2,N,8,3] from vsrd_projection_step weighted by
+ * (iou_weight, l1_weight) (config.json:120-127).  If `losses` is non-NULL it also records
+ * losses[5] = (total, silhouette, eikonal, iou, l1) from render_loss_parts[2] (weighted, as
+ * vsrd_composite_forward accumulates them) and projection_losses[2] (unweighted; NULL = none). */
+int vsrd_decode_boxes_backward(const VsrdBoxRanges* ranges, const float* raw_locations, const float* raw_dimensions,
+                               const float* raw_orientations, int num_instances, const float* half_extents,
+                               const float* rotations, const float* grad_locations, const float* grad_half_extents,
+                               const float* grad_rotations, const float* grad_boxes_3d, float iou_weight, float l1_weight,
+                               float* grad_raw_locations, float* grad_raw_dimensions, float* grad_raw_orientations,
+                               const float* render_loss_parts, const float* projection_losses, float* losses, void* stream);
+
+/* torch.optim.Adam (amsgrad off, no weight decay) + ExponentialLR (config.json:177-215; main.py:863-865) over
+ * ONE flat arena of `numel` floats holding every parameter, group after group.  Group k covers
+ * [group_end[k-1], group_end[k]); its learning rate at optimisation step s is base_lr[k] * exp(log_gamma * s);
+ * its own Adam step count is s - first_step[k] + 1 (the reference's Adam skips parameters without a gradient,
+ * so the hypernetwork groups start counting after the warm-up); groups with s < first_step[k] are untouched.
+ * s = step_state->step when step_state is a non-NULL DEVICE pointer, else `step`. */
+typedef struct VsrdAdamGroups {
+    int32_t num_groups;
+    int32_t _pad;
+    int64_t group_end[VSRD_MAX_PARAM_GROUPS];
+    int64_t first_step[VSRD_MAX_PARAM_GROUPS];
+    float base_lr[VSRD_MAX_PARAM_GROUPS];
+    float beta1, beta2, eps, _pad2;
+    double log_gamma;
+} VsrdAdamGroups;
+int vsrd_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t numel,
+                   const VsrdAdamGroups* groups, const VsrdStepState* step_state, int64_t step, void* stream);
+
 /* ---- schedule (scripts/main.py:420-431, 677): set_step >= 0 jumps to that step, < 0 advances by one;
  * recomputes temperature / std_deviation (cosine annealing), cosine_ratio, the eikonal switch and the
  * per-step seed in DEVICE memory. */

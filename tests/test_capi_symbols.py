@@ -30,7 +30,8 @@ def test_header_declares_expected_entry_points():
     assert "vsrd_field_forward" in names and "vsrd_field_backward" in names
     assert "vsrd_composite_forward" in names and "vsrd_composite_backward" in names
     assert len(names) >= 19
-    assert {'vsrd_projection_step', 'vsrd_select_rays', 'vsrd_ray_cdf_build', 'vsrd_step_state_update'} <= set(names)
+    assert {'vsrd_projection_step', 'vsrd_select_rays', 'vsrd_ray_cdf_build', 'vsrd_step_state_update',
+            'vsrd_hyper_forward', 'vsrd_hyper_backward', 'vsrd_decode_boxes', 'vsrd_adam_step'} <= set(names)
 
 
 def test_library_exports_every_declared_symbol(lib):
@@ -56,11 +57,17 @@ def test_struct_layout_matches_header():
     assert ctypes.sizeof(_lib.VsrdRays) == 32
     assert ctypes.sizeof(_lib.VsrdRenderParams) == 16
     assert ctypes.sizeof(_lib.VsrdLoss) == 16
+    # model entry points (sizes printed by a C program including the header: gcc, LP64)
+    assert ctypes.sizeof(_lib.VsrdHyperLayer) == 48 and ctypes.sizeof(_lib.VsrdHyperNet) == 248
+    assert ctypes.sizeof(_lib.VsrdHyperLayerGrads) == 40 and ctypes.sizeof(_lib.VsrdHyperNetGrads) == 208
+    assert ctypes.sizeof(_lib.VsrdBoxRanges) == 48 and ctypes.sizeof(_lib.VsrdAdamGroups) == 192
     text = open(HEADER).read()
     assert f"#define VSRD_MLP_WEIGHTS {_lib.MLP_WEIGHTS}" in text
     assert f"#define VSRD_GRAD_STRIDE {_lib.GRAD_STRIDE}" in text
     assert f"#define VSRD_MAX_INSTANCES {_lib.MAX_INSTANCES}" in text
     assert f"#define VSRD_MAX_INTERVALS {_lib.MAX_INTERVALS}" in text
+    assert f"#define VSRD_HYPER_WIDTH {_lib.HYPER_WIDTH}" in text
+    assert f"#define VSRD_MAX_PARAM_GROUPS {_lib.MAX_PARAM_GROUPS}" in text
 
 
 def test_argument_errors_are_reported_without_gpu(lib):

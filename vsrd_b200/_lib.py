@@ -97,6 +97,65 @@ class VsrdLoss(ctypes.Structure):
     ]
 
 
+HYPER_WIDTH = 256
+HYPER_MAX_LAYERS = 5
+MAX_PARAM_GROUPS = 8
+
+
+class VsrdHyperLayer(ctypes.Structure):
+    _fields_ = [
+        ("weight_v", ctypes.c_void_p),
+        ("weight_g", ctypes.c_void_p),
+        ("bias", ctypes.c_void_p),
+        ("ln_weight", ctypes.c_void_p),
+        ("ln_bias", ctypes.c_void_p),
+        ("in_features", ctypes.c_int32),
+        ("out_features", ctypes.c_int32),
+    ]
+
+
+class VsrdHyperNet(ctypes.Structure):
+    _fields_ = [("num_layers", ctypes.c_int32), ("_pad", ctypes.c_int32), ("layers", VsrdHyperLayer * HYPER_MAX_LAYERS)]
+
+
+class VsrdHyperLayerGrads(ctypes.Structure):
+    _fields_ = [
+        ("weight_v", ctypes.c_void_p),
+        ("weight_g", ctypes.c_void_p),
+        ("bias", ctypes.c_void_p),
+        ("ln_weight", ctypes.c_void_p),
+        ("ln_bias", ctypes.c_void_p),
+    ]
+
+
+class VsrdHyperNetGrads(ctypes.Structure):
+    _fields_ = [("num_layers", ctypes.c_int32), ("_pad", ctypes.c_int32), ("layers", VsrdHyperLayerGrads * HYPER_MAX_LAYERS)]
+
+
+class VsrdBoxRanges(ctypes.Structure):
+    _fields_ = [
+        ("location_min", ctypes.c_float * 3),
+        ("location_max", ctypes.c_float * 3),
+        ("dimension_min", ctypes.c_float * 3),
+        ("dimension_max", ctypes.c_float * 3),
+    ]
+
+
+class VsrdAdamGroups(ctypes.Structure):
+    _fields_ = [
+        ("num_groups", ctypes.c_int32),
+        ("_pad", ctypes.c_int32),
+        ("group_end", ctypes.c_int64 * MAX_PARAM_GROUPS),
+        ("first_step", ctypes.c_int64 * MAX_PARAM_GROUPS),
+        ("base_lr", ctypes.c_float * MAX_PARAM_GROUPS),
+        ("beta1", ctypes.c_float),
+        ("beta2", ctypes.c_float),
+        ("eps", ctypes.c_float),
+        ("_pad2", ctypes.c_float),
+        ("log_gamma", ctypes.c_double),
+    ]
+
+
 # name -> (restype, argtypes); must list every symbol include/vsrd_b200.h declares
 _P = ctypes.POINTER
 _V = ctypes.c_void_p
@@ -125,6 +184,13 @@ SIGNATURES = {
     "vsrd_field_points": (_I, [_P(VsrdScene), _V, _I, _V, _V]),
     "vsrd_union_points": (_I, [_P(VsrdScene), _V, _I, _V, _V, _V]),
     "vsrd_sphere_trace_step": (_I, [_V, _V, _I, _I, ctypes.c_float, ctypes.c_float, _V, _V, _V, _V, _I, _V]),
+    "vsrd_hyper_scratch_floats": (ctypes.c_size_t, [_I]),
+    "vsrd_hyper_forward": (_I, [_P(VsrdHyperNet), _V, _I, _V, _V, _V]),
+    "vsrd_hyper_backward": (_I, [_P(VsrdHyperNet), _P(VsrdHyperNetGrads), _V, _I, _V, _V, _V, _V, _V]),
+    "vsrd_decode_boxes": (_I, [_P(VsrdBoxRanges), _V, _V, _V, _I, _V, _V, _V, _V, _V]),
+    "vsrd_decode_boxes_backward": (_I, [_P(VsrdBoxRanges), _V, _V, _V, _I, _V, _V, _V, _V, _V, _V, ctypes.c_float,
+                                        ctypes.c_float, _V, _V, _V, _V, _V, _V, _V]),
+    "vsrd_adam_step": (_I, [_V, _V, _V, _V, ctypes.c_int64, _P(VsrdAdamGroups), _V, ctypes.c_int64, _V]),
     "vsrd_step_state_update": (_I, [_V, _P(VsrdSchedule), ctypes.c_int64, _V]),
 }
 

@@ -2,7 +2,7 @@
 
     python -m vsrd_b200.build [--force] [--verbose]
 
-Six translation units are compiled in parallel (the field kernels are fully unrolled and take a
+Seven translation units are compiled in parallel (the field kernels are fully unrolled and take a
 few minutes of ptxas time each) and linked into `vsrd_b200/libvsrd_b200.so`.  The .so is git-ignored
 but travels to the GPU box with the source snapshot.
 """
@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ_DIR = os.path.join(HERE, "_obj")
 LIB_PATH = os.path.join(HERE, "libvsrd_b200.so")
-SOURCES = ["vsrd_render.cu", "vsrd_field_fwd.cu", "vsrd_field_bwd.cu", "vsrd_field_bwd_mma.cu", "vsrd_frame.cu", "vsrd_surface.cu"]
+SOURCES = ["vsrd_render.cu", "vsrd_field_fwd.cu", "vsrd_field_bwd.cu", "vsrd_field_bwd_mma.cu", "vsrd_frame.cu", "vsrd_surface.cu", "vsrd_model.cu"]
 HEADERS = ["vsrd_common.cuh", "vsrd_math.cuh", "vsrd_frag.cuh", "vsrd_frame_math.cuh", os.path.join("..", "..", "include", "vsrd_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -95,7 +95,7 @@ class FrameLabeler:
                  num_samples: int = 100, distance_range=(0.0, 100.0), seed: int = 0, loss_weights: Optional[Dict] = None,
                  learning_rates: Optional[Dict] = None, temperature=(1.0, 0.1), std_deviation=(1.0, 0.1),
                  use_graph: bool = True, rays: str = "draw", inject_samples: bool = False, initial_parameters=None,
-                 model_seed: Optional[int] = None):
+                 model_seed: Optional[int] = None, models: str = "fused"):
         import vsrd
         dev = inputs.soft_masks.device
         if dev.type != "cuda":
@@ -106,6 +106,9 @@ class FrameLabeler:
         self.weights = dict(LOSS_WEIGHTS, **(loss_weights or {}))
         if rays not in ("draw", "indices", "batches"):
             raise ValueError(f"rays must be 'draw', 'indices' or 'batches', got {rays!r}")
+        if models not in ("fused", "torch"):
+            raise ValueError(f"models must be 'fused' or 'torch', got {models!r}")
+        self.models = models
         self.use_graph, self.rays, self.inject_samples = bool(use_graph), rays, bool(inject_samples)
         h, w = inputs.image_size
         n = inputs.num_instances
@@ -139,15 +142,25 @@ class FrameLabeler:
                     getattr(self.detector, name).copy_(value.reshape(getattr(self.detector, name).shape))
         lrs = dict(LEARNING_RATES, **(learning_rates or {}))
         self._base_lrs = [lrs["locations"], lrs["dimensions"], lrs["orientations"], lrs["embeddings"], lrs["hyper_distance_field"]]
-        groups = [
-            dict(params=[self.detector.locations]), dict(params=[self.detector.dimensions]),
-            dict(params=[self.detector.orientations]), dict(params=[self.detector.embeddings]),
-            dict(params=list(self.hyper.parameters())),
-        ]
-        for g, lr in zip(groups, self._base_lrs):
-            g["lr"] = torch.tensor(lr, dtype=torch.float32, device=dev)                # tensor lr: updated in-graph
-        self.optimizer = torch.optim.Adam(groups, lr=1e-2, capturable=True, fused=True)
         self._log_gamma = math.log(0.01) / float(num_steps)                            # ExponentialLR, config.json:211-215
+        if models == "fused":
+            # decode, hypernetwork, their backward and Adam as a dozen launches over one flat arena (csrc/vsrd_model.cu)
+            from .models import ParameterArena
+            self.arena = ParameterArena(self.detector, self.hyper, self._base_lrs, num_steps=num_steps, warmup_steps=warmup_steps)
+            self.optimizer = None
+            self.side_stream = torch.cuda.Stream(device=dev)
+            self.side_stream2 = torch.cuda.Stream(device=dev)
+        else:
+            # the reference's own formulation: nn.Modules under autograd + torch.optim.Adam (~150 launches per step)
+            self.arena = None
+            groups = [
+                dict(params=[self.detector.locations]), dict(params=[self.detector.dimensions]),
+                dict(params=[self.detector.orientations]), dict(params=[self.detector.embeddings]),
+                dict(params=list(self.hyper.parameters())),
+            ]
+            for g, lr in zip(groups, self._base_lrs):
+                g["lr"] = torch.tensor(lr, dtype=torch.float32, device=dev)            # tensor lr: updated in-graph
+            self.optimizer = torch.optim.Adam(groups, lr=1e-2, capturable=True, fused=True)
 
         # ---- static I/O of the step
         self.pixel_indices = torch.zeros(self.num_rays, dtype=torch.int64, device=dev)
@@ -165,6 +178,8 @@ class FrameLabeler:
 
     # ---- one optimisation step (main.py:328-865), enqueued on the current stream (= self.stream) ----
     def _step_body(self, residual: bool) -> None:
+        if self.arena is not None:
+            return self._step_body_fused(residual)
         st = self.state
         # learning rates of this step: lr0 * gamma^step (scheduler.step() follows optimizer.step(), main.py:863-865)
         decay = torch.exp(self._step_view.double() * self._log_gamma).float()
@@ -197,6 +212,62 @@ class FrameLabeler:
         self.optimizer.step()
         with torch.no_grad():
             self.losses.copy_(torch.stack([loss.detach(), parts[0], parts[1], w_iou * proj[0].detach(), w_l1 * proj[1].detach()]))
+        st.advance()
+
+    def _step_body_fused(self, residual: bool) -> None:
+        """The same step with the models, their backward and the optimiser as hand-written launches over the
+        parameter arena: no autograd, ~30 launches in total.  The projection / matching kernel (one CTA, ~50 us
+        of latency) and the ray draw run on a side stream next to the hypernetwork forward; captured into the
+        step's CUDA graph they become parallel branches."""
+        st, arena, main = self.state, self.arena, torch.cuda.current_stream()
+        side, side2 = self.side_stream, self.side_stream2
+        w = self.weights
+        loc, dim, rot, boxes_3d = arena.decode()
+        # branch 1: projection + matching (+ target gather, which needs the matched ground-truth order)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            _, gt_indices, proj_losses, proj_grad = ops.projection_step(self.views, boxes_3d, self.gt_boxes, self.visible)
+        # branch 2: the ray batch of this step
+        if self.rays == "draw":
+            side2.wait_stream(main)
+            with torch.cuda.stream(side2):
+                pix, status = ops.select_rays(self.cdf, self.num_rays, step_state=st)
+                self.draw_failures.add_(status)
+                self.pixel_indices.copy_(pix)
+                origins, directions = ops.gather_rays(self.inv_projection, self.camera_positions, self.pixel_indices,
+                                                      self.height, self.width)
+            side.wait_stream(side2)
+        else:
+            origins, directions = ops.gather_rays(self.inv_projection, self.camera_positions, self.pixel_indices,
+                                                  self.height, self.width)
+        if self.rays != "batches":
+            with torch.cuda.stream(side):
+                self.targets.copy_(ops.gather_targets(self.inputs.soft_masks, self.pixel_indices, gt_indices))
+        mlp_weights = arena.hyper_forward() if residual else None
+        if self.rays != "batches":
+            main.wait_stream(side)            # "batches": the projection branch joins just before the decode backward
+
+        eik_w = w["eikonal_loss"] if residual else 0.0
+        scene = ops.SceneArgs(loc, rot, dim, mlp_weights, 1.0, self.scale, st)
+        coarse = ops.place_coarse(self.bins, self.num_rays, self.jitter, 0, st)
+        rays = ops.RayArgs(origins, directions, coarse)
+        field = ops.field_forward(scene, rays)
+        _, _, coarse_w, _ = ops.composite_forward(scene, rays, field, 1.0, 0.0, 1e-6)
+        fine = ops.place_fine(coarse, coarse_w, self.sorted_uniforms, 0, st)
+        rays = ops.RayArgs(origins, directions, fine)
+        field = ops.field_forward(scene, rays)
+        labels, _, _, parts = ops.composite_forward(scene, rays, field, 1.0, 0.0, 1e-6, targets=self.targets,
+                                                    silhouette_weight=w["silhouette_loss"], eikonal_weight=eik_w)
+        adjoint = ops.composite_backward(scene, rays, field, 1.0, 0.0, 1e-6, targets=self.targets, labels=labels,
+                                         silhouette_weight=w["silhouette_loss"], eikonal_weight=eik_w)
+        g_loc, g_rot, g_dim, g_w = ops.field_backward(scene, rays, adjoint)
+        if residual:
+            arena.hyper_backward(g_w)
+        if self.rays == "batches":
+            main.wait_stream(side)
+        arena.decode_backward(dim, rot, g_loc, g_dim, g_rot, proj_grad, w["iou_projection_loss"], w["l1_projection_loss"],
+                              parts, proj_losses, self.losses)
+        arena.adam_step(st)
         st.advance()
 
     def _capture(self, residual: bool) -> None:

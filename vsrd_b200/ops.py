@@ -390,3 +390,63 @@ def sphere_trace_step(union_out, directions, positions, foreground, converged, a
     _lib.check(_lib.load().vsrd_sphere_trace_step(
         _ptr(union_out), _ptr(directions), int(directions.shape[0] == p and p > 0), p, float(convergence_criteria),
         float(bounding_radius or 0.0), _ptr(positions), _ptr(foreground), _ptr(converged), _ptr(active), int(iteration), _stream()))
+
+
+# ---- a3 / a4 / a16: models and optimiser (csrc/vsrd_model.cu) --------------------------------------
+
+def hyper_forward(net: "_lib.VsrdHyperNet", embeddings: torch.Tensor, activations: Optional[torch.Tensor] = None,
+                  mlp_weights: Optional[torch.Tensor] = None):
+    """HyperDistanceField.forward: embeddings [N,256] -> (mlp_weights [N,out], activations [L-1,N,256])."""
+    emb = _f32(embeddings, "embeddings").reshape(-1, _lib.HYPER_WIDTH)
+    n, layers = emb.shape[0], net.num_layers
+    out_features = net.layers[layers - 1].out_features
+    if activations is None:
+        activations = torch.empty(layers - 1, n, _lib.HYPER_WIDTH, device=emb.device, dtype=torch.float32)
+    if mlp_weights is None:
+        mlp_weights = torch.empty(n, out_features, device=emb.device, dtype=torch.float32)
+    _lib.check(_lib.load().vsrd_hyper_forward(ctypes.byref(net), _ptr(emb), n, _ptr(activations), _ptr(mlp_weights), _stream()))
+    return mlp_weights, activations
+
+
+def hyper_backward(net, grads, embeddings: torch.Tensor, activations: torch.Tensor, grad_mlp_weights: torch.Tensor,
+                   grad_embeddings: torch.Tensor) -> None:
+    """Backward of `hyper_forward`: fills every tensor `grads` points at and grad_embeddings [N,256]."""
+    emb = _f32(embeddings, "embeddings").reshape(-1, _lib.HYPER_WIDTH)
+    n = emb.shape[0]
+    gw = _f32(grad_mlp_weights, "grad_mlp_weights").reshape(n, -1)
+    scratch = torch.empty(_lib.load().vsrd_hyper_scratch_floats(n), device=emb.device, dtype=torch.float32)
+    _lib.check(_lib.load().vsrd_hyper_backward(ctypes.byref(net), ctypes.byref(grads), _ptr(emb), n, _ptr(activations),
+                                               _ptr(gw), _ptr(grad_embeddings), _ptr(scratch), _stream()))
+
+
+def decode_boxes(ranges, raw_locations, raw_dimensions, raw_orientations):
+    """BoxParameters3D.forward on raw [N,3], [N,3], [N,2] -> (locations, half_extents, rotations [N,3,3], boxes_3d [N,8,3])."""
+    loc = _f32(raw_locations, "raw_locations").reshape(-1, 3)
+    n, dev = loc.shape[0], loc.device
+    dim = _f32(raw_dimensions, "raw_dimensions").reshape(n, 3)
+    ori = _f32(raw_orientations, "raw_orientations").reshape(n, 2)
+    out = [torch.empty(n, *s, device=dev, dtype=torch.float32) for s in ((3,), (3,), (3, 3), (8, 3))]
+    _lib.check(_lib.load().vsrd_decode_boxes(ctypes.byref(ranges), _ptr(loc), _ptr(dim), _ptr(ori), n,
+                                             *[_ptr(t) for t in out], _stream()))
+    return tuple(out)
+
+
+def decode_boxes_backward(ranges, raw_locations, raw_dimensions, raw_orientations, half_extents, rotations,
+                          grad_locations, grad_half_extents, grad_rotations, grad_boxes_3d, iou_weight, l1_weight,
+                          grad_raw_locations, grad_raw_dimensions, grad_raw_orientations,
+                          render_loss_parts=None, projection_losses=None, losses=None) -> None:
+    n = raw_locations.reshape(-1, 3).shape[0]
+    _lib.check(_lib.load().vsrd_decode_boxes_backward(
+        ctypes.byref(ranges), _ptr(raw_locations), _ptr(raw_dimensions), _ptr(raw_orientations), n,
+        _ptr(half_extents), _ptr(rotations), _ptr(grad_locations), _ptr(grad_half_extents), _ptr(grad_rotations),
+        _ptr(grad_boxes_3d), float(iou_weight), float(l1_weight), _ptr(grad_raw_locations), _ptr(grad_raw_dimensions),
+        _ptr(grad_raw_orientations), _ptr(render_loss_parts), _ptr(projection_losses), _ptr(losses), _stream()))
+
+
+def adam_step(params, grads, exp_avg, exp_avg_sq, groups, step_state=None, step: int = 0) -> None:
+    """torch.optim.Adam + ExponentialLR over a flat arena (see include/vsrd_b200.h VsrdAdamGroups)."""
+    for t, name in ((params, "params"), (grads, "grads"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq")):
+        if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != params.numel():
+            raise RuntimeError(f"vsrd_b200: {name} must be a contiguous CUDA float32 tensor of the arena's size")
+    _lib.check(_lib.load().vsrd_adam_step(_ptr(params), _ptr(grads), _ptr(exp_avg), _ptr(exp_avg_sq), params.numel(),
+                                          ctypes.byref(groups), _state_ptr(step_state), int(step), _stream()))
