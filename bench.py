@@ -408,23 +408,38 @@ def run_native(args):
     labeler.state.set_step(start_step)
     labeler.step_index = start_step
     pool_pin, targets_pin = pool.pin_memory(), targets.pin_memory()
-    loss_pin = torch.zeros(5, dtype=torch.float32).pin_memory()
+    loss_pin = [torch.zeros(5, dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_ready = [torch.cuda.Event() for _ in range(2)]
 
-    def e2e_step(k):
-        labeler.step(pool_pin[k], targets_pin[k])                        # H2D copies + graph replay on the labeler's stream
+    def e2e_enqueue(k):
+        """Step k: H2D copies of its ray batch + graph replay + D2H copy of its losses, all on the labeler's stream."""
+        labeler.step(pool_pin[k], targets_pin[k])
         with torch.cuda.stream(labeler.stream):
-            loss_pin.copy_(labeler.losses, non_blocking=True)            # D2H: the step's losses
-        labeler.stream.synchronize()
-        return float(loss_pin[0])
+            loss_pin[k & 1].copy_(labeler.losses, non_blocking=True)
+            loss_ready[k & 1].record()
 
-    for k in range(W):
-        e2e_step(k)
+    def e2e_read(k):
+        loss_ready[k & 1].synchronize()
+        return float(loss_pin[k & 1][0])
+
+    def e2e_run(first, count):
+        """Every step's loss is read on the host; the read of step k overlaps the execution of step k+1 (the
+        reference itself reads losses every 50 steps only, main.py:872)."""
+        last = float("nan")
+        for k in range(first, first + count):
+            e2e_enqueue(k)
+            if k > first:
+                last = e2e_read(k - 1)
+                if not math.isfinite(last):
+                    raise RuntimeError("bench.py: non-finite loss from the end-to-end leg")
+        return e2e_read(first + count - 1)
+
+    e2e_run(0, W)
     barrier()
     e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(labeler.stream):
         e_start.record()
-    for k in range(K):
-        last = e2e_step(W + k)
+    last = e2e_run(W, K)
     with torch.cuda.stream(labeler.stream):
         e_end.record()
     barrier()
@@ -445,7 +460,7 @@ def run_native(args):
         def torch_step(k):
             lab2.step(pool_pin[k], targets_pin[k])
             with torch.cuda.stream(lab2.stream):
-                loss_pin.copy_(lab2.losses, non_blocking=True)
+                loss_pin[0].copy_(lab2.losses, non_blocking=True)
             lab2.stream.synchronize()
 
         for k in range(W + 2):

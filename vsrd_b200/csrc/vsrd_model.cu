@@ -34,7 +34,8 @@ constexpr int kHW = VSRD_HYPER_WIDTH;        // hypernetwork width == embedding 
 constexpr int kThreadsM = 256;
 constexpr int kWarpsM = kThreadsM / 32;
 constexpr int kPL = kHW / 32;                // channels per lane of a 256-wide row
-constexpr int kHiddenCtas = 16;              // CTAs (= partial sums) of a hidden layer's backward
+constexpr int kHiddenCtas = 32;              // CTAs (= partial sums) of a hidden layer's backward
+constexpr int kMaxRowsPerCta = 64;           // rows of one Linear a backward CTA may own
 constexpr int kLastCtas = 64;                // ... of the output layer's backward
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -137,13 +138,30 @@ __global__ void __launch_bounds__(kThreadsM) hyper_layer_backward_kernel(LayerBa
     extern __shared__ __align__(16) float smem_m[];
     const int N = a.N, O = a.O;
     float* sA = smem_m;                   // [N][256] input activations
-    float* sDA = sA + N * kHW;            // [N][256] this CTA's partial of dL/d(input activations); xhat scratch first
+    float* sDA = sA + N * kHW;            // [N][256] xhat scratch of the LayerNorm adjoint
     float* sDY = sDA + N * kHW;           // [N][256] upstream gradient (hidden layers only)
     __shared__ float sRstd[VSRD_MAX_INSTANCES];
+    __shared__ float sScaled[kMaxRowsPerCta * 32];   // [local row][instance] dy g / |v|
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     stage_activations(a.x_in, a.ln_in_w, a.ln_in_b, N, sA);
     if (a.dy == nullptr) {
+        // sDY <- sum of the partials of the layer above: 128-bit loads, all partials of a chunk in flight at once
+        {
+            const float4* src = reinterpret_cast<const float4*>(a.partials_in);
+            float4* dst = reinterpret_cast<float4*>(sDY);
+            const int chunks = N * (kHW / 4);
+            for (int e = threadIdx.x; e < chunks; e += kThreadsM) {
+                float4 s = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll 8
+                for (int p = 0; p < a.num_partials; ++p) {
+                    const float4 v = __ldg(src + (size_t)p * chunks + e);
+                    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+                }
+                dst[e] = s;
+            }
+        }
+        __syncthreads();
         // dz = (sum of partials) * gelu'(z), z = LayerNorm(y_out) affine; keep dz in sDY and xhat in sDA
         for (int n = warp; n < N; n += kWarpsM) {
             float y[kPL], xhat[kPL], rstd;
@@ -154,10 +172,8 @@ __global__ void __launch_bounds__(kThreadsM) hyper_layer_backward_kernel(LayerBa
 #pragma unroll
             for (int k = 0; k < kPL; ++k) {
                 const int i = lane + 32 * k;
-                float da = 0.0f;
-                for (int p = 0; p < a.num_partials; ++p) da += __ldg(a.partials_in + ((size_t)p * N + n) * kHW + i);
                 const float z = fmaf(xhat[k], __ldg(a.ln_out_w + i), __ldg(a.ln_out_b + i));
-                sDY[n * kHW + i] = da * gelu_slope(z);
+                sDY[n * kHW + i] *= gelu_slope(z);
                 sDA[n * kHW + i] = xhat[k];
             }
         }
@@ -189,75 +205,73 @@ __global__ void __launch_bounds__(kThreadsM) hyper_layer_backward_kernel(LayerBa
     }
     __syncthreads();
 
-    for (int c = 0; c < N; c += 8) {          // instances in chunks of 8 accumulators per channel
-        float acc[8][kPL];
+    // phase 1, one warp per output row: dW = dy^T a with the weight-norm adjoint, db; the row's scaled upstream
+    // gradient dy[n][o] g / |v| is parked in shared memory for phase 2
+    const int row_stride = gridDim.x * kWarpsM;
+    int r = warp;                                  // local row index: o = blockIdx.x * 8 + (r & 7) + (r >> 3) * row_stride
+    for (int o = blockIdx.x * kWarpsM + warp; o < O; o += row_stride, r += kWarpsM) {
+        float v[kPL], q = 0.0f;
+#pragma unroll
+        for (int k = 0; k < kPL; ++k) { v[k] = __ldg(a.wv + (size_t)o * kHW + lane + 32 * k); q = fmaf(v[k], v[k], q); }
+        const float inv = 1.0f / sqrtf(warp_sum(q));
+        const float g = __ldg(a.wg + o);
+        const float scale = g * inv;
+        float mine = 0.0f;                         // lane n holds dy[n][o]
+        if (lane < N) mine = a.dy != nullptr ? __ldg(a.dy + (size_t)lane * O + o) : sDY[lane * kHW + o];
+        sScaled[r * 32 + lane] = mine * scale;
+        float dw[kPL], db = 0.0f;
+#pragma unroll
+        for (int k = 0; k < kPL; ++k) dw[k] = 0.0f;
+        for (int n = 0; n < N; ++n) {
+            const float d = __shfl_sync(kFull, mine, n);
+            db += d;
+#pragma unroll
+            for (int k = 0; k < kPL; ++k) dw[k] = fmaf(d, sA[n * kHW + lane + 32 * k], dw[k]);
+        }
+        float s = 0.0f;
+#pragma unroll
+        for (int k = 0; k < kPL; ++k) s = fmaf(dw[k], v[k], s);
+        s = warp_sum(s);
+        // w = g v / |v|:  dg = (dw . v) / |v|,  dv = (g / |v|) dw - (g (dw . v) / |v|^3) v
+        const float back = g * s * inv * inv * inv;
+#pragma unroll
+        for (int k = 0; k < kPL; ++k) a.g_wv[(size_t)o * kHW + lane + 32 * k] = fmaf(scale, dw[k], -back * v[k]);
+        if (lane == 0) { a.g_wg[o] = s * inv; a.g_bias[o] = db; }
+    }
+    __syncthreads();
+    // phase 2, one warp per 32 input channels: this CTA's partial of da[n][i] = sum_o dy[n][o] w[o][i] over its rows,
+    // accumulated in row order by the lane that owns channel i (no cross-warp reduction, deterministic)
+    const int i = 32 * warp + lane;
+    const int rows = (O - blockIdx.x * kWarpsM + row_stride - 1) / row_stride * kWarpsM;    // upper bound on local rows
+    float* out = a.partials_out + (size_t)blockIdx.x * N * kHW;
+    for (int c = 0; c < N; c += 8) {               // instances in chunks of 8 accumulators
+        float acc[8];
+#pragma unroll
+        for (int nn = 0; nn < 8; ++nn) acc[nn] = 0.0f;
+#pragma unroll 4
+        for (int rr = 0; rr < rows; ++rr) {
+            const int o = blockIdx.x * kWarpsM + (rr & (kWarpsM - 1)) + (rr >> 3) * row_stride;
+            if (o < O) {
+                const float wv = __ldg(a.wv + (size_t)o * kHW + i);
+#pragma unroll
+                for (int nn = 0; nn < 8; ++nn) acc[nn] = fmaf(sScaled[rr * 32 + ((c + nn) & 31)], wv, acc[nn]);
+            }
+        }
 #pragma unroll
         for (int nn = 0; nn < 8; ++nn)
-#pragma unroll
-            for (int k = 0; k < kPL; ++k) acc[nn][k] = 0.0f;
-        for (int o = blockIdx.x * kWarpsM + warp; o < O; o += gridDim.x * kWarpsM) {
-            float v[kPL], q = 0.0f;
-#pragma unroll
-            for (int k = 0; k < kPL; ++k) { v[k] = __ldg(a.wv + (size_t)o * kHW + lane + 32 * k); q = fmaf(v[k], v[k], q); }
-            const float inv = 1.0f / sqrtf(warp_sum(q));
-            const float g = __ldg(a.wg + o);
-            const float scale = g * inv;
-            float mine = 0.0f;                 // lane n holds dy[n][o]
-            if (lane < N) mine = a.dy != nullptr ? __ldg(a.dy + (size_t)lane * O + o) : sDY[lane * kHW + o];
-            if (c == 0) {
-                float dw[kPL], db = 0.0f;
-#pragma unroll
-                for (int k = 0; k < kPL; ++k) dw[k] = 0.0f;
-                for (int n = 0; n < N; ++n) {
-                    const float d = __shfl_sync(kFull, mine, n);
-                    db += d;
-#pragma unroll
-                    for (int k = 0; k < kPL; ++k) dw[k] = fmaf(d, sA[n * kHW + lane + 32 * k], dw[k]);
-                }
-                float s = 0.0f;
-#pragma unroll
-                for (int k = 0; k < kPL; ++k) s = fmaf(dw[k], v[k], s);
-                s = warp_sum(s);
-                // w = g v / |v|:  dg = (dw . v) / |v|,  dv = (g / |v|) dw - (g (dw . v) / |v|^3) v
-                const float back = g * s * inv * inv * inv;
-#pragma unroll
-                for (int k = 0; k < kPL; ++k) a.g_wv[(size_t)o * kHW + lane + 32 * k] = fmaf(scale, dw[k], -back * v[k]);
-                if (lane == 0) { a.g_wg[o] = s * inv; a.g_bias[o] = db; }
-            }
-#pragma unroll
-            for (int nn = 0; nn < 8; ++nn) {
-                const float d = __shfl_sync(kFull, mine, (c + nn) & 31) * scale;
-                if (c + nn < N) {
-#pragma unroll
-                    for (int k = 0; k < kPL; ++k) acc[nn][k] = fmaf(d, v[k], acc[nn][k]);
-                }
-            }
-        }
-        // the 8 warps add their accumulators into the CTA's partial one after the other (fixed order)
-        for (int w = 0; w < kWarpsM; ++w) {
-            if (warp == w) {
-#pragma unroll
-                for (int nn = 0; nn < 8; ++nn)
-                    if (c + nn < N) {
-#pragma unroll
-                        for (int k = 0; k < kPL; ++k) {
-                            float* p = sDA + (c + nn) * kHW + lane + 32 * k;
-                            *p = (w == 0 ? 0.0f : *p) + acc[nn][k];
-                        }
-                    }
-            }
-            __syncthreads();
-        }
+            if (c + nn < N) out[(size_t)(c + nn) * kHW + i] = acc[nn];
     }
-    float* out = a.partials_out + (size_t)blockIdx.x * N * kHW;
-    for (int e = threadIdx.x; e < N * kHW; e += kThreadsM) out[e] = sDA[e];
 }
 
-__global__ void sum_partials_kernel(const float* __restrict__ partials, int num_partials, int count, float* __restrict__ out) {
+__global__ void sum_partials_kernel(const float4* __restrict__ partials, int num_partials, int chunks, float4* __restrict__ out) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= count) return;
-    float s = 0.0f;
-    for (int p = 0; p < num_partials; ++p) s += __ldg(partials + (size_t)p * count + e);
+    if (e >= chunks) return;
+    float4 s = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll 8
+    for (int p = 0; p < num_partials; ++p) {
+        const float4 v = __ldg(partials + (size_t)p * chunks + e);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
     out[e] = s;
 }
 
@@ -503,7 +517,7 @@ int vsrd_hyper_backward(const VsrdHyperNet* net, const VsrdHyperNetGrads* grads,
     VSRD_CHECK_ARG(embeddings && activations && grad_mlp_weights && grad_embeddings && scratch, "hyper backward pointers must not be NULL");
     if (model::setup()) return 1;
     const int N = num_instances, L = net->num_layers;
-    float* part[2] = {scratch, scratch + (size_t)kLastCtas * N * kHW};     // ping (64 partials) / pong (16 partials)
+    float* part[2] = {scratch, scratch + (size_t)kLastCtas * N * kHW};     // ping (output layer's partials first) / pong
     int prev_partials = 0;
     for (int l = L - 1; l >= 0; --l) {
         const VsrdHyperLayer& P = net->layers[l];
@@ -528,13 +542,18 @@ int vsrd_hyper_backward(const VsrdHyperNet* net, const VsrdHyperNetGrads* grads,
         a.g_wv = G.weight_v; a.g_wg = G.weight_g; a.g_bias = G.bias;
         a.partials_out = part[(L - 1 - l) & 1];
         const int grid = last ? kLastCtas : kHiddenCtas;
+        VSRD_CHECK_ARG((P.out_features + grid * kWarpsM - 1) / (grid * kWarpsM) * kWarpsM <= kMaxRowsPerCta,
+                       "output layer too wide for the backward kernel's row table");
         const size_t smem = (size_t)(last ? 2 : 3) * N * kHW * sizeof(float);
         hyper_layer_backward_kernel<<<grid, kThreadsM, smem, (cudaStream_t)stream>>>(a);
         VSRD_CHECK_LAUNCH();
         prev_partials = grid;
     }
-    const int count = N * kHW;
-    sum_partials_kernel<<<(count + 255) / 256, 256, 0, (cudaStream_t)stream>>>(part[(L - 1) & 1], prev_partials, count, grad_embeddings);
+    VSRD_CHECK_ARG((reinterpret_cast<uintptr_t>(scratch) & 15) == 0 && (reinterpret_cast<uintptr_t>(grad_embeddings) & 15) == 0,
+                   "scratch and grad_embeddings must be 16-byte aligned");
+    const int chunks = N * kHW / 4;
+    sum_partials_kernel<<<(chunks + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(part[(L - 1) & 1]), prev_partials, chunks, reinterpret_cast<float4*>(grad_embeddings));
     VSRD_CHECK_LAUNCH();
     return 0;
 }
