@@ -585,7 +585,12 @@ def run_native(args):
             "gpu_launches": SilhouetteStep.KERNELS_PER_STEP * K,
             "roofline": {"bound": "fp32_fma", "kernel": "field_backward_kernel<residual>", "achieved": achieved,
                          "peak": fma_peak_tflops, "unit": "TFLOP/s",
-                         "frac": (achieved / fma_peak_tflops) if achieved else None, "traffic": None,
+                         "frac": (achieved / fma_peak_tflops) if achieved else None,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this exact shape, from the
+                         # `ncu --set full` capture summarised in profiles/r01_v8_ncu_summary.txt (one pass over the
+                         # 25.5 MB adjoint buffer; everything else stays in L2 / shared memory)
+                         "traffic": (26452480 + 1280) if (args.rays, args.samples, args.instances) == (1000, 100, 8) else None,
+                         "traffic_unit": "bytes per launch (ncu --set full, profiles/r01_v8_ncu_summary.txt)",
                          "peak_source": f"{sms} SMs x 128 lanes x 2 x sm_max_mhz {sm_max:.0f} (MEASURED_PEAKS.json clock)",
                          "kernel_ms": bwd_ms, "algorithmic_flops_per_launch": bwd_flops,
                          "algorithmic_hbm_bytes_per_step": hbm_bytes,
