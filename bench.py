@@ -326,7 +326,18 @@ def run_native(args):
     device = torch.device("cuda", local_rank)
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=device)
+        # NCCL prints its version banner on the C-level stdout at communicator creation; the driver reads ONE JSON
+        # line from stdout, so point fd 1 at stderr until the communicator exists
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=device)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     _lib.load()
 
     K, W = args.steps, max(args.warmup, 3)
