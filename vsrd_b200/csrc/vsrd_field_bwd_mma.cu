@@ -7,7 +7,7 @@
 // w.r.t. the 1617 MLP weights and the 15 pose parameters of the instance ("one tangent + one reverse
 // sweep"; the scalar restatement is vsrd_math.cuh::field_backward).
 //
-// One warp owns a tile of 32 samples of one instance in the mma.sync fragment layout of vsrd_frag.cuh:
+// One warp owns a tile of 16 MT samples of one instance in the mma.sync fragment layout of vsrd_frag.cuh:
 //   1. lane == sample: position, box SDF, tangent direction v = R^T dG, PE arguments
 //   2. dual forward sweep (value + tangent along v): 3xTF32 mma.sync contractions chained in registers,
 //      LayerNorm statistics by quad reductions; LayerNorm outputs (z, zd) of layers 1..3 go to a
@@ -28,17 +28,27 @@
 namespace vsrd {
 namespace bwd5 {
 
-constexpr int kWarpsB = 8;
-constexpr int kThreadsB = kWarpsB * 32;
-constexpr int kStashFloats = 3 * 32 * 32;     // per warp: layers 1..3 x [z 8 pair rows | zd 8 pair rows] x 32 lanes (float2)
 constexpr int kAccHidden = 0;                 // hidden layer l: fragments 3 (l-1) + {inputs 0-7, inputs 8-15, bias}
 constexpr int kAccL0 = 9;                     // layer 0: input tiles 0..5, bias
 constexpr int kAccLast = 16;                  // last layer: this lane's 4 channels
 constexpr int kAccPose = 17;                  // (sum obar, pose 0..2) (pose 3..6) (pose 7..10) (pose 11..14), lane == sample
-constexpr int kAccFrags = 21;
-constexpr int kAccFloat4 = kAccFrags * 32;
-constexpr size_t kSmemBytes = frag::kWeightBytes
-    + (size_t)kWarpsB * (kAccFloat4 * sizeof(float4) + kStashFloats * sizeof(float) + 32 * sizeof(float));
+
+// MT = m-tiles (16 samples) per warp tile.  MT = 2: 8 warps x 255 registers, pose accumulators in shared memory.
+// MT = 1: 12 warps x <= 168 registers (3 warps per scheduler instead of 2), pose accumulators in registers so that
+// 12 warps' weight-gradient accumulators + stashes still fit the 227 KB of shared memory.
+template <int MT>
+struct BwdCfg {
+    static constexpr int kWarps = MT == 2 ? 8 : 12;
+    static constexpr int kThreads = kWarps * 32;
+    static constexpr int kRows = 16 * MT;
+    static constexpr bool kPoseInRegs = MT == 1;
+    static constexpr int kAccFrags = kPoseInRegs ? 17 : 21;
+    static constexpr int kAccFloat4 = kAccFrags * 32;
+    static constexpr int kLayerPairs = 4 * MT;                      // pair rows (float2 x 32 lanes) of z per layer; as many of zd
+    static constexpr int kStashFloats = 3 * 2 * kLayerPairs * 32 * 2;   // per warp: layers 1..3 x [z | zd]
+    static constexpr size_t kSmemBytes = frag::kWeightBytes
+        + (size_t)kWarps * (kAccFloat4 * sizeof(float4) + kStashFloats * sizeof(float) + 32 * sizeof(float));
+};
 
 using frag::f2;
 using frag::bc;
@@ -128,21 +138,26 @@ __device__ __forceinline__ void pose_terms(const float x[3], const Instance& I, 
     p.coef[2] = pi_scale;
 }
 
-__global__ void __launch_bounds__(kThreadsB, 1) field_backward_mma_kernel(
+template <int MT>
+__global__ void __launch_bounds__(BwdCfg<MT>::kThreads, 1) field_backward_mma_kernel(
         SceneDev scene, RaysDev rays, const float4* __restrict__ adjoint, float* __restrict__ partials,
         int tiles_per_inst) {
+    using Cfg = BwdCfg<MT>;
+    constexpr int kWarpsB = Cfg::kWarps, kThreadsB = Cfg::kThreads, kRows = Cfg::kRows, kSlots = 2 * MT;
+    constexpr int kAccFloat4 = Cfg::kAccFloat4, kAccFrags = Cfg::kAccFrags, kLayerPairs = Cfg::kLayerPairs;
+    constexpr int kLayerStride = 2 * kLayerPairs * 32;      // float2 per layer in the stash
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4* sF = reinterpret_cast<float4*>(smem_raw);
     float* sTail = reinterpret_cast<float*>(sF + frag::kFragFloat4);
     float4* sAcc = reinterpret_cast<float4*>(sTail + frag::kTailFloats);
     float* sStash = reinterpret_cast<float*>(sAcc + kWarpsB * kAccFloat4);
-    float* sRed = sStash + kWarpsB * kStashFloats;          // [warp][32]: last layer (17) + pose (15)
+    float* sRed = sStash + kWarpsB * Cfg::kStashFloats;     // [warp][32]: last layer (17) + pose (15)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int t = lane & 3;
     const int quad_base = lane & ~3;
     float4* accL = sAcc + warp * kAccFloat4 + lane;         // accL[fragment * 32]
-    float2* stash = reinterpret_cast<float2*>(sStash + warp * kStashFloats) + lane;
+    float2* stash = reinterpret_cast<float2*>(sStash + warp * Cfg::kStashFloats) + lane;
     const float4* fragL = sF + lane;
 
     const int total = rays.R * rays.M;
@@ -165,20 +180,24 @@ __global__ void __launch_bounds__(kThreadsB, 1) field_backward_mma_kernel(
         const f2 w4p0 = make_float2(sTail[frag::kTailW4 + 2 * t], sTail[frag::kTailW4 + 2 * t + 1]);
         const f2 w4p1 = make_float2(sTail[frag::kTailW4 + 8 + 2 * t], sTail[frag::kTailW4 + 8 + 2 * t + 1]);
         const float b4 = sTail[frag::kTailB4];
+        float pose_reg[Cfg::kPoseInRegs ? 16 : 1];          // (sum obar, pose 0..14) of this lane's samples
+#pragma unroll
+        for (int k = 0; k < (Cfg::kPoseInRegs ? 16 : 1); ++k) pose_reg[k] = 0.0f;
 
 #pragma unroll 1
         for (long long tile = seg + warp; tile < seg_end; tile += kWarpsB) {
-            const int base = (int)(tile - (long long)inst * tiles_per_inst) * 32;
-            const int idx = min(base + lane, total - 1);
-            const bool valid = base + lane < total;
+            const int base = (int)(tile - (long long)inst * tiles_per_inst) * kRows;
+            const int row = lane & (kRows - 1);             // MT = 1: lanes 16..31 shadow rows 0..15 with zero adjoints
+            const int idx = min(base + row, total - 1);
+            const bool valid = lane < kRows && base + row < total;
             const int r = idx / rays.M;
             const int j = idx - r * rays.M;
             // ------------------------------------------------------------ 1. lane == sample
             float4 adj = make_float4(0.0f, 0.0f, 0.0f, 0.0f);   // zero adjoints contribute exactly zero
             if (valid) adj = __ldg(adj_inst + idx);
             if (!__any_sync(kFull, adj.x != 0.0f || adj.y != 0.0f || adj.z != 0.0f || adj.w != 0.0f)) continue;
-            f2 arow[2][3], adrow[2][3];                    // pairs = rows (g, g + 8) of each m-tile
-            float ddrow[4];
+            f2 arow[MT][3], adrow[MT][3];                  // pairs = rows (g, g + 8) of each m-tile
+            float ddrow[kSlots];
             {
                 float x[3];
                 sample_position(rays, r, j, x);
@@ -189,26 +208,29 @@ __global__ void __launch_bounds__(kThreadsB, 1) field_backward_mma_kernel(
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     const float vc = I.R[c] * adj.y + I.R[3 + c] * adj.z + I.R[6 + c] * adj.w;
-                    float v[4];
-                    frag::lanes_to_rows(kPiF * (m[c] / scene.scale), lane, v);
-                    arow[0][c] = make_float2(v[0], v[1]);
-                    arow[1][c] = make_float2(v[2], v[3]);
-                    frag::lanes_to_rows(coef[c] * vc, lane, v);
-                    adrow[0][c] = make_float2(v[0], v[1]);
-                    adrow[1][c] = make_float2(v[2], v[3]);
+                    f2 v[MT];
+                    frag::lanes_to_row_pairs<MT>(kPiF * (m[c] / scene.scale), lane, v);
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) arow[mt][c] = v[mt];
+                    frag::lanes_to_row_pairs<MT>(coef[c] * vc, lane, v);
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) adrow[mt][c] = v[mt];
                 }
-                frag::lanes_to_rows(adj.x, lane, ddrow);
+                f2 v[MT];
+                frag::lanes_to_row_pairs<MT>(adj.x, lane, v);
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) { ddrow[2 * mt] = v[mt].x; ddrow[2 * mt + 1] = v[mt].y; }
             }
             // ------------------------------------------------------------ 2. dual forward sweep
-            frag::Encoding2 e;
-            frag::encode2(arow, t, e);
+            frag::EncodingT<MT> e;
+            frag::encode2<MT>(arow, t, e);
             const float f0 = (float)(1 << t), f1 = 16.0f * f0;
-            f2 h[2][2][2], hd[2][2][2];                    // [m-tile][n-tile][row g | row g + 8]
+            f2 h[MT][2][2], hd[MT][2][2];                  // [m-tile][n-tile][row g | row g + 8]
 #pragma unroll
             for (int nt = 0; nt < 2; ++nt) {
                 const f2 bias = make_float2(sTail[8 * nt + 2 * t], sTail[8 * nt + 2 * t + 1]);
 #pragma unroll
-                for (int mt = 0; mt < 2; ++mt) { h[mt][nt][0] = bias; h[mt][nt][1] = bias; }
+                for (int mt = 0; mt < MT; ++mt) { h[mt][nt][0] = bias; h[mt][nt][1] = bias; }
             }
 #pragma unroll
             for (int c = 0; c < 3; ++c)
@@ -218,7 +240,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) field_backward_mma_kernel(
                     const float fk = f ? f1 : f0;
                     const float4 w0 = fragL[(frag::kF0 + 2 * ks) * 32], w1 = fragL[(frag::kF0 + 2 * ks + 1) * 32];
 #pragma unroll
-                    for (int mt = 0; mt < 2; ++mt) {
+                    for (int mt = 0; mt < MT; ++mt) {
                         const f2 cs = e.cs[mt][c][f], sn = e.sn[mt][c][f];
                         uint32_t ah[4], al[4], adh[4], adl[4];
                         frag::a_from_row_pairs(cs, sn, ah, al);
@@ -235,12 +257,14 @@ __global__ void __launch_bounds__(kThreadsB, 1) field_backward_mma_kernel(
                     }
                 }
             // layers 1..3: LayerNorm -> GELU -> linear; lane t keeps 1/sigma and mz of layer t + 1
-            float rreg[4] = {0.0f, 0.0f, 0.0f, 0.0f}, mreg[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            float rreg[kSlots], mreg[kSlots];
+#pragma unroll
+            for (int s = 0; s < kSlots; ++s) { rreg[s] = 0.0f; mreg[s] = 0.0f; }
 #pragma unroll 1
             for (int l = 1; l <= 3; ++l) {
-                float2* st = stash + (l - 1) * 16 * 32;
+                float2* st = stash + (l - 1) * kLayerStride;
 #pragma unroll
-                for (int s = 0; s < 4; ++s) {
+                for (int s = 0; s < kSlots; ++s) {
                     f2& p0 = h[s >> 1][0][s & 1];
                     f2& p1 = h[s >> 1][1][s & 1];
                     f2& d0 = hd[s >> 1][0][s & 1];
@@ -249,7 +273,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) field_backward_mma_kernel(
                     ln_dual2(p0, p1, d0, d1, rs, mz);
                     if (t == l - 1) { rreg[s] = rs; mreg[s] = mz; }
                     st[(2 * s) * 32] = p0; st[(2 * s + 1) * 32] = p1;
-                    st[(8 + 2 * s) * 32] = d0; st[(8 + 2 * s + 1) * 32] = d1;
+                    st[(kLayerPairs + 2 * s) * 32] = d0; st[(kLayerPairs + 2 * s + 1) * 32] = d1;
                     f2 Phi, phi, zz;
                     frag::gelu_terms2(p0, Phi, phi, zz);
                     d0 = mul2(d0, fma2(p0, phi, Phi));
@@ -258,12 +282,12 @@ __global__ void __launch_bounds__(kThreadsB, 1) field_backward_mma_kernel(
                     d1 = mul2(d1, fma2(p1, phi, Phi));
                     p1 = mul2(p1, Phi);
                 }
-                f2 hn[2][2][2], hdn[2][2][2];
+                f2 hn[MT][2][2], hdn[MT][2][2];
 #pragma unroll
                 for (int nt = 0; nt < 2; ++nt) {
                     const f2 bias = make_float2(sTail[16 * l + 8 * nt + 2 * t], sTail[16 * l + 8 * nt + 2 * t + 1]);
 #pragma unroll
-                    for (int mt = 0; mt < 2; ++mt) {
+                    for (int mt = 0; mt < MT; ++mt) {
                         hn[mt][nt][0] = bias; hn[mt][nt][1] = bias;
                         hdn[mt][nt][0] = bc(0.0f); hdn[mt][nt][1] = bc(0.0f);
                     }
@@ -273,7 +297,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) field_backward_mma_kernel(
                 for (int ks = 0; ks < 2; ++ks) {
                     const float4 w0 = fl[(2 * ks) * 32], w1 = fl[(2 * ks + 1) * 32];
 #pragma unroll
-                    for (int mt = 0; mt < 2; ++mt) {
+                    for (int mt = 0; mt < MT; ++mt) {
                         uint32_t ah[4], al[4], adh[4], adl[4];
                         frag::a_from_c(h[mt][ks], ah, al);
                         frag::a_from_c(hd[mt][ks], adh, adl);
@@ -281,7 +305,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) field_backward_mma_kernel(
                     }
                 }
 #pragma unroll
-                for (int mt = 0; mt < 2; ++mt)
+                for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
                     for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
@@ -290,13 +314,13 @@ __global__ void __launch_bounds__(kThreadsB, 1) field_backward_mma_kernel(
             // ------------------------------------------------------------ 3. reverse sweep
             // layer 4 (16 -> 1), LayerNorm outputs stay in registers; hb / hdb: adjoints of the output of
             // linear layer 3 and of its tangent (C layout)
-            f2 hb[2][2][2], hdb[2][2][2];
+            f2 hb[MT][2][2], hdb[MT][2][2];
             {
                 const float4 last4 = accL[kAccLast * 32];
                 f2 last0 = make_float2(last4.x, last4.y), last1 = make_float2(last4.z, last4.w);
                 float obsum = 0.0f;
 #pragma unroll
-                for (int s = 0; s < 4; ++s) {
+                for (int s = 0; s < kSlots; ++s) {
                     f2 z[2] = {h[s >> 1][0][s & 1], h[s >> 1][1][s & 1]};
                     f2 zd[2] = {hd[s >> 1][0][s & 1], hd[s >> 1][1][s & 1]};
                     float rs, mz;
@@ -322,21 +346,25 @@ __global__ void __launch_bounds__(kThreadsB, 1) field_backward_mma_kernel(
                     hdb[s >> 1][0][s & 1] = hdbv[0]; hdb[s >> 1][1][s & 1] = hdbv[1];
                 }
                 accL[kAccLast * 32] = make_float4(last0.x, last0.y, last1.x, last1.y);
-                float4 p0 = accL[kAccPose * 32];
-                p0.x += obsum;
-                accL[kAccPose * 32] = p0;
+                if constexpr (Cfg::kPoseInRegs) {
+                    pose_reg[0] += obsum;
+                } else {
+                    float4 p0 = accL[kAccPose * 32];
+                    p0.x += obsum;
+                    accL[kAccPose * 32] = p0;
+                }
             }
 #pragma unroll 1
             for (int l = 3; l >= 1; --l) {
                 // adjoints of gelu(z_l) and its tangent: W_l^T hb, W_l^T hdb
-                f2 gb[2][2][2], gdb[2][2][2];
+                f2 gb[MT][2][2], gdb[MT][2][2];
                 {
                     const float4* fl = fragL + (frag::kR1 + 4 * (l - 1)) * 32;
 #pragma unroll
                     for (int ks = 0; ks < 2; ++ks) {
                         const float4 w0 = fl[(2 * ks) * 32], w1 = fl[(2 * ks + 1) * 32];
 #pragma unroll
-                        for (int mt = 0; mt < 2; ++mt) {
+                        for (int mt = 0; mt < MT; ++mt) {
                             uint32_t ah[4], al[4], adh[4], adl[4];
                             frag::a_from_c(hb[mt][ks], ah, al);
                             frag::a_from_c(hdb[mt][ks], adh, adl);
@@ -352,15 +380,15 @@ __global__ void __launch_bounds__(kThreadsB, 1) field_backward_mma_kernel(
                     const float4 a = accW[n * 32];
                     D[n][0] = make_float2(a.x, a.y); D[n][1] = make_float2(a.z, a.w);
                 }
-                const float2* st = stash + (l - 1) * 16 * 32;
+                const float2* st = stash + (l - 1) * kLayerStride;
 #pragma unroll
-                for (int mt = 0; mt < 2; ++mt) {
+                for (int mt = 0; mt < MT; ++mt) {
                     f2 z[2][2], zd[2][2], g[2][2], gd[2][2], g1[2][2], g2[2][2];      // [row half][channel pair]
 #pragma unroll
                     for (int hf = 0; hf < 2; ++hf) {
                         const int s = 2 * mt + hf;
                         z[hf][0] = st[(2 * s) * 32]; z[hf][1] = st[(2 * s + 1) * 32];
-                        zd[hf][0] = st[(8 + 2 * s) * 32]; zd[hf][1] = st[(8 + 2 * s + 1) * 32];
+                        zd[hf][0] = st[(kLayerPairs + 2 * s) * 32]; zd[hf][1] = st[(kLayerPairs + 2 * s + 1) * 32];
                         gelu_pair(z[hf][0], zd[hf][0], g[hf][0], gd[hf][0], g1[hf][0], g2[hf][0]);
                         gelu_pair(z[hf][1], zd[hf][1], g[hf][1], gd[hf][1], g1[hf][1], g2[hf][1]);
                     }
@@ -395,7 +423,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) field_backward_mma_kernel(
             // layer 0: weight gradient against the encoding and its tangent, then the encoding adjoint
             //   abar_c  = sum_k 2^k (ebar_sin cos - ebar_cos sin - da (edbar_cos cos + edbar_sin sin))
             //   adbar_c = sum_k 2^k (edbar_sin cos - edbar_cos sin)
-            float abar[4][3], adbar[4][3];
+            float abar[kSlots][3], adbar[kSlots][3];
             {
                 f2 D0[7][2];
 #pragma unroll
@@ -404,7 +432,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) field_backward_mma_kernel(
                     D0[n][0] = make_float2(a.x, a.y); D0[n][1] = make_float2(a.z, a.w);
                 }
 #pragma unroll
-                for (int mt = 0; mt < 2; ++mt) {
+                for (int mt = 0; mt < MT; ++mt) {
                     const int s0 = 2 * mt, s1 = 2 * mt + 1;
                     {
                         uint32_t ah[4], al[4], adh[4], adl[4];
@@ -462,10 +490,11 @@ __global__ void __launch_bounds__(kThreadsB, 1) field_backward_mma_kernel(
                 float ga[3], gad[3];
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    const float va[4] = {abar[0][c], abar[1][c], abar[2][c], abar[3][c]};
-                    const float vd[4] = {adbar[0][c], adbar[1][c], adbar[2][c], adbar[3][c]};
-                    ga[c] = frag::rows_to_lanes(va, lane);
-                    gad[c] = frag::rows_to_lanes(vd, lane);
+                    float va[kSlots], vd[kSlots];
+#pragma unroll
+                    for (int sl = 0; sl < kSlots; ++sl) { va[sl] = abar[sl][c]; vd[sl] = adbar[sl][c]; }
+                    ga[c] = frag::row_slots_to_lanes<MT>(va, lane);
+                    gad[c] = frag::row_slots_to_lanes<MT>(vd, lane);
                 }
                 float x[3];
                 sample_position(rays, r, j, x);
@@ -485,14 +514,21 @@ __global__ void __launch_bounds__(kThreadsB, 1) field_backward_mma_kernel(
 #pragma unroll
                     for (int k = 0; k < 3; ++k) pose[6 + 3 * m + k] = p.b.y[m] * p.pbar[k] + dG[m] * p.vbar[k];
                 }
-                float4 a0 = accL[kAccPose * 32], a1 = accL[(kAccPose + 1) * 32];
-                float4 a2 = accL[(kAccPose + 2) * 32], a3 = accL[(kAccPose + 3) * 32];
-                a0.y += pose[0]; a0.z += pose[1]; a0.w += pose[2];
-                a1.x += pose[3]; a1.y += pose[4]; a1.z += pose[5]; a1.w += pose[6];
-                a2.x += pose[7]; a2.y += pose[8]; a2.z += pose[9]; a2.w += pose[10];
-                a3.x += pose[11]; a3.y += pose[12]; a3.z += pose[13]; a3.w += pose[14];
-                accL[kAccPose * 32] = a0; accL[(kAccPose + 1) * 32] = a1;
-                accL[(kAccPose + 2) * 32] = a2; accL[(kAccPose + 3) * 32] = a3;
+                if constexpr (Cfg::kPoseInRegs) {
+                    if (lane < kRows) {                    // shadow lanes hold copies of rows 0..15: count each sample once
+#pragma unroll
+                        for (int m = 0; m < kNumPose; ++m) pose_reg[1 + m] += pose[m];
+                    }
+                } else {
+                    float4 a0 = accL[kAccPose * 32], a1 = accL[(kAccPose + 1) * 32];
+                    float4 a2 = accL[(kAccPose + 2) * 32], a3 = accL[(kAccPose + 3) * 32];
+                    a0.y += pose[0]; a0.z += pose[1]; a0.w += pose[2];
+                    a1.x += pose[3]; a1.y += pose[4]; a1.z += pose[5]; a1.w += pose[6];
+                    a2.x += pose[7]; a2.y += pose[8]; a2.z += pose[9]; a2.w += pose[10];
+                    a3.x += pose[11]; a3.y += pose[12]; a3.z += pose[13]; a3.w += pose[14];
+                    accL[kAccPose * 32] = a0; accL[(kAccPose + 1) * 32] = a1;
+                    accL[(kAccPose + 2) * 32] = a2; accL[(kAccPose + 3) * 32] = a3;
+                }
             }
             __syncwarp();
         }
@@ -501,7 +537,11 @@ __global__ void __launch_bounds__(kThreadsB, 1) field_backward_mma_kernel(
             // last layer: reduce over the 8 quads (lane bits 2..4); bias / pose: over all 32 lanes
             float4 last = accL[kAccLast * 32];
             float v[16];
-            {
+            if constexpr (Cfg::kPoseInRegs) {
+                v[0] = 0.25f * pose_reg[0];                // obar was accumulated by all 4 lanes of each quad
+#pragma unroll
+                for (int k = 1; k < 16; ++k) v[k] = pose_reg[k];
+            } else {
                 const float4 a0 = accL[kAccPose * 32], a1 = accL[(kAccPose + 1) * 32];
                 const float4 a2 = accL[(kAccPose + 2) * 32], a3 = accL[(kAccPose + 3) * 32];
                 v[0] = 0.25f * a0.x;                       // obar was accumulated by all 4 lanes of each quad
@@ -585,6 +625,8 @@ __global__ void reduce_segment_rows_kernel(const float* __restrict__ partials, i
 }
 
 static int g_sms = 0;
+static int g_bwd_mt = 1;       // m-tiles per warp tile: MT = 1 ships (12 warps x 168 registers: 0.782 ms vs 0.810 ms for
+                               // MT = 2, 8 warps x 255 registers, R=1000 S=100 N=8); VSRD_BWD_MT=2 selects the other variant
 
 static int setup() {
     if (g_sms) return 0;
@@ -592,10 +634,32 @@ static int setup() {
     if (cudaGetDevice(&dev) != cudaSuccess) return fail("vsrd_b200: no CUDA device%s");
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return fail("vsrd_b200: cudaGetDeviceProperties failed%s");
-    if (cudaFuncSetAttribute(field_backward_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)kSmemBytes) != cudaSuccess)
+    if (cudaFuncSetAttribute(field_backward_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)BwdCfg<2>::kSmemBytes) != cudaSuccess ||
+        cudaFuncSetAttribute(field_backward_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)BwdCfg<1>::kSmemBytes) != cudaSuccess)
         return fail("vsrd_b200: cannot reserve %s of shared memory for field_backward_mma_kernel (built for sm_100a)", "206 KB");
+    const char* mt = getenv("VSRD_BWD_MT");
+    if (mt && (mt[0] == '1' || mt[0] == '2')) g_bwd_mt = mt[0] - '0';
     g_sms = prop.multiProcessorCount;
+    return 0;
+}
+
+template <int MT>
+static int launch(const SceneDev& s, const RaysDev& r, const float* adjoint, float* partials,
+                  float* gloc, float* grot, float* gdim, float* gW, cudaStream_t st) {
+    using Cfg = BwdCfg<MT>;
+    const long long total = (long long)r.R * r.M;
+    const int tiles_per_inst = (int)((total + Cfg::kRows - 1) / Cfg::kRows);
+    const long long all_tiles = (long long)s.N * tiles_per_inst;
+    const long long want = (all_tiles + Cfg::kWarps - 1) / Cfg::kWarps;
+    const int grid = (int)(want < g_sms ? want : g_sms);
+    field_backward_mma_kernel<MT><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(
+        s, r, (const float4*)adjoint, partials, tiles_per_inst);
+    VSRD_CHECK_LAUNCH();
+    const dim3 rgrid((kGradStride + 127) / 128, (unsigned)s.N);
+    reduce_segment_rows_kernel<<<rgrid, 128, 0, st>>>(partials, grid, tiles_per_inst, all_tiles, gloc, grot, gdim, gW);
+    VSRD_CHECK_LAUNCH();
     return 0;
 }
 
@@ -609,18 +673,8 @@ int backward_mma_partial_rows(int num_instances) {
 int launch_field_backward_mma(const SceneDev& s, const RaysDev& r, const float* adjoint, float* partials,
                               float* gloc, float* grot, float* gdim, float* gW, cudaStream_t st) {
     if (bwd5::setup()) return 1;
-    const long long total = (long long)r.R * r.M;
-    const int tiles_per_inst = (int)((total + 31) / 32);
-    const long long all_tiles = (long long)s.N * tiles_per_inst;
-    const long long want = (all_tiles + bwd5::kWarpsB - 1) / bwd5::kWarpsB;
-    const int grid = (int)(want < bwd5::g_sms ? want : bwd5::g_sms);
-    bwd5::field_backward_mma_kernel<<<grid, bwd5::kThreadsB, bwd5::kSmemBytes, st>>>(
-        s, r, (const float4*)adjoint, partials, tiles_per_inst);
-    VSRD_CHECK_LAUNCH();
-    const dim3 rgrid((kGradStride + 127) / 128, (unsigned)s.N);
-    bwd5::reduce_segment_rows_kernel<<<rgrid, 128, 0, st>>>(partials, grid, tiles_per_inst, all_tiles, gloc, grot, gdim, gW);
-    VSRD_CHECK_LAUNCH();
-    return 0;
+    return bwd5::g_bwd_mt == 1 ? bwd5::launch<1>(s, r, adjoint, partials, gloc, grot, gdim, gW, st)
+                               : bwd5::launch<2>(s, r, adjoint, partials, gloc, grot, gdim, gW, st);
 }
 
 }  // namespace vsrd
