@@ -1,0 +1,208 @@
+"""Size-independent properties at BASELINE.json's full sizes (cfg2: R=1000, S=100, N=8; cfg3: N=24 dense) and the
+edge cases of the renderer path: single / maximum instance counts, ragged and empty ray batches, the maximum
+interval count, rays that miss everything (importance placement extrapolates), and the two
+m-tile variants of the backward field kernel.  Small cases are checked against the CPU oracle; full-size ones
+through properties the algorithm guarantees (partition of unity of the soft labels, per-ray independence,
+linearity of the adjoint, instance-permutation equivariance, bit-reproducibility)."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from oracle import vsrd_oracle as oracle
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _scene(n, layout, seed=0):
+    """Ground-truth-posed boxes + a random-init residual field (default nn.Linear init under weight_norm)."""
+    import vsrd
+    from vsrd_b200 import synthetic
+    frame = synthetic.make_frame(n, 17, seed=seed, layout=layout)
+    torch.manual_seed(seed)
+    hyper = vsrd.models.HyperDistanceField(in_channels=48, out_channels_list=[16] * 4, hyper_in_channels=256,
+                                           hyper_out_channels_list=[256] * 4)
+    with torch.no_grad():
+        weights = hyper(torch.rand(n, 256))
+    return frame, [frame.gt_locations.clone(), frame.gt_rotations.clone(), frame.gt_half_extents.clone(), weights]
+
+
+def _rays(frame, r, seed=1):
+    gen = torch.Generator().manual_seed(seed)
+    pix = frame.draw_pixel_indices(r, gen)
+    h, w = frame.image_size
+    inv_proj, cam = frame.inverse_projections()
+    view, v, u = pix // (h * w), (pix // w) % h, pix % w
+    d = torch.einsum("rmn,rn->rm", inv_proj[view], torch.stack([u, v, torch.ones_like(u)], -1).float())
+    return cam[view].contiguous(), torch.nn.functional.normalize(d, dim=-1).contiguous()
+
+
+def _render(F, leaves, o, d, s, seed=3, requires_grad=False, **sched):
+    gen = torch.Generator().manual_seed(seed)
+    r = d.shape[0]
+    jitter = torch.rand(r, s, generator=gen).to(DEV)
+    uniforms = torch.sort(torch.rand(r, s, generator=gen), dim=-1).values.to(DEV)
+    dev_leaves = [t.to(DEV).requires_grad_(requires_grad) if t is not None else None for t in leaves]
+    sched = dict(dict(temperature=0.55, std_deviation=0.55, cosine_ratio=0.5), **sched)
+    out = F.two_pass_render(*dev_leaves, o.to(DEV), d.to(DEV), num_samples=s, jitter=jitter, sorted_uniforms=uniforms, **sched)
+    return dev_leaves, out
+
+
+@pytest.fixture(scope="module")
+def F():
+    from vsrd_b200 import functional
+    return functional
+
+
+@pytest.mark.parametrize("n,layout", [(8, "street"), (24, "parking")])
+def test_full_size_properties(F, n, layout):
+    frame, leaves = _scene(n, layout)
+    o, d = _rays(frame, 1000)
+    dev_leaves, (labels, grads, cd, cw, fd, fw) = _render(F, leaves, o, d, 100, requires_grad=True)
+    assert labels.shape == (1000, n) and grads.shape == (1000, 199, 3) and fd.shape == (1000, 200) and fw.shape == (1000, 199)
+    for t in (labels, grads, cw, fw):
+        assert torch.isfinite(t).all()
+    # placement: ascending, inside the range unless the coarse pass saw nothing on that ray
+    assert bool((fd[:, 1:] >= fd[:, :-1]).all()) and bool((cd[:, 1:] > cd[:, :-1]).all())
+    # soft labels are a partition of unity per sample, so the per-ray label mass equals the accumulated opacity
+    assert bool((labels >= 0).all()) and bool((fw >= 0).all())
+    assert torch.allclose(labels.sum(1), fw.sum(1), atol=2e-5)
+    assert float(fw.sum(1).max()) <= 1.0 + 1e-5
+    assert float(labels.sum(1).max()) > 0.5, "the synthetic rays must hit the boxes for this test to mean anything"
+
+    # per-ray independence: any sub-batch renders bit-identically
+    sel = torch.arange(137, 611)
+    _, (l2, g2, _, _, fd2, fw2) = _render(F, leaves, o, d, 100)
+    assert torch.equal(l2, labels.detach()) and torch.equal(fw2, fw.detach())            # bit-reproducible
+    gen = torch.Generator().manual_seed(3)
+    jitter = torch.rand(1000, 100, generator=gen).to(DEV)
+    uniforms = torch.sort(torch.rand(1000, 100, generator=gen), dim=-1).values.to(DEV)
+    sub = F.two_pass_render(*[t.detach() for t in dev_leaves], o[sel].to(DEV), d[sel].to(DEV), num_samples=100,
+                            jitter=jitter[sel], sorted_uniforms=uniforms[sel], temperature=0.55, std_deviation=0.55, cosine_ratio=0.5)
+    assert torch.equal(sub[0], labels.detach()[sel]) and torch.equal(sub[4], fd[sel]) and torch.equal(sub[1], grads.detach()[sel])
+
+    # the adjoint is linear in the upstream gradient, and bit-reproducible
+    gen = torch.Generator(device=DEV).manual_seed(5)
+    u1, u2 = torch.randn(labels.shape, device=DEV, generator=gen), torch.randn(labels.shape, device=DEV, generator=gen)
+    v1 = torch.randn(grads.shape, device=DEV, generator=gen) * 0.1
+    ga = torch.autograd.grad([labels, grads], dev_leaves, [u1, v1], retain_graph=True)
+    gb = torch.autograd.grad([labels, grads], dev_leaves, [u2, torch.zeros_like(v1)], retain_graph=True)
+    gs = torch.autograd.grad([labels, grads], dev_leaves, [u1 + u2, v1], retain_graph=True)
+    ga2 = torch.autograd.grad([labels, grads], dev_leaves, [u1, v1], retain_graph=True)
+    for a, b, s_, a2 in zip(ga, gb, gs, ga2):
+        assert torch.isfinite(s_).all()
+        assert torch.equal(a, a2)
+        assert float((a + b - s_).norm()) <= 2e-4 * float(s_.norm()) + 1e-7, float((a + b - s_).norm() / s_.norm())
+
+    # instance-permutation equivariance (the union sums the instances in a different order: rounding only)
+    perm = torch.randperm(n, generator=torch.Generator().manual_seed(9))
+    _, (lp, gp, *_rest) = _render(F, [t[perm] for t in leaves], o, d, 100)
+    # a few importance samples may land in the neighbouring bin when a coarse weight changes in the last bit
+    diff = (lp - labels.detach()[:, perm]).abs()
+    assert float(diff.max()) < 2e-3 and float((diff < 2e-5).float().mean()) > 0.99, (float(diff.max()), float((diff < 2e-5).float().mean()))
+
+
+@pytest.mark.parametrize("n", [1, 32])
+@pytest.mark.parametrize("r", [1, 33])
+def test_instance_count_and_ragged_batch_edges_match_oracle(F, n, r):
+    """N = 1 and N = VSRD_MAX_INSTANCES, ray counts that fill neither a warp tile nor a CTA."""
+    frame, leaves = _scene(n, "parking" if n > 8 else "street", seed=2)
+    o, d = _rays(frame, r, seed=4)
+    s = 12
+    dev_leaves, (labels, grads, cd, cw, fd, fw) = _render(F, leaves, o, d, s, requires_grad=True, temperature=0.7, std_deviation=0.4)
+    scene = oracle.Scene(*[t.double().requires_grad_(True) for t in leaves], 0.7)            # fp64 oracle
+    out = oracle.render_pass(scene.field(), o.double(), d.double(), fd.detach().cpu().double().t()[..., None].contiguous(), 0.4, 0.5)
+    assert float((labels.detach().cpu() - out[0].detach()).abs().max()) < 1e-4
+    assert float((fw.detach().cpu() - out[3].detach().squeeze(-1).t()).abs().max()) < 1e-4
+    gen = torch.Generator().manual_seed(6)
+    c = torch.randn(r, n, generator=gen)
+    got = torch.autograd.grad((labels * c.to(DEV)).sum(), dev_leaves)
+    want = torch.autograd.grad((out[0] * c.double()).sum(), [scene.locations, scene.rotations, scene.half_extents, scene.mlp_weights])
+    for a, b in zip(got, want):
+        denom = float(b.norm())
+        if denom > 1e-6:
+            assert float((a.cpu().double() - b).norm()) / denom < 2e-3, float((a.cpu().double() - b).norm()) / denom
+
+
+def test_empty_ray_batch(F):
+    frame, leaves = _scene(3, "street", seed=7)
+    o, d = torch.zeros(0, 3), torch.zeros(0, 3)
+    dev_leaves, (labels, grads, cd, cw, fd, fw) = _render(F, leaves, o, d, 10, requires_grad=True)
+    assert labels.shape == (0, 3) and grads.shape == (0, 19, 3) and fd.shape == (0, 20) and fw.shape == (0, 19)
+    g = torch.autograd.grad(labels.sum() + grads.sum(), dev_leaves)
+    torch.cuda.synchronize()
+    assert all(float(t.abs().max()) == 0.0 for t in g)       # no rays: zero gradients, no launch error
+
+
+def test_maximum_interval_count(F):
+    """2 S - 1 = 511 intervals per ray: the largest fine pass the kernels take (VSRD_MAX_INTERVALS = 512)."""
+    frame, leaves = _scene(4, "street", seed=8)
+    o, d = _rays(frame, 5, seed=2)
+    _, (labels, grads, cd, cw, fd, fw) = _render(F, leaves, o, d, 256)
+    assert fd.shape == (5, 512) and torch.isfinite(labels).all() and torch.isfinite(grads).all()
+    scene = oracle.Scene(*leaves, 0.55)
+    with torch.no_grad():
+        out = oracle.render_pass(scene.field(), o, d, fd.cpu().t()[..., None].contiguous(), 0.55, 0.5)
+    assert float((labels.cpu() - out[0]).abs().max()) < 1e-4
+    from vsrd_b200 import ops
+    with pytest.raises(RuntimeError, match="intervals"):
+        ops.RayArgs(o.to(DEV), d.to(DEV), torch.zeros(5, 514, device=DEV))
+
+
+def test_rays_that_miss_everything_follow_the_reference(F):
+    """A ray whose coarse weights are all exactly zero has cdf == 0, so inverse-transform sampling extrapolates far
+    beyond the range (samplers.py:23-36).  The kernels must reproduce that placement and stay finite."""
+    frame, leaves = _scene(4, "street", seed=9)
+    r, s = 16, 20
+    o = torch.zeros(r, 3)
+    d = torch.nn.functional.normalize(torch.tensor([[0.0, -1.0, -0.2]]).repeat(r, 1) + 0.01 * torch.arange(r)[:, None], dim=-1)
+    gen = torch.Generator().manual_seed(3)
+    jitter, uniforms = torch.rand(r, s, generator=gen), torch.sort(torch.rand(r, s, generator=gen), dim=-1).values
+    sched = dict(temperature=0.1, std_deviation=0.1, cosine_ratio=1.0)
+    out = F.two_pass_render(*[t.to(DEV) for t in leaves], o.to(DEV), d.to(DEV), num_samples=s, jitter=jitter.to(DEV),
+                            sorted_uniforms=uniforms.to(DEV), **sched)
+    labels, grads, cd, cw, fd, fw = [t.cpu() for t in out]
+    scene = oracle.Scene(*leaves, 0.1)
+    with torch.no_grad():
+        ref = oracle.two_pass_render(scene.field(), o, d, [0.0, 100.0], s, 0.1, 1.0,
+                                     jitter=jitter[:, None, :], sorted_uniforms=uniforms[:, None, :])
+    assert float(cw.abs().max()) == 0.0 and float(ref[3].abs().max()) == 0.0, "these rays must see nothing in the coarse pass"
+    ref_fd = ref[4].squeeze(-1).t()
+    assert float(fd.max()) > 1e3                                   # the extrapolation happened
+    assert torch.allclose(fd, ref_fd, rtol=1e-6, atol=1e-4)
+    assert torch.isfinite(labels).all() and torch.isfinite(grads).all()
+    assert float((labels - ref[0]).abs().max()) < 1e-4
+
+
+_BWD_SCRIPT = r"""
+import sys, torch
+sys.path.insert(0, {root!r})
+from tests.test_gpu_properties import _scene, _rays, _render
+from vsrd_b200 import functional as F
+frame, leaves = _scene(5, "street", seed=11)
+o, d = _rays(frame, 77, seed=5)
+dev_leaves, (labels, grads, *_r) = _render(F, leaves, o, d, 24, requires_grad=True)
+gen = torch.Generator(device="cuda").manual_seed(1)
+u = torch.randn(labels.shape, device="cuda", generator=gen)
+v = torch.randn(grads.shape, device="cuda", generator=gen) * 0.1
+g = torch.autograd.grad([labels, grads], dev_leaves, [u, v])
+torch.save([t.cpu() for t in g], sys.argv[1])
+"""
+
+
+def test_backward_m_tile_variants_agree(tmp_path):
+    """VSRD_BWD_MT selects 16- or 32-sample warp tiles in the backward field kernel (read once per process)."""
+    outs = []
+    for mt in ("1", "2"):
+        path = str(tmp_path / f"g{mt}.pt")
+        env = dict(os.environ, VSRD_BWD_MT=mt)
+        proc = subprocess.run([sys.executable, "-c", _BWD_SCRIPT.format(root=ROOT), path], env=env, capture_output=True, text=True, timeout=600)
+        assert proc.returncode == 0, proc.stderr[-2000:]
+        outs.append(torch.load(path))
+    for a, b in zip(*outs):
+        assert float((a - b).norm()) <= 1e-5 * float(b.norm()) + 1e-9, float((a - b).norm() / b.norm())

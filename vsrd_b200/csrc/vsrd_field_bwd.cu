@@ -603,7 +603,7 @@ int vsrd_field_backward(const VsrdScene* scene, const VsrdRays* rays, const floa
                         float* grad_mlp_weights, void* stream) {
     SceneDev s; RaysDev r;
     if (check_scene(scene, s) || check_rays(rays, r)) return 1;
-    VSRD_CHECK_ARG(adjoint && partials && grad_locations && grad_rotations && grad_half_extents, "NULL pointer");
+    VSRD_CHECK_ARG((adjoint || r.R == 0) && partials && grad_locations && grad_rotations && grad_half_extents, "NULL pointer");
     VSRD_CHECK_ARG(!s.W || grad_mlp_weights, "grad_mlp_weights is NULL while mlp_weights are given");
     if (device_setup()) return 1;
     cudaStream_t st = (cudaStream_t)stream;

@@ -332,9 +332,9 @@ using namespace vsrd;
 extern "C" {
 
 static int launch_field(const SceneDev& s, const RaysDev& r, float* field, void* stream) {
-    VSRD_CHECK_ARG(field != nullptr, "field is NULL");
     const size_t total = (size_t)r.R * r.M;
     if (total == 0) return 0;
+    VSRD_CHECK_ARG(field != nullptr, "field is NULL");
     VSRD_CHECK_ARG(total < (size_t)1 << 31, "R*M must be < 2^31");
     if (forward_setup()) return 1;
     cudaStream_t st = (cudaStream_t)stream;

@@ -411,9 +411,9 @@ int vsrd_ray_directions(const float* inv_projection, int num_views, int height, 
 
 int vsrd_gather_rays(const float* inv_projection, const float* camera_positions, const int64_t* pixel_indices,
                      int num_rays, int num_views, int height, int width, float* origins, float* directions, void* stream) {
-    VSRD_CHECK_ARG(inv_projection && camera_positions && pixel_indices && origins && directions, "NULL pointer");
     VSRD_CHECK_ARG(num_rays >= 0 && num_views >= 1 && height >= 1 && width >= 1, "bad size");
     if (num_rays == 0) return 0;
+    VSRD_CHECK_ARG(inv_projection && camera_positions && pixel_indices && origins && directions, "NULL pointer");
     gather_rays_kernel<<<(num_rays + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
         inv_projection, camera_positions, pixel_indices, num_rays, height, width, origins, directions);
     VSRD_CHECK_LAUNCH();
@@ -422,10 +422,10 @@ int vsrd_gather_rays(const float* inv_projection, const float* camera_positions,
 
 int vsrd_place_coarse(const float* bins, const float* jitter, uint64_t seed, const VsrdStepState* step_state,
                       int num_rays, int num_samples, float* distances, void* stream) {
-    VSRD_CHECK_ARG(bins && distances, "NULL pointer");
     VSRD_CHECK_ARG(num_rays >= 0 && num_samples >= 1, "bad size");
     const size_t total = (size_t)num_rays * num_samples;
-    if (total == 0) return 0;
+    if (total == 0) return 0;                              // an empty ray batch is a no-op (buffers may be NULL)
+    VSRD_CHECK_ARG(bins && distances, "NULL pointer");
     if (render_setup()) return 1;
     const size_t want = (total + 255) / 256, cap = (size_t)g_num_sms_render * 16;
     place_coarse_kernel<<<(int)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(bins, jitter, seed, step_state, num_rays, num_samples, distances);
@@ -436,10 +436,10 @@ int vsrd_place_coarse(const float* bins, const float* jitter, uint64_t seed, con
 int vsrd_place_fine(const float* coarse_distances, const float* coarse_weights, const float* sorted_uniforms,
                     uint64_t seed, const VsrdStepState* step_state, int num_rays, int num_samples,
                     float* distances, void* stream) {
-    VSRD_CHECK_ARG(coarse_distances && coarse_weights && distances, "NULL pointer");
     VSRD_CHECK_ARG(num_rays >= 0, "bad size");
     VSRD_CHECK_ARG(num_samples >= 2 && 2 * num_samples - 1 <= VSRD_MAX_INTERVALS, "num_samples must be in [2, 256]");
     if (num_rays == 0) return 0;
+    VSRD_CHECK_ARG(coarse_distances && coarse_weights && distances, "NULL pointer");
     const size_t smem = (size_t)kWarps * 4 * num_samples * sizeof(float);
     place_fine_kernel<<<(num_rays + kWarps - 1) / kWarps, kThreads, smem, (cudaStream_t)stream>>>(
         coarse_distances, coarse_weights, sorted_uniforms, seed, step_state, num_rays, num_samples, distances);
@@ -454,8 +454,8 @@ int vsrd_composite_forward(const VsrdScene* scene, const VsrdRays* rays, const V
     if (check_scene(scene, s) || check_rays(rays, r)) return 1;
     VSRD_CHECK_ARG(params != nullptr, "params is NULL");
     VSRD_CHECK_ARG(s.state != nullptr || params->std_deviation > 0.0f, "std_deviation must be positive");
-    VSRD_CHECK_ARG(field && labels && gradients && weights, "NULL pointer");
     if (r.R == 0) return 0;
+    VSRD_CHECK_ARG(field && labels && gradients && weights, "NULL pointer");
     LossDev l{nullptr, 0.0f, 0.0f};
     if (loss && loss->targets) {
         VSRD_CHECK_ARG(loss_out != nullptr, "loss_out is NULL while loss targets are given");
@@ -481,8 +481,8 @@ int vsrd_composite_backward(const VsrdScene* scene, const VsrdRays* rays, const 
     if (check_scene(scene, s) || check_rays(rays, r)) return 1;
     VSRD_CHECK_ARG(params != nullptr, "params is NULL");
     VSRD_CHECK_ARG(s.state != nullptr || params->std_deviation > 0.0f, "std_deviation must be positive");
-    VSRD_CHECK_ARG(field && adjoint, "NULL pointer");
     if (r.R == 0) return 0;
+    VSRD_CHECK_ARG(field && adjoint, "NULL pointer");
     LossDev l{nullptr, 0.0f, 0.0f};
     if (loss && loss->targets) {
         VSRD_CHECK_ARG(labels != nullptr, "labels (forward output) required for the in-kernel loss gradient");
