@@ -52,6 +52,7 @@ def main():
     ap.add_argument("kernel")
     ap.add_argument("file")
     ap.add_argument("--top", type=int, default=40)
+    ap.add_argument("--section", default=None, help="regex on the MANGLED name for the disassembly (default: the kernel regex)")
     args = ap.parse_args()
     raw = subprocess.run(["ncu", "-i", args.report, "--page", "source", "--csv", "--kernel-name", f"regex:{args.kernel}"],
                          check=True, capture_output=True, text=True).stdout
@@ -59,7 +60,7 @@ def main():
     blocks = raw.split('"Kernel Name"')
     body = blocks[1].split("\n", 1)[1]
     rows = list(csv.DictReader(io.StringIO(body)))
-    dis = disasm_lines(args.obj, args.kernel, args.file)
+    dis = disasm_lines(args.obj, args.section or args.kernel, args.file)
     if len(dis) != len(rows):
         print(f"warning: {len(rows)} profiled instructions vs {len(dis)} disassembled", file=sys.stderr)
     src = open(args.file).read().splitlines()

@@ -603,6 +603,49 @@ VSRD_HD void union_forward(Load load, int N, float T, UnionEval& u) {
     u.g[0] = g0; u.g[1] = g1; u.g[2] = g2;
 }
 
+// Register-resident variant for the compositing kernels (N <= 16): every instance's field value is loaded once
+// (all loads in flight together), the IEEE division d_i / T — the one rounding that is amplified by exp — and
+// exp(-d_i/T - mneg) are evaluated ONCE per instance and kept (q[], e[]); the remaining scalar divisions
+// (1/Z, 1/T applied to the cancellation-free (d_i - dbar)) become reciprocal multiplications, 1 ulp apart from
+// union_forward.  The 4-pass form above costs ~6 divisions + 4 exp per (sample, instance): 80 % of the
+// compositing kernels' instructions (profiles/r01_v10_hotspots.txt).
+template <int NMAX>
+struct UnionRegs {
+    Vec4 f[NMAX];     // (d_i, grad d_i)
+    float e[NMAX];    // exp(-d_i/T - mneg), 0 for i >= N
+    float invZ, invT;
+};
+
+template <int NMAX>
+VSRD_HD void union_forward_regs(UnionRegs<NMAX>& R, int N, float T, UnionEval& u) {
+    float q[NMAX];
+    float mneg = -INFINITY;
+    VSRD_UNROLL for (int i = 0; i < NMAX; ++i) {
+        q[i] = -INFINITY;
+        if (i < N) { q[i] = -(R.f[i].x / T); mneg = fmaxf(mneg, q[i]); }
+    }
+    float Z = 0.0f, ds = 0.0f;
+    VSRD_UNROLL for (int i = 0; i < NMAX; ++i) {
+        R.e[i] = 0.0f;
+        if (i < N) {
+            R.e[i] = expf(q[i] - mneg);
+            Z += R.e[i];
+            ds += R.e[i] * R.f[i].x;
+        }
+    }
+    const float dbar = ds / Z;
+    R.invZ = 1.0f / Z;
+    R.invT = 1.0f / T;
+    float g0 = 0.0f, g1 = 0.0f, g2 = 0.0f;
+    VSRD_UNROLL for (int i = 0; i < NMAX; ++i) if (i < N) {
+        const float w = R.e[i] * R.invZ;
+        const float c = w * (1.0f - (R.f[i].x - dbar) * R.invT);
+        g0 += c * R.f[i].y; g1 += c * R.f[i].z; g2 += c * R.f[i].w;
+    }
+    u.mneg = mneg; u.Z = Z; u.dbar = dbar;
+    u.g[0] = g0; u.g[1] = g1; u.g[2] = g2;
+}
+
 struct OpacityEval {
     float gn, inv, cs;      // |g|, 1/max(|g|,1e-12), dir . n
     float n[3];
@@ -669,6 +712,31 @@ VSRD_HD void union_backward(Load load, WBar wbar, Store store, int N, float T, c
         const float lam = gam * ui;
         Vec4 a;
         a.x = dbar_adj * c - w * invT * (wbar(i) - S1) - w * invT * (lam - S2) - w * gam * invT + c * S3 * invT;
+        a.y = c * gbar[0]; a.z = c * gbar[1]; a.w = c * gbar[2];
+        store(i, a);
+    }
+}
+
+// union_backward on the register-resident values of union_forward_regs.
+template <int NMAX, class WBar, class Store>
+VSRD_HD void union_backward_regs(const UnionRegs<NMAX>& R, WBar wbar, Store store, int N, const UnionEval& u,
+                                 float dbar_adj, const float gbar[3]) {
+    float S1 = 0.0f, S2 = 0.0f, S3 = 0.0f;
+    float w[NMAX], ui[NMAX], gam[NMAX];
+    VSRD_UNROLL for (int i = 0; i < NMAX; ++i) if (i < N) {
+        w[i] = R.e[i] * R.invZ;
+        ui[i] = 1.0f - (R.f[i].x - u.dbar) * R.invT;
+        gam[i] = gbar[0] * R.f[i].y + gbar[1] * R.f[i].z + gbar[2] * R.f[i].w;
+        S1 += wbar(i) * w[i];
+        S2 += gam[i] * ui[i] * w[i];
+        S3 += gam[i] * w[i];
+    }
+    const float invT = R.invT;
+    VSRD_UNROLL for (int i = 0; i < NMAX; ++i) if (i < N) {
+        const float c = w[i] * ui[i];
+        const float lam = gam[i] * ui[i];
+        Vec4 a;
+        a.x = dbar_adj * c - w[i] * invT * (wbar(i) - S1) - w[i] * invT * (lam - S2) - w[i] * gam[i] * invT + c * S3 * invT;
         a.y = c * gbar[0]; a.z = c * gbar[1]; a.w = c * gbar[2];
         store(i, a);
     }

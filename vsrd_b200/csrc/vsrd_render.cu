@@ -207,6 +207,8 @@ struct LossDev {
     float eik_w;
 };
 
+constexpr int kRegsMaxInstances = 16;
+
 template <int NMAX>
 __global__ void __launch_bounds__(VSRD_MAX_INTERVALS) composite_forward_kernel(
         SceneDev scene, RaysDev rays, float sigma, float rho, float eps, const float4* __restrict__ field,
@@ -232,10 +234,18 @@ __global__ void __launch_bounds__(VSRD_MAX_INTERVALS) composite_forward_kernel(
     UnionEval u;
     OpacityEval o;
     float alpha = 0.0f;
+    constexpr bool kRegs = NMAX <= kRegsMaxInstances;   // all instances' field values live in registers
+    UnionRegs<kRegs ? NMAX : 1> ur;
     if (valid) {
         const float dir[3] = {__ldg(rays.dirs + 3 * r), __ldg(rays.dirs + 3 * r + 1), __ldg(rays.dirs + 3 * r + 2)};
         const float* trow = rays.dist + (size_t)r * (M + 1);
-        union_forward(load, N, T, u);
+        if constexpr (kRegs) {
+#pragma unroll
+            for (int i = 0; i < NMAX; ++i) ur.f[i] = i < N ? load(i) : Vec4{0.0f, 0.0f, 0.0f, 0.0f};
+            union_forward_regs<NMAX>(ur, N, T, u);
+        } else {
+            union_forward(load, N, T, u);
+        }
         const float delta = __ldg(trow + j + 1) - __ldg(trow + j);
         opacity_forward(u, dir, delta, sigma, rho, eps, o);
         alpha = o.alpha;
@@ -252,7 +262,10 @@ __global__ void __launch_bounds__(VSRD_MAX_INTERVALS) composite_forward_kernel(
 #pragma unroll
     for (int n = 0; n < NMAX; ++n) {
         if (n < N) {
-            const float part = warp_sum(valid ? k * expf(-(load(n).x / T) - u.mneg) : 0.0f);
+            float num = 0.0f;                                  // softmin numerator exp(-d_n/T - mneg)
+            if constexpr (kRegs) { if (valid) num = ur.e[n]; }
+            else if (valid) num = expf(-(load(n).x / T) - u.mneg);
+            const float part = warp_sum(k * num);
             if (lane == 0) s_lab[warp][n] = part;
         }
     }
@@ -335,14 +348,27 @@ __global__ void __launch_bounds__(VSRD_MAX_INTERVALS) composite_backward_kernel(
     UnionEval u;
     OpacityEval o;
     float alpha = 0.0f, a = 0.0f, delta = 0.0f;
+    constexpr bool kRegs = NMAX <= kRegsMaxInstances;   // all instances' field values live in registers
+    UnionRegs<kRegs ? NMAX : 1> ur;
     if (valid) {
         const float* trow = rays.dist + (size_t)r * (M + 1);
-        union_forward(load, N, T, u);
+        if constexpr (kRegs) {
+#pragma unroll
+            for (int i = 0; i < NMAX; ++i) ur.f[i] = i < N ? load(i) : Vec4{0.0f, 0.0f, 0.0f, 0.0f};
+            union_forward_regs<NMAX>(ur, N, T, u);
+        } else {
+            union_forward(load, N, T, u);
+        }
         delta = __ldg(trow + j + 1) - __ldg(trow + j);
         opacity_forward(u, dir, delta, sigma, rho, eps, o);
         alpha = o.alpha;
         if (grad_weights) a = __ldg(grad_weights + idx);
-        for (int n = 0; n < N; ++n) a += s_gl[n] * (expf(-(load(n).x / T) - u.mneg) / u.Z);
+        if constexpr (kRegs) {
+#pragma unroll
+            for (int n = 0; n < NMAX; ++n) if (n < N) a += s_gl[n] * (ur.e[n] * ur.invZ);
+        } else {
+            for (int n = 0; n < N; ++n) a += s_gl[n] * (expf(-(load(n).x / T) - u.mneg) / u.Z);
+        }
     }
     const float trans = block_transmittance(alpha, warp, lane, num_warps, s_tot);
     const float omega = trans * alpha;
@@ -372,7 +398,8 @@ __global__ void __launch_bounds__(VSRD_MAX_INTERVALS) composite_backward_kernel(
         auto store = [&](int i, const Vec4& q) {
             adjoint[(size_t)i * stride + idx] = make_float4(q.x, q.y, q.z, q.w);
         };
-        union_backward(load, wbar, store, N, T, u, dbar_adj, gbar);
+        if constexpr (kRegs) union_backward_regs<NMAX>(ur, wbar, store, N, u, dbar_adj, gbar);
+        else union_backward(load, wbar, store, N, T, u, dbar_adj, gbar);
     }
 }
 
