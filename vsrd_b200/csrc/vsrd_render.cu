@@ -142,11 +142,20 @@ __global__ void __launch_bounds__(kThreads) place_fine_kernel(
     __syncwarp();
     // torch.cumsum on CPU accumulates float32 inputs in double and rounds each prefix (verified);
     // follow it so bin boundaries agree with the oracle.
-    if (lane == 0) {
-        double acc = 0.0;
-        cdf[0] = 0.0f;
-        for (int k = 0; k < S - 1; ++k) {
-            acc += (double)(__ldg(coarse_w + (size_t)r * (S - 1) + k) / denom);
+    // Here: each lane sums a contiguous chunk in double, the chunk totals are scanned across the warp in double,
+    // every prefix is rounded to float once.  (Double re-association moves a prefix by <= 1e-16 relative, far
+    // below the float rounding of the result.)
+    {
+        const int n = S - 1, chunk = (n + 31) / 32, k0 = lane * chunk;
+        double local = 0.0;
+        for (int k = k0; k < min(k0 + chunk, n); ++k) local += (double)(__ldg(coarse_w + (size_t)r * n + k) / denom);
+        double incl = local;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const double up = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += up; }
+        double acc = incl - local;                  // sum of all earlier chunks
+        if (lane == 0) cdf[0] = 0.0f;
+        for (int k = k0; k < min(k0 + chunk, n); ++k) {
+            acc += (double)(__ldg(coarse_w + (size_t)r * n + k) / denom);
             cdf[k + 1] = (float)acc;
         }
     }
