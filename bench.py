@@ -416,8 +416,7 @@ def run_native(args):
                            initial_parameters=dict(locations=raw_loc.to(device), dimensions=raw_dim.to(device),
                                                    orientations=raw_ori.to(device)))
     start_step = 1500 - (K + W) // 2                      # mid-schedule, residual field on (as the device leg)
-    labeler.state.set_step(start_step)
-    labeler.step_index = start_step
+    labeler.seek(start_step)
     pool_pin, targets_pin = pool.pin_memory(), targets.pin_memory()
     loss_pin = [torch.zeros(5, dtype=torch.float32).pin_memory() for _ in range(2)]
     loss_ready = [torch.cuda.Event() for _ in range(2)]
@@ -465,8 +464,7 @@ def run_native(args):
                             rays="batches", use_graph=use_graph, seed=rank, model_seed=rank, models="torch",
                             initial_parameters=dict(locations=raw_loc.to(device), dimensions=raw_dim.to(device),
                                                     orientations=raw_ori.to(device)))
-        lab2.state.set_step(start_step)
-        lab2.step_index = start_step
+        lab2.seek(start_step)
 
         def torch_step(k):
             lab2.step(pool_pin[k], targets_pin[k])

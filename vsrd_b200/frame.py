@@ -173,6 +173,18 @@ class FrameLabeler:
         # all of the frame's work is enqueued on its own stream, after the set-up above
         self.stream = torch.cuda.Stream(device=dev)
         self.stream.wait_stream(torch.cuda.current_stream())
+        # Fused path, on-device draws: the ray batch of step k+1 is drawn DURING step k (it only depends on the CDF
+        # and on the seed of step k+1), so the ~50 us single-CTA draw never sits on the critical path.  A second
+        # device-resident schedule runs one step ahead to supply that seed.
+        self.state_ahead = None
+        if self.arena is not None and rays == "draw":
+            self.state_ahead = ops.StepState(num_steps=num_steps, warmup_steps=warmup_steps, temperature=temperature,
+                                             std_deviation=std_deviation, eikonal_weight=self.weights["eikonal_loss"],
+                                             seed=seed, device=dev)
+            self.next_pixel_indices = torch.zeros(self.num_rays, dtype=torch.int64, device=dev)
+            with torch.cuda.stream(self.stream):
+                self._draw_ahead(self.state)          # batch of step 0
+                self.state_ahead.set_step(1)
         self._graphs: Dict[bool, torch.cuda.CUDAGraph] = {}
         self._eager_done: Dict[bool, int] = {False: 0, True: 0}
 
@@ -223,29 +235,18 @@ class FrameLabeler:
         side, side2 = self.side_stream, self.side_stream2
         w = self.weights
         loc, dim, rot, boxes_3d = arena.decode()
-        # branch 1: projection + matching (+ target gather, which needs the matched ground-truth order)
+        # branch 1 (side): projection + matching, then the target gather (needs the matched ground-truth order);
+        # its results are first needed by the fine compositing pass (targets) and the decode backward (gradients)
+        if self.rays == "draw":
+            self.pixel_indices.copy_(self.next_pixel_indices)         # drawn during the previous step
         side.wait_stream(main)
         with torch.cuda.stream(side):
             _, gt_indices, proj_losses, proj_grad = ops.projection_step(self.views, boxes_3d, self.gt_boxes, self.visible)
-        # branch 2: the ray batch of this step
-        if self.rays == "draw":
-            side2.wait_stream(main)
-            with torch.cuda.stream(side2):
-                pix, status = ops.select_rays(self.cdf, self.num_rays, step_state=st)
-                self.draw_failures.add_(status)
-                self.pixel_indices.copy_(pix)
-                origins, directions = ops.gather_rays(self.inv_projection, self.camera_positions, self.pixel_indices,
-                                                      self.height, self.width)
-            side.wait_stream(side2)
-        else:
-            origins, directions = ops.gather_rays(self.inv_projection, self.camera_positions, self.pixel_indices,
-                                                  self.height, self.width)
-        if self.rays != "batches":
-            with torch.cuda.stream(side):
+            if self.rays != "batches":
                 self.targets.copy_(ops.gather_targets(self.inputs.soft_masks, self.pixel_indices, gt_indices))
+        origins, directions = ops.gather_rays(self.inv_projection, self.camera_positions, self.pixel_indices,
+                                              self.height, self.width)
         mlp_weights = arena.hyper_forward() if residual else None
-        if self.rays != "batches":
-            main.wait_stream(side)            # "batches": the projection branch joins just before the decode backward
 
         eik_w = w["eikonal_loss"] if residual else 0.0
         scene = ops.SceneArgs(loc, rot, dim, mlp_weights, 1.0, self.scale, st)
@@ -256,6 +257,13 @@ class FrameLabeler:
         fine = ops.place_fine(coarse, coarse_w, self.sorted_uniforms, 0, st)
         rays = ops.RayArgs(origins, directions, fine)
         field = ops.field_forward(scene, rays)
+        main.wait_stream(side)                                        # targets / projection results from here on
+        if self.state_ahead is not None:
+            # branch 2 (side2): the NEXT step's ray batch, next to this step's backward
+            side2.wait_stream(main)
+            with torch.cuda.stream(side2):
+                self._draw_ahead(self.state_ahead)
+                self.state_ahead.advance()
         labels, _, _, parts = ops.composite_forward(scene, rays, field, 1.0, 0.0, 1e-6, targets=self.targets,
                                                     silhouette_weight=w["silhouette_loss"], eikonal_weight=eik_w)
         adjoint = ops.composite_backward(scene, rays, field, 1.0, 0.0, 1e-6, targets=self.targets, labels=labels,
@@ -263,12 +271,28 @@ class FrameLabeler:
         g_loc, g_rot, g_dim, g_w = ops.field_backward(scene, rays, adjoint)
         if residual:
             arena.hyper_backward(g_w)
-        if self.rays == "batches":
-            main.wait_stream(side)
+        if self.state_ahead is not None:
+            main.wait_stream(side2)
         arena.decode_backward(dim, rot, g_loc, g_dim, g_rot, proj_grad, w["iou_projection_loss"], w["l1_projection_loss"],
                               parts, proj_losses, self.losses)
         arena.adam_step(st)
         st.advance()
+
+    def _draw_ahead(self, state) -> None:
+        """Draws the ray batch keyed by `state`'s seed into `next_pixel_indices` (current stream)."""
+        pix, status = ops.select_rays(self.cdf, self.num_rays, step_state=state)
+        self.draw_failures.add_(status)
+        self.next_pixel_indices.copy_(pix)
+
+    def seek(self, step: int) -> None:
+        """Continue from optimisation step `step` (schedule, learning-rate decay, sampler streams); parameters and
+        optimiser moments are left as they are."""
+        with torch.cuda.stream(self.stream):
+            self.state.set_step(step)
+            if self.state_ahead is not None:
+                self._draw_ahead(self.state)
+                self.state_ahead.set_step(step + 1)
+        self.step_index = int(step)
 
     def _capture(self, residual: bool) -> None:
         graph = torch.cuda.CUDAGraph()
