@@ -79,7 +79,16 @@ typedef struct VsrdRays {
     const float* origins;         /* [R,3]   ray_positions                                    */
     const float* directions;      /* [R,3]   ray_directions                                   */
     const float* distances;       /* [R,M+1] sampled_distances, ascending                     */
+    /* Optional instance culling.  union_bound[R*M] = min over instances of the BOX SDF at every sample
+     * (vsrd_union_bound).  The residual lies in (0,1), so an instance whose box SDF exceeds union_bound + 1 by more than
+     * VSRD_CULL_LOG_EPS * temperature has a soft-min weight below exp(-VSRD_CULL_LOG_EPS) ~ 1e-13 of the dominant one:
+     * warp tiles made of such samples skip the residual MLP (forward: box value and gradient are written; backward:
+     * nothing is accumulated).  NULL disables it.  cull_stats (DEVICE uint64[2], may be NULL) accumulates
+     * {tiles skipped, tiles visited} over all field launches. */
+    const float* union_bound;
+    unsigned long long* cull_stats;
 } VsrdRays;
+#define VSRD_CULL_LOG_EPS 30.0f
 
 /* Arguments of hierarchical_volumetric_rendering (vsrd/rendering/renderers.py:177-188). */
 typedef struct VsrdRenderParams {
@@ -137,6 +146,10 @@ int vsrd_place_coarse(const float* bins, const float* jitter, uint64_t seed, con
 int vsrd_place_fine(const float* coarse_distances, const float* coarse_weights, const float* sorted_uniforms,
                     uint64_t seed, const VsrdStepState* step_state, int num_rays, int num_samples,
                     float* distances, void* stream);
+
+/* union_bound[R*M] = min_i box_sdf_i(sample) for the culling test described at VsrdRays (reads origins / directions /
+ * distances and the box parameters of `scene`; rays->union_bound itself is ignored). */
+int vsrd_union_bound(const VsrdScene* scene, const VsrdRays* rays, float* union_bound, void* stream);
 
 /* ---- a5-a8: per-(sample, instance) field: box SDF + residual MLP, value and spatial gradient.
  * out field[N][R*M] as float4 (d_i, dd_i/dx, dd_i/dy, dd_i/dz). */

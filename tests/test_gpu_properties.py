@@ -59,8 +59,18 @@ def F():
     return functional
 
 
+@pytest.fixture
+def no_culling():
+    from vsrd_b200 import ops
+    ops.set_culling(False)
+    yield
+    ops.set_culling(True)
+
+
 @pytest.mark.parametrize("n,layout", [(8, "street"), (24, "parking")])
-def test_full_size_properties(F, n, layout):
+def test_full_size_properties(F, n, layout, no_culling):
+    """Bit-level properties are those of the kernels themselves: instance culling (which may skip a warp tile in one
+    batch composition and not in another, a <= 1e-13 relative perturbation) is off here and has its own test below."""
     frame, leaves = _scene(n, layout)
     o, d = _rays(frame, 1000)
     dev_leaves, (labels, grads, cd, cw, fd, fw) = _render(F, leaves, o, d, 100, requires_grad=True)
@@ -206,3 +216,34 @@ def test_backward_m_tile_variants_agree(tmp_path):
         outs.append(torch.load(path))
     for a, b in zip(*outs):
         assert float((a - b).norm()) <= 1e-5 * float(b.norm()) + 1e-9, float((a - b).norm() / b.norm())
+
+
+@pytest.mark.parametrize("n,layout,temperature,share", [(8, "street", 0.1, 0.2), (24, "parking", 0.3, 0.2)])
+def test_instance_culling_is_invisible_at_the_parity_bar(F, n, layout, temperature, share):
+    """Late-schedule temperatures (weights below exp(-30) are dropped): the culled and the un-culled kernels
+    must agree far inside the parity tolerances, and the kernels must actually have skipped tiles."""
+    from vsrd_b200 import ops
+    frame, leaves = _scene(n, layout, seed=0)
+    o, d = _rays(frame, 500, seed=2)
+    sched = dict(temperature=temperature, std_deviation=temperature, cosine_ratio=0.9)
+    results = []
+    try:
+        for enabled in (True, False):
+            ops.set_culling(enabled)
+            ops.culling_counters(DEV, reset=True)
+            dev_leaves, (labels, grads, cd, cw, fd, fw) = _render(F, leaves, o, d, 64, requires_grad=True, **sched)
+            gen = torch.Generator(device=DEV).manual_seed(3)
+            u = torch.randn(labels.shape, device=DEV, generator=gen)
+            v = torch.randn(grads.shape, device=DEV, generator=gen) * 0.01
+            g = torch.autograd.grad([labels, grads], dev_leaves, [u, v])
+            results.append((labels.detach(), grads.detach(), fd, fw.detach(), g, ops.culling_counters(DEV)))
+    finally:
+        ops.set_culling(True)
+    (la, ga, fda, fwa, gra, (culled, visited)), (lb, gb, fdb, fwb, grb, (culled_off, visited_off)) = results
+    assert visited > 0 and culled > share * visited, (culled, visited)    # a large share of the tiles is far
+    assert culled_off == 0 and visited_off == 0
+    assert torch.equal(fda, fdb)                                          # identical sample placement
+    assert float((la - lb).abs().max()) < 1e-9 and float((fwa - fwb).abs().max()) < 1e-9
+    assert float((ga - gb).abs().max()) < 1e-6
+    for a, b in zip(gra, grb):
+        assert float((a - b).norm()) <= 1e-6 * float(b.norm()) + 1e-12, float((a - b).norm() / b.norm())

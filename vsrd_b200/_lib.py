@@ -77,6 +77,8 @@ class VsrdRays(ctypes.Structure):
         ("origins", ctypes.c_void_p),
         ("directions", ctypes.c_void_p),
         ("distances", ctypes.c_void_p),
+        ("union_bound", ctypes.c_void_p),
+        ("cull_stats", ctypes.c_void_p),
     ]
 
 
@@ -168,6 +170,7 @@ SIGNATURES = {
     "vsrd_gather_rays": (_I, [_V, _V, _V, _I, _I, _I, _I, _V, _V, _V]),
     "vsrd_place_coarse": (_I, [_V, _V, ctypes.c_uint64, _V, _I, _I, _V, _V]),
     "vsrd_place_fine": (_I, [_V, _V, _V, ctypes.c_uint64, _V, _I, _I, _V, _V]),
+    "vsrd_union_bound": (_I, [_P(VsrdScene), _P(VsrdRays), _V, _V]),
     "vsrd_field_forward": (_I, [_P(VsrdScene), _P(VsrdRays), _V, _V]),
     "vsrd_composite_forward": (_I, [_P(VsrdScene), _P(VsrdRays), _P(VsrdRenderParams), _V, _V, _V, _V,
                                     _P(VsrdLoss), _V, _V]),

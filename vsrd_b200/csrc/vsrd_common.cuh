@@ -46,7 +46,15 @@ struct RaysDev {
     const float* origins;
     const float* dirs;
     const float* dist;
+    const float* bound;               // min over instances of the box SDF per sample, or NULL (no culling)
+    unsigned long long* cull_stats;   // {tiles skipped, tiles visited} or NULL
 };
+
+constexpr float kCullLogEps = VSRD_CULL_LOG_EPS;
+
+__device__ __forceinline__ float scene_temperature(const SceneDev& s) {
+    return s.state != nullptr ? s.state->temperature : s.T;
+}
 
 __device__ __forceinline__ Vec4 ld4(const float4* p) {
     const float4 v = __ldg(p);
@@ -98,7 +106,7 @@ inline int check_rays(const VsrdRays* r, RaysDev& d) {
     VSRD_CHECK_ARG(r->num_rays >= 0, "num_rays must be non-negative");
     VSRD_CHECK_ARG(r->num_intervals >= 1 && r->num_intervals <= VSRD_MAX_INTERVALS, "num_intervals must be in [1, 512]");
     VSRD_CHECK_ARG(r->num_rays == 0 || (r->origins && r->directions && r->distances), "ray pointers must not be NULL");
-    d = RaysDev{r->num_rays, r->num_intervals, r->origins, r->directions, r->distances};
+    d = RaysDev{r->num_rays, r->num_intervals, r->origins, r->directions, r->distances, r->union_bound, r->cull_stats};
     return 0;
 }
 

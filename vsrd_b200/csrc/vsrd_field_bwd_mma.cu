@@ -165,6 +165,8 @@ __global__ void __launch_bounds__(BwdCfg<MT>::kThreads, 1) field_backward_mma_ke
     const long long begin = all_tiles * blockIdx.x / gridDim.x;
     const long long end = all_tiles * (blockIdx.x + 1) / gridDim.x;
     const float pi_scale = kPiF / scene.scale;
+    const float cull_margin = kCullLogEps * scene_temperature(scene);
+    unsigned tiles_visited = 0, tiles_culled = 0;          // per warp; two atomics per warp at the end
 
     for (long long seg = begin; seg < end;) {
         const int inst = (int)(seg / tiles_per_inst);
@@ -203,6 +205,11 @@ __global__ void __launch_bounds__(BwdCfg<MT>::kThreads, 1) field_backward_mma_ke
                 sample_position(rays, r, j, x);
                 BoxEval b;
                 box_eval(x, I, b);
+                if (rays.bound != nullptr) {                // instance culling, same test as the forward kernel
+                    const bool far = !valid || b.value - (__ldg(rays.bound + idx) + 1.0f) > cull_margin;
+                    ++tiles_visited;
+                    if (__all_sync(kFull, far)) { ++tiles_culled; continue; }
+                }
                 const float m[3] = {fabsf(b.p[0]), b.p[1], b.p[2]};
                 const float coef[3] = {b.s[0] * pi_scale, pi_scale, pi_scale};
 #pragma unroll
@@ -602,6 +609,10 @@ __global__ void __launch_bounds__(BwdCfg<MT>::kThreads, 1) field_backward_mma_ke
             }
         }
         seg = seg_end;
+    }
+    if (lane == 0 && rays.cull_stats != nullptr && tiles_visited) {
+        atomicAdd(rays.cull_stats, (unsigned long long)tiles_culled);
+        atomicAdd(rays.cull_stats + 1, (unsigned long long)tiles_visited);
     }
 }
 

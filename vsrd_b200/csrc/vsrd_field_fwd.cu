@@ -82,6 +82,8 @@ __global__ void __launch_bounds__(FwdCfg<MT>::kThreads, 1) field_forward_mma_ker
     const long long all_tiles = (long long)scene.N * tiles_per_inst;
     const long long begin = all_tiles * blockIdx.x / gridDim.x;
     const long long end = all_tiles * (blockIdx.x + 1) / gridDim.x;
+    const float cull_margin = kCullLogEps * scene_temperature(scene);
+    unsigned tiles_visited = 0, tiles_culled = 0;          // per warp; two atomics per warp at the end
 
     for (long long seg = begin; seg < end;) {
         const int inst = (int)(seg / tiles_per_inst);
@@ -108,6 +110,23 @@ __global__ void __launch_bounds__(FwdCfg<MT>::kThreads, 1) field_forward_mma_ker
             sample_position(rays, r, j, x);
             BoxEval b;
             box_eval(x, I, b);
+            if (rays.bound != nullptr) {
+                // instance culling (VsrdRays::union_bound): every sample of the tile is farther from this instance's box
+                // than the nearest box + the residual's range + 30 T -> soft-min weight < 1e-13: box value suffices
+                const bool in_range = lane < kRows && base + lane < total;
+                const bool far = !in_range || b.value - (__ldg(rays.bound + idx) + 1.0f) > cull_margin;
+                ++tiles_visited;
+                if (__all_sync(kFull, far)) {
+                    if (in_range)
+                        field[(size_t)inst * total + base + lane] = make_float4(
+                            b.value,
+                            I.R[0] * b.gp[0] + I.R[1] * b.gp[1] + I.R[2] * b.gp[2],
+                            I.R[3] * b.gp[0] + I.R[4] * b.gp[1] + I.R[5] * b.gp[2],
+                            I.R[6] * b.gp[0] + I.R[7] * b.gp[1] + I.R[8] * b.gp[2]);
+                    ++tiles_culled;
+                    continue;
+                }
+            }
             f2 arow[MT][3];                                // PE arguments of rows (g, g + 8) of each m-tile
             {
                 const float m[3] = {fabsf(b.p[0]), b.p[1], b.p[2]};
@@ -287,6 +306,30 @@ __global__ void __launch_bounds__(FwdCfg<MT>::kThreads, 1) field_forward_mma_ker
         }
         seg = seg_end;
     }
+    if (lane == 0 && rays.cull_stats != nullptr && tiles_visited) {
+        atomicAdd(rays.cull_stats, (unsigned long long)tiles_culled);
+        atomicAdd(rays.cull_stats + 1, (unsigned long long)tiles_visited);
+    }
+}
+
+// min over the instances of the BOX SDF at every sample (the culling bound, see VsrdRays::union_bound)
+__global__ void union_bound_kernel(SceneDev scene, RaysDev rays, float* __restrict__ bound) {
+    const size_t total = (size_t)rays.R * rays.M;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int r = (int)(idx / rays.M);
+    const int j = (int)(idx - (size_t)r * rays.M);
+    float x[3];
+    sample_position(rays, r, j, x);
+    float lowest = INFINITY;
+    for (int i = 0; i < scene.N; ++i) {
+        Instance I;
+        load_instance(scene, i, I);
+        BoxEval b;
+        box_eval(x, I, b);
+        lowest = fminf(lowest, b.value);
+    }
+    bound[idx] = lowest;
 }
 
 static int g_fwd_sms = 0;
@@ -356,12 +399,24 @@ int vsrd_field_forward(const VsrdScene* scene, const VsrdRays* rays, float* fiel
     return launch_field(s, r, field, stream);
 }
 
+int vsrd_union_bound(const VsrdScene* scene, const VsrdRays* rays, float* union_bound, void* stream) {
+    SceneDev s; RaysDev r;
+    if (check_scene(scene, s) || check_rays(rays, r)) return 1;
+    const size_t total = (size_t)r.R * r.M;
+    if (total == 0) return 0;
+    VSRD_CHECK_ARG(union_bound != nullptr, "union_bound is NULL");
+    VSRD_CHECK_ARG(total < (size_t)1 << 31, "R*M must be < 2^31");
+    union_bound_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(s, r, union_bound);
+    VSRD_CHECK_LAUNCH();
+    return 0;
+}
+
 int vsrd_field_points(const VsrdScene* scene, const float* points, int num_points, float* field, void* stream) {
     SceneDev s;
     if (check_scene(scene, s)) return 1;
     VSRD_CHECK_ARG(num_points >= 0, "num_points must be non-negative");
     VSRD_CHECK_ARG(num_points == 0 || points != nullptr, "points is NULL");
-    const RaysDev r{num_points, 1, points, nullptr, nullptr};     // points mode of sample_position()
+    const RaysDev r{num_points, 1, points, nullptr, nullptr, nullptr, nullptr};     // points mode of sample_position()
     return launch_field(s, r, field, stream);
 }
 

@@ -19,7 +19,8 @@ from .functional import distance_bins
 
 
 class SilhouetteStep:
-    KERNELS_PER_STEP = 10   # gather, place_coarse, field, composite, place_fine, field, composite, composite_bwd, field_bwd, reduce
+    # gather, place_coarse, (cull bound, field), composite, place_fine, (cull bound, field), composite, composite_bwd, field_bwd, reduce
+    KERNELS_PER_STEP = 12
 
     def __init__(self, *, inv_projection, camera_positions, image_size, num_rays: int, num_samples: int,
                  distance_range=(0.0, 100.0), scale: float = 100.0, epsilon: float = 1e-6,

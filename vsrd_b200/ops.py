@@ -7,6 +7,7 @@ enqueued on torch's current stream, so the calls compose with CUDA graphs and st
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -75,7 +76,48 @@ class RayArgs:
         self.num_intervals = self.distances.shape[1] - 1
         if self.num_intervals > _lib.MAX_INTERVALS:
             raise RuntimeError(f"vsrd_b200: at most {_lib.MAX_INTERVALS} intervals per ray, got {self.num_intervals}")
-        self.struct = VsrdRays(r, self.num_intervals, _ptr(self.origins), _ptr(self.directions), _ptr(self.distances))
+        self.union_bound = None       # culling bound (enable_culling)
+        self.struct = VsrdRays(r, self.num_intervals, _ptr(self.origins), _ptr(self.directions), _ptr(self.distances), None, None)
+
+    def enable_culling(self, scene: "SceneArgs") -> None:
+        """Computes the per-sample culling bound (min box SDF over the instances, one small launch) and attaches it:
+        the field kernels then skip the residual MLP on warp tiles whose soft-min weight is provably < 1e-13
+        (include/vsrd_b200.h, VsrdRays::union_bound)."""
+        if self.union_bound is not None or self.num_rays == 0:
+            return
+        dev = self.directions.device
+        self.union_bound = torch.empty(self.num_rays * self.num_intervals, device=dev, dtype=torch.float32)
+        _lib.check(_lib.load().vsrd_union_bound(ctypes.byref(scene.struct), ctypes.byref(self.struct),
+                                                _ptr(self.union_bound), _stream()))
+        self.struct.union_bound = _ptr(self.union_bound)
+        self.struct.cull_stats = _ptr(_cull_stats(dev))
+
+
+# ---- instance culling (SURVEY.md 8d) -----------------------------------------------------------------
+_culling = os.environ.get("VSRD_CULL", "1") != "0"
+_cull_counters = {}
+
+
+def set_culling(enabled: bool) -> None:
+    """Instance culling in the residual field kernels (on by default; VSRD_CULL=0 turns it off at import)."""
+    global _culling
+    _culling = bool(enabled)
+
+
+def _cull_stats(device) -> torch.Tensor:
+    key = torch.device(device).index or 0
+    if key not in _cull_counters:
+        _cull_counters[key] = torch.zeros(2, dtype=torch.int64, device=device)
+    return _cull_counters[key]
+
+
+def culling_counters(device="cuda", reset: bool = False):
+    """(warp tiles skipped, warp tiles visited) accumulated by the field kernels on `device` (synchronises)."""
+    t = _cull_stats(torch.device(device))
+    culled, visited = (int(v) for v in t.cpu())
+    if reset:
+        t.zero_()
+    return culled, visited
 
 
 def _state_ptr(step_state) -> Optional[int]:
@@ -150,6 +192,8 @@ def place_fine(coarse_distances, coarse_weights, sorted_uniforms: Optional[torch
 # ---- field + compositing ----------------------------------------------------------------------
 
 def field_forward(scene: SceneArgs, rays: RayArgs) -> torch.Tensor:
+    if _culling and scene.mlp_weights is not None:
+        rays.enable_culling(scene)
     field = torch.empty(scene.num_instances, rays.num_rays * rays.num_intervals, 4,
                         device=rays.directions.device, dtype=torch.float32)
     _lib.check(_lib.load().vsrd_field_forward(ctypes.byref(scene.struct), ctypes.byref(rays.struct), _ptr(field), _stream()))
