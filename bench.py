@@ -58,6 +58,8 @@ def parse_args():
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--frames", type=int, default=2, help="whole frames labelled (in flight together) for frames/hour; 0 = skip")
     ap.add_argument("--frame-steps", type=int, default=3000)
+    ap.add_argument("--schedule-frac", type=float, default=0.5,
+                    help="operating point of the device-resident leg on the annealing schedule (0.5 = step 1500 of 3000)")
     ap.add_argument("--compare-torch-models", action="store_true",
                     help="also time the end-to-end step with the models as nn.Modules under autograd (informational)")
     return ap.parse_args()
@@ -344,7 +346,7 @@ def run_native(args):
     total = K + W
     frame, inv_proj, cam, pool, targets = build_frame_inputs(args, rank, device, total)
     detector, hyper, encoder = make_models(args, frame, rank, device)
-    sched = schedule_at()
+    sched = schedule_at(args.schedule_frac)
     units = args.rays * (3 * args.samples - 2)
 
     # ---------------- device-resident leg ("value") ----------------
@@ -384,6 +386,7 @@ def run_native(args):
             ends[k].record()
         barrier()
     dev_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
+    culled_tiles, visited_tiles = ops.culling_counters(device, reset=True)
     loss_value = float(step.out["loss_parts"].sum())
     if not math.isfinite(loss_value):
         raise RuntimeError("bench.py: non-finite loss from the device-resident leg")
@@ -605,6 +608,11 @@ def run_native(args):
                          "algorithmic_hbm_bytes_per_step": hbm_bytes,
                          "hbm_peak_gbs": peaks.get("hbm_gbs")},
             "kernel_ms": per_kernel,
+            "culling": {"enabled": visited_tiles > 0, "warp_tiles_skipped": culled_tiles, "warp_tiles_visited": visited_tiles,
+                        "skipped_fraction": (culled_tiles / visited_tiles) if visited_tiles else 0.0,
+                        "note": "instance culling (SURVEY 8d): tiles whose soft-min weight is < exp(-30) skip the residual "
+                                "MLP; counted in-kernel over warm-up + timed steps of the device-resident leg; `value` counts "
+                                "nominal ray-samples"},
             "clocks": clocks.summary(),
             "loss": loss_value,
         }

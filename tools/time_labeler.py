@@ -40,7 +40,9 @@ torch.cuda.synchronize(); t3 = time.perf_counter()
 out = lab.boxes()
 gt = synthetic.gt_corners(frame)
 err = float((out["boxes_3d"].cpu().mean(1) - gt.mean(1)).norm(dim=-1).mean())
-res = dict(first_frame_setup_s=t2 - t0, first_frame_steps_s=t3 - t2,
+from vsrd_b200 import ops as _ops
+culled, visited = _ops.culling_counters(dev, reset=True)
+res = dict(culled_tile_fraction_first_frame=(culled / visited) if visited else 0.0, first_frame_setup_s=t2 - t0, first_frame_steps_s=t3 - t2,
            warmup_ms_per_step=(marks[w] - marks[10]) / (w - 10) * 1e3,
            main_ms_per_step=(t3 - marks[w + 10]) / (a.steps - w - 10) * 1e3,
            centre_error_m=err, losses=lab.losses.tolist(), draw_failures=int(lab.draw_failures))

@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(FwdCfg<MT>::kThreads, 1) field_forward_mma_ker
     using Cfg = FwdCfg<MT>;
     constexpr int kRows = Cfg::kRows, kSlots = 2 * MT, kLayerPairs = 4 * MT;   // pair rows of z (then as many of g1/sigma) per layer
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_next_tile;
     float4* sF = reinterpret_cast<float4*>(smem_raw);
     float* sTail = reinterpret_cast<float*>(sF + kFragFloat4);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -90,6 +91,7 @@ __global__ void __launch_bounds__(FwdCfg<MT>::kThreads, 1) field_forward_mma_ker
         const long long seg_end = min(end, (long long)(inst + 1) * tiles_per_inst);
         __syncthreads();                                   // previous instance's tiles are done
         stage_weight_fragments(scene.W + (size_t)inst * kNumW, sF, sTail);
+        if (threadIdx.x == 0) s_next_tile = 0;
         __syncthreads();
         Instance I;
         load_instance(scene, inst, I);
@@ -98,8 +100,14 @@ __global__ void __launch_bounds__(FwdCfg<MT>::kThreads, 1) field_forward_mma_ker
         const f2 w4p1 = make_float2(sTail[kTailW4 + 8 + 2 * t], sTail[kTailW4 + 8 + 2 * t + 1]);
         const float b4 = sTail[kTailB4];
 
+        // Warps take tiles from a CTA-wide counter (outputs are per sample, so the assignment is free to vary): with
+        // instance culling the cost of a tile is bimodal, and a static stride leaves the slowest warp near the worst case.
 #pragma unroll 1
-        for (long long tile = seg + warp; tile < seg_end; tile += Cfg::kWarps) {
+        while (true) {
+            int claimed = 0;
+            if (lane == 0) claimed = atomicAdd(&s_next_tile, 1);
+            const long long tile = seg + __shfl_sync(kFull, claimed, 0);
+            if (tile >= seg_end) break;
             const int base = (int)(tile - (long long)inst * tiles_per_inst) * kRows;
             // ------------------------------------------------------------ 1. lane == sample (lanes < kRows)
             const int row = lane & (kRows - 1);

@@ -252,7 +252,7 @@ class FrameLabeler:
         scene = ops.SceneArgs(loc, rot, dim, mlp_weights, 1.0, self.scale, st)
         coarse = ops.place_coarse(self.bins, self.num_rays, self.jitter, 0, st)
         rays = ops.RayArgs(origins, directions, coarse)
-        field = ops.field_forward(scene, rays)
+        field = ops.field_forward(scene, rays, cull=False)
         _, _, coarse_w, _ = ops.composite_forward(scene, rays, field, 1.0, 0.0, 1e-6)
         fine = ops.place_fine(coarse, coarse_w, self.sorted_uniforms, 0, st)
         rays = ops.RayArgs(origins, directions, fine)

@@ -22,11 +22,11 @@ class _RenderPass(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, locations, rotations, half_extents, mlp_weights, origins, directions, distances,
-                temperature, scale, std_deviation, cosine_ratio, epsilon, step_state=None):
+                temperature, scale, std_deviation, cosine_ratio, epsilon, step_state=None, cull=None):
         scene = SceneArgs(locations.detach(), rotations.detach(), half_extents.detach(),
                           None if mlp_weights is None else mlp_weights.detach(), temperature, scale, step_state)
         rays = RayArgs(origins.detach(), directions.detach(), distances.detach())
-        field = ops.field_forward(scene, rays)
+        field = ops.field_forward(scene, rays, cull=cull)
         labels, grads, weights, _ = ops.composite_forward(scene, rays, field, std_deviation, cosine_ratio, epsilon)
         ctx.scene, ctx.rays, ctx.field = scene, rays, field
         ctx.render = (std_deviation, cosine_ratio, epsilon)
@@ -40,7 +40,7 @@ class _RenderPass(torch.autograd.Function):
                                          grad_labels=grad_labels, grad_gradients=grad_gradients,
                                          grad_weights=grad_weights)
         g_loc, g_rot, g_dim, g_w = ops.field_backward(ctx.scene, ctx.rays, adjoint)
-        return g_loc, g_rot, g_dim, (g_w if ctx.has_mlp else None), None, None, None, None, None, None, None, None, None
+        return g_loc, g_rot, g_dim, (g_w if ctx.has_mlp else None), None, None, None, None, None, None, None, None, None, None
 
 
 def render_pass(locations, rotations, half_extents, mlp_weights, ray_positions, ray_directions, distances, *,
@@ -54,9 +54,12 @@ def render_pass(locations, rotations, half_extents, mlp_weights, ray_positions, 
     differentiable w.r.t. the first four arguments.  `step_state` (ops.StepState) makes the kernels read
     temperature / std_deviation / cosine_ratio from device memory instead (CUDA-graph replay across steps).
     """
+    # no-grad calls are the coarse placement passes of the two-pass wrapper (main.py:515-516): culling off there
+    # (ops.field_forward); decided here because grad mode is always off inside Function.forward
+    cull = None if torch.is_grad_enabled() else False
     return _RenderPass.apply(locations, rotations, half_extents, mlp_weights, ray_positions, ray_directions,
                              distances, float(temperature), float(scale), float(std_deviation),
-                             float(cosine_ratio), float(epsilon), step_state)
+                             float(cosine_ratio), float(epsilon), step_state, cull)
 
 
 def distance_bins(distance_range: Sequence[float], num_samples: int, device) -> torch.Tensor:

@@ -191,8 +191,11 @@ def place_fine(coarse_distances, coarse_weights, sorted_uniforms: Optional[torch
 
 # ---- field + compositing ----------------------------------------------------------------------
 
-def field_forward(scene: SceneArgs, rays: RayArgs) -> torch.Tensor:
-    if _culling and scene.mlp_weights is not None:
+def field_forward(scene: SceneArgs, rays: RayArgs, cull: Optional[bool] = None) -> torch.Tensor:
+    """`cull`: instance culling for this pass (None = the module default, see set_culling).  Callers switch it off for
+    the coarse pass: its 32-sample tiles span ~32 m of ray and are almost never skippable, so the bound launch is not
+    worth it there."""
+    if (_culling if cull is None else cull) and scene.mlp_weights is not None:
         rays.enable_culling(scene)
     field = torch.empty(scene.num_instances, rays.num_rays * rays.num_intervals, 4,
                         device=rays.directions.device, dtype=torch.float32)
