@@ -87,8 +87,16 @@ typedef struct VsrdRays {
      * {tiles skipped, tiles visited} over all field launches. */
     const float* union_bound;
     unsigned long long* cull_stats;
+    /* Backward side of the culling: live_tiles [N][ceil(R*M / vsrd_backward_tile_rows())] bytes, ZEROED by the caller
+     * before vsrd_composite_backward, which (a) writes exact zeros for the adjoints of instances whose soft-min weight
+     * is below exp(-VSRD_CULL_LOG_EPS) and (b) marks every warp tile of vsrd_field_backward that received a non-zero
+     * adjoint.  vsrd_field_backward then visits only the marked tiles (compacted in order per thread block, so the
+     * work is balanced and the accumulation order stays deterministic).  NULL disables it. */
+    uint8_t* live_tiles;
 } VsrdRays;
 #define VSRD_CULL_LOG_EPS 30.0f
+/* Samples per warp tile of the backward field kernel (16 or 32), for sizing VsrdRays::live_tiles. */
+int vsrd_backward_tile_rows(void);
 
 /* Arguments of hierarchical_volumetric_rendering (vsrd/rendering/renderers.py:177-188). */
 typedef struct VsrdRenderParams {

@@ -54,7 +54,7 @@ def test_struct_layout_matches_header():
     assert ctypes.sizeof(_lib.VsrdStepState) == 32
     assert ctypes.sizeof(_lib.VsrdSchedule) == 48
     assert ctypes.sizeof(_lib.VsrdViews) == 32
-    assert ctypes.sizeof(_lib.VsrdRays) == 48
+    assert ctypes.sizeof(_lib.VsrdRays) == 56
     assert ctypes.sizeof(_lib.VsrdRenderParams) == 16
     assert ctypes.sizeof(_lib.VsrdLoss) == 16
     # model entry points (sizes printed by a C program including the header: gcc, LP64)
@@ -74,7 +74,7 @@ def test_argument_errors_are_reported_without_gpu(lib):
     """Validation happens before any CUDA call, so the error convention is testable on CPU."""
     from vsrd_b200 import _lib
     scene = _lib.VsrdScene(0, 0, None, None, None, None, 1.0, 100.0, None)
-    rays = _lib.VsrdRays(1, 1, None, None, None, None, None)
+    rays = _lib.VsrdRays(1, 1, None, None, None, None, None, None)
     status = lib.vsrd_field_forward(ctypes.byref(scene), ctypes.byref(rays), None, None)
     assert status != 0
     assert b"num_instances" in lib.vsrd_last_error()

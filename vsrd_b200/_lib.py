@@ -79,6 +79,7 @@ class VsrdRays(ctypes.Structure):
         ("distances", ctypes.c_void_p),
         ("union_bound", ctypes.c_void_p),
         ("cull_stats", ctypes.c_void_p),
+        ("live_tiles", ctypes.c_void_p),
     ]
 
 
@@ -166,6 +167,7 @@ SIGNATURES = {
     "vsrd_version": (_I, []),
     "vsrd_last_error": (ctypes.c_char_p, []),
     "vsrd_backward_blocks_per_instance": (_I, [_I, _I, _I]),
+    "vsrd_backward_tile_rows": (_I, []),
     "vsrd_ray_directions": (_I, [_V, _I, _I, _I, _V, _V]),
     "vsrd_gather_rays": (_I, [_V, _V, _V, _I, _I, _I, _I, _V, _V, _V]),
     "vsrd_place_coarse": (_I, [_V, _V, ctypes.c_uint64, _V, _I, _I, _V, _V]),

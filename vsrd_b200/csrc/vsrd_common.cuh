@@ -48,6 +48,7 @@ struct RaysDev {
     const float* dist;
     const float* bound;               // min over instances of the box SDF per sample, or NULL (no culling)
     unsigned long long* cull_stats;   // {tiles skipped, tiles visited} or NULL
+    unsigned char* live;              // [N][tiles] marks of backward tiles with a non-zero adjoint, or NULL
 };
 
 constexpr float kCullLogEps = VSRD_CULL_LOG_EPS;
@@ -106,13 +107,14 @@ inline int check_rays(const VsrdRays* r, RaysDev& d) {
     VSRD_CHECK_ARG(r->num_rays >= 0, "num_rays must be non-negative");
     VSRD_CHECK_ARG(r->num_intervals >= 1 && r->num_intervals <= VSRD_MAX_INTERVALS, "num_intervals must be in [1, 512]");
     VSRD_CHECK_ARG(r->num_rays == 0 || (r->origins && r->directions && r->distances), "ray pointers must not be NULL");
-    d = RaysDev{r->num_rays, r->num_intervals, r->origins, r->directions, r->distances, r->union_bound, r->cull_stats};
+    d = RaysDev{r->num_rays, r->num_intervals, r->origins, r->directions, r->distances, r->union_bound, r->cull_stats, r->live_tiles};
     return 0;
 }
 
 // vsrd_field_bwd_mma.cu: tensor-core field backward for residual instances.
 // Rows of VSRD_GRAD_STRIDE floats the caller must provide in `partials` (-1 on error).
 int backward_mma_partial_rows(int num_instances);
+int backward_mma_tile_rows();         // samples per warp tile (16 or 32); -1 on error
 int launch_field_backward_mma(const SceneDev& s, const RaysDev& r, const float* adjoint, float* partials,
                               float* gloc, float* grot, float* gdim, float* gW, cudaStream_t st);
 

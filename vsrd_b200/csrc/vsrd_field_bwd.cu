@@ -585,6 +585,8 @@ using namespace vsrd;
 
 extern "C" {
 
+int vsrd_backward_tile_rows(void) { return backward_mma_tile_rows(); }
+
 int vsrd_backward_blocks_per_instance(int num_instances, int num_rays, int num_intervals) {
     if (device_setup()) return -1;
     // the residual kernel has the lower occupancy; size for the larger grid so one buffer fits both

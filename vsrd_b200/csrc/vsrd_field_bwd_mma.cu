@@ -165,8 +165,10 @@ __global__ void __launch_bounds__(BwdCfg<MT>::kThreads, 1) field_backward_mma_ke
     const long long begin = all_tiles * blockIdx.x / gridDim.x;
     const long long end = all_tiles * (blockIdx.x + 1) / gridDim.x;
     const float pi_scale = kPiF / scene.scale;
-    const float cull_margin = kCullLogEps * scene_temperature(scene);
     unsigned tiles_visited = 0, tiles_culled = 0;          // per warp; two atomics per warp at the end
+    constexpr int kChunkTiles = 2048;
+    __shared__ unsigned short s_list[kChunkTiles];
+    __shared__ int s_live;
 
     for (long long seg = begin; seg < end;) {
         const int inst = (int)(seg / tiles_per_inst);
@@ -186,8 +188,36 @@ __global__ void __launch_bounds__(BwdCfg<MT>::kThreads, 1) field_backward_mma_ke
 #pragma unroll
         for (int k = 0; k < (Cfg::kPoseInRegs ? 16 : 1); ++k) pose_reg[k] = 0.0f;
 
+        // With culling the cost of a tile is bimodal; a static stride over all tiles leaves the slowest warp near the
+        // worst case.  vsrd_composite_backward marked the tiles that received a non-zero adjoint (rays.live): per chunk
+        // the CTA compacts the marked tile indices IN ORDER and the warps stride over that list: balanced, and the
+        // accumulation order stays a function of the inputs only (deterministic).
+        const unsigned char* live = rays.live != nullptr ? rays.live + (size_t)inst * tiles_per_inst : nullptr;
 #pragma unroll 1
-        for (long long tile = seg + warp; tile < seg_end; tile += kWarpsB) {
+        for (long long chunk = seg; chunk < seg_end; chunk += kChunkTiles) {
+        const int chunk_tiles = (int)min((long long)kChunkTiles, seg_end - chunk);
+        int live_tiles = chunk_tiles;
+        if (live != nullptr) {
+            if (warp == 0) {
+                const unsigned char* flags = live + (chunk - (long long)inst * tiles_per_inst);
+                const int per = (chunk_tiles + 31) / 32, first = lane * per, last = min(first + per, chunk_tiles);
+                int mine = 0;
+                for (int q = first; q < last; ++q) mine += __ldg(flags + q) ? 1 : 0;
+                int incl = mine;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int up = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += up; }
+                int pos = incl - mine;
+                for (int q = first; q < last; ++q)
+                    if (__ldg(flags + q)) s_list[pos++] = (unsigned short)q;
+                if (lane == 31) s_live = incl;
+            }
+            __syncthreads();
+            live_tiles = s_live;
+            if (lane == 0 && warp == 0) { tiles_visited += (unsigned)chunk_tiles; tiles_culled += (unsigned)(chunk_tiles - live_tiles); }
+        }
+#pragma unroll 1
+        for (int k = warp; k < live_tiles; k += kWarpsB) {
+            const long long tile = chunk + (live != nullptr ? (int)s_list[k] : k);
             const int base = (int)(tile - (long long)inst * tiles_per_inst) * kRows;
             const int row = lane & (kRows - 1);             // MT = 1: lanes 16..31 shadow rows 0..15 with zero adjoints
             const int idx = min(base + row, total - 1);
@@ -205,11 +235,6 @@ __global__ void __launch_bounds__(BwdCfg<MT>::kThreads, 1) field_backward_mma_ke
                 sample_position(rays, r, j, x);
                 BoxEval b;
                 box_eval(x, I, b);
-                if (rays.bound != nullptr) {                // instance culling, same test as the forward kernel
-                    const bool far = !valid || b.value - (__ldg(rays.bound + idx) + 1.0f) > cull_margin;
-                    ++tiles_visited;
-                    if (__all_sync(kFull, far)) { ++tiles_culled; continue; }
-                }
                 const float m[3] = {fabsf(b.p[0]), b.p[1], b.p[2]};
                 const float coef[3] = {b.s[0] * pi_scale, pi_scale, pi_scale};
 #pragma unroll
@@ -539,6 +564,8 @@ __global__ void __launch_bounds__(BwdCfg<MT>::kThreads, 1) field_backward_mma_ke
             }
             __syncwarp();
         }
+        if (live != nullptr) __syncthreads();               // the tile list is rebuilt for the next chunk
+        }
         // ---------------------------------------------------------------- flush this segment
         {
             // last layer: reduce over the 8 quads (lane bits 2..4); bias / pose: over all 32 lanes
@@ -675,6 +702,11 @@ static int launch(const SceneDev& s, const RaysDev& r, const float* adjoint, flo
 }
 
 }  // namespace bwd5
+
+int backward_mma_tile_rows() {
+    if (bwd5::setup()) return -1;
+    return bwd5::g_bwd_mt == 1 ? 16 : 32;
+}
 
 int backward_mma_partial_rows(int num_instances) {
     if (bwd5::setup()) return -1;

@@ -424,7 +424,7 @@ int vsrd_field_points(const VsrdScene* scene, const float* points, int num_point
     if (check_scene(scene, s)) return 1;
     VSRD_CHECK_ARG(num_points >= 0, "num_points must be non-negative");
     VSRD_CHECK_ARG(num_points == 0 || points != nullptr, "points is NULL");
-    const RaysDev r{num_points, 1, points, nullptr, nullptr, nullptr, nullptr};     // points mode of sample_position()
+    const RaysDev r{num_points, 1, points, nullptr, nullptr, nullptr, nullptr, nullptr};     // points mode of sample_position()
     return launch_field(s, r, field, stream);
 }
 

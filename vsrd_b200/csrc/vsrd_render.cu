@@ -314,7 +314,7 @@ template <int NMAX>
 __global__ void __launch_bounds__(VSRD_MAX_INTERVALS) composite_backward_kernel(
         SceneDev scene, RaysDev rays, float sigma, float rho, float eps, const float4* __restrict__ field,
         const float* __restrict__ grad_labels, const float* __restrict__ grad_grads, const float* __restrict__ grad_weights,
-        LossDev loss, const float* __restrict__ labels, float4* __restrict__ adjoint) {
+        LossDev loss, const float* __restrict__ labels, float4* __restrict__ adjoint, int tile_shift, int tiles_per_inst) {
     __shared__ float s_tot[kMaxRayWarps];
     __shared__ float s_suf[kMaxRayWarps];
     __shared__ float s_gl[NMAX];
@@ -357,6 +357,8 @@ __global__ void __launch_bounds__(VSRD_MAX_INTERVALS) composite_backward_kernel(
     UnionEval u;
     OpacityEval o;
     float alpha = 0.0f, a = 0.0f, delta = 0.0f;
+    unsigned live_mask = 0;                             // instances with a non-zero adjoint at this sample
+    constexpr float kCullWeight = 9.3576e-14f;          // exp(-VSRD_CULL_LOG_EPS)
     constexpr bool kRegs = NMAX <= kRegsMaxInstances;   // all instances' field values live in registers
     UnionRegs<kRegs ? NMAX : 1> ur;
     if (valid) {
@@ -405,10 +407,30 @@ __global__ void __launch_bounds__(VSRD_MAX_INTERVALS) composite_backward_kernel(
         }
         auto wbar = [&](int i) { return omega * s_gl[i]; };
         auto store = [&](int i, const Vec4& q) {
-            adjoint[(size_t)i * stride + idx] = make_float4(q.x, q.y, q.z, q.w);
+            Vec4 v = q;
+            if (rays.live != nullptr) {
+                // culling: an instance whose soft-min weight is below exp(-30) gets an exactly zero adjoint
+                float wi;
+                if constexpr (kRegs) wi = ur.e[i] * ur.invZ;
+                else wi = expf(-(load(i).x / T) - u.mneg) / u.Z;
+                if (wi < kCullWeight) v = Vec4{0.0f, 0.0f, 0.0f, 0.0f};
+                if (v.x != 0.0f || v.y != 0.0f || v.z != 0.0f || v.w != 0.0f) live_mask |= 1u << i;
+            }
+            adjoint[(size_t)i * stride + idx] = make_float4(v.x, v.y, v.z, v.w);
         };
         if constexpr (kRegs) union_backward_regs<NMAX>(ur, wbar, store, N, u, dbar_adj, gbar);
         else union_backward(load, wbar, store, N, T, u, dbar_adj, gbar);
+    }
+    if (rays.live != nullptr) {
+        // mark the backward field kernel's warp tiles (2^tile_shift consecutive samples of the flat [R*M] index) that
+        // received a non-zero adjoint; every writer stores the same byte, so no atomics are needed
+        const int tile = valid ? (int)(idx >> tile_shift) : -1 - lane;
+        const unsigned peers = __match_any_sync(kFull, tile);
+        const bool leader = valid && lane == __ffs(peers) - 1;
+        for (int i = 0; i < N; ++i) {
+            const unsigned votes = __ballot_sync(kFull, (live_mask >> i) & 1u);
+            if (leader && (votes & peers)) rays.live[(size_t)i * tiles_per_inst + tile] = 1;
+        }
     }
 }
 
@@ -526,9 +548,16 @@ int vsrd_composite_backward(const VsrdScene* scene, const VsrdRays* rays, const 
     }
     const int grid = r.R, block = 32 * ((r.M + 31) / 32);
     cudaStream_t st = (cudaStream_t)stream;
+    int tile_shift = 0, tiles_per_inst = 0;
+    if (r.live != nullptr) {
+        const int rows = backward_mma_tile_rows();
+        if (rows < 0) return 1;
+        tile_shift = rows == 16 ? 4 : 5;
+        tiles_per_inst = (int)(((size_t)r.R * r.M + rows - 1) / rows);
+    }
 #define VSRD_LAUNCH_CB(NMAX) composite_backward_kernel<NMAX><<<grid, block, 0, st>>>( \
         s, r, params->std_deviation, params->cosine_ratio, params->epsilon, (const float4*)field, \
-        grad_labels, grad_gradients, grad_weights, l, labels, (float4*)adjoint)
+        grad_labels, grad_gradients, grad_weights, l, labels, (float4*)adjoint, tile_shift, tiles_per_inst)
     if (s.N <= 8) VSRD_LAUNCH_CB(8);
     else if (s.N <= 16) VSRD_LAUNCH_CB(16);
     else VSRD_LAUNCH_CB(32);

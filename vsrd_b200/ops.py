@@ -76,8 +76,9 @@ class RayArgs:
         self.num_intervals = self.distances.shape[1] - 1
         if self.num_intervals > _lib.MAX_INTERVALS:
             raise RuntimeError(f"vsrd_b200: at most {_lib.MAX_INTERVALS} intervals per ray, got {self.num_intervals}")
-        self.union_bound = None       # culling bound (enable_culling)
-        self.struct = VsrdRays(r, self.num_intervals, _ptr(self.origins), _ptr(self.directions), _ptr(self.distances), None, None)
+        self.union_bound = None       # culling bound and backward tile marks (enable_culling)
+        self.live_tiles = None
+        self.struct = VsrdRays(r, self.num_intervals, _ptr(self.origins), _ptr(self.directions), _ptr(self.distances), None, None, None)
 
     def enable_culling(self, scene: "SceneArgs") -> None:
         """Computes the per-sample culling bound (min box SDF over the instances, one small launch) and attaches it:
@@ -89,8 +90,14 @@ class RayArgs:
         self.union_bound = torch.empty(self.num_rays * self.num_intervals, device=dev, dtype=torch.float32)
         _lib.check(_lib.load().vsrd_union_bound(ctypes.byref(scene.struct), ctypes.byref(self.struct),
                                                 _ptr(self.union_bound), _stream()))
+        rows = _lib.load().vsrd_backward_tile_rows()
+        if rows < 1:
+            _lib.check(1)
+        tiles = (self.num_rays * self.num_intervals + rows - 1) // rows
+        self.live_tiles = torch.zeros(scene.num_instances, tiles, device=dev, dtype=torch.uint8)
         self.struct.union_bound = _ptr(self.union_bound)
         self.struct.cull_stats = _ptr(_cull_stats(dev))
+        self.struct.live_tiles = _ptr(self.live_tiles)
 
 
 # ---- instance culling -----------------------------------------------------------------
@@ -235,6 +242,8 @@ def composite_backward(scene: SceneArgs, rays: RayArgs, field, std_deviation, co
         labels = _f32(labels, "labels").reshape(r, n)
     adjoint = torch.empty_like(field)
     params = _params(std_deviation, cosine_ratio, epsilon)
+    if rays.live_tiles is not None:
+        rays.live_tiles.zero_()              # marks of an earlier backward through the same pass
     _lib.check(_lib.load().vsrd_composite_backward(
         ctypes.byref(scene.struct), ctypes.byref(rays.struct), ctypes.byref(params), _ptr(field),
         _ptr(grad_labels), _ptr(grad_gradients), _ptr(grad_weights),
