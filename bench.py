@@ -570,6 +570,8 @@ def run_native(args):
         # algorithmic contraction flops of the backward field kernel: 4F per (fine sample, instance)
         # (reverse-over-reverse beyond the 2F forward; the kernel's own 2F recompute earns no credit)
         bwd_flops = 4 * F_MLP * args.instances * args.rays * m_fine
+        if visited_tiles:      # executed = nominal * (1 - culled fraction), counted in-kernel
+            bwd_flops = int(bwd_flops * (1.0 - culled_tiles / visited_tiles))
         achieved = bwd_flops / (bwd_ms * 1e-3) / 1e12 if bwd_ms == bwd_ms and bwd_ms > 0 else None
         hbm_bytes = 80 * args.instances * args.rays * m_fine   # 80*N B per fine ray-sample (3-kernel split)
         line = {
