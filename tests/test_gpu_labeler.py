@@ -174,3 +174,28 @@ def test_two_gpu_sequence_labeling_gathers_every_frame():
     assert proc.returncode == 0, proc.stderr[-2000:]
     line = json.loads([l for l in proc.stdout.splitlines() if l.startswith("{")][-1])
     assert line["n_gpus"] == 2 and line["gathered_frames"] == 5 and line["all_frames_gathered_and_finite"]
+
+
+def test_checkpoint_round_trip_and_reference_format():
+    """checkpoint() follows scripts/main.py:1109-1121 (`models` -> state dicts under the config's names, loadable into a
+    fresh BoxParameters3D as tools/kitti_360/make_predictions.py:50-58 does); load_checkpoint() resumes bit-for-bit."""
+    import vsrd
+    frame, init = _frame(seed=5)
+    kw = dict(num_steps=20, warmup_steps=6, num_rays=128, num_samples=16, seed=2, use_graph=False)
+    a, _ = _labeler(frame, init, **kw)
+    for _ in range(10):
+        a.step()
+    ckpt = a.checkpoint()
+    assert ckpt["step"] == 9 and set(ckpt["models"]) == {"detector", "hyper_distance_field", "positional_encoder"}
+    det = vsrd.models.BoxParameters3D(*ckpt["models"]["detector"]["embeddings"].shape)
+    det.load_state_dict(ckpt["models"]["detector"])
+    with torch.no_grad():
+        assert torch.allclose(det()["boxes_3d"][0], a.boxes()["boxes_3d"].cpu(), atol=1e-6)
+    b, _ = _labeler(frame, init, **kw)
+    b.load_checkpoint(ckpt)
+    assert b.step_index == 10
+    for _ in range(10):
+        a.step()
+        b.step()
+    assert torch.equal(a.boxes()["boxes_3d"], b.boxes()["boxes_3d"])
+    assert torch.equal(a.arena.params, b.arena.params)

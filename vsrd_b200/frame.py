@@ -343,6 +343,44 @@ class FrameLabeler:
         return dict(boxes_3d=world["boxes_3d"][0], locations=world["locations"][0],
                     dimensions=world["dimensions"][0], orientations=world["orientations"][0])
 
+    # ---- checkpoints (scripts/main.py:1109-1121, 134-136) ----------------------------------------------
+    def checkpoint(self) -> Dict:
+        """What the reference saves as `step_{step}.pt` for a frame: `step`, `models` = state dicts under the config's
+        model names (`detector` is what tools/kitti_360/make_predictions.py:50-58 loads to produce the pseudo labels),
+        plus the Adam moments so `load_checkpoint` resumes bit-for-bit.  Host tensors; waits for the labeler's stream."""
+        import vsrd
+        self.stream.synchronize()
+        cpu = lambda sd: {k: v.detach().cpu().clone() for k, v in sd.items()}
+        ckpt = dict(step=self.step_index - 1,
+                    models=dict(detector=cpu(self.detector.state_dict()),
+                                hyper_distance_field=cpu(self.hyper.state_dict()),
+                                positional_encoder=cpu(vsrd.models.SinusoidalEncoder(num_frequencies=8).state_dict())),
+                    metrics=dict(losses=self.losses.detach().cpu().clone()))
+        if self.arena is not None:
+            ckpt["optimizer"] = dict(kind="vsrd_b200.arena", exp_avg=self.arena.exp_avg.cpu(), exp_avg_sq=self.arena.exp_avg_sq.cpu())
+        else:
+            ckpt["optimizer"] = self.optimizer.state_dict()
+        return ckpt
+
+    def load_checkpoint(self, ckpt: Dict) -> None:
+        """Restore parameters, optimiser moments and the schedule position from `checkpoint()` (or, parameters only,
+        from a checkpoint written by the reference's main.py)."""
+        with torch.cuda.stream(self.stream), torch.no_grad():
+            for module, key in ((self.detector, "detector"), (self.hyper, "hyper_distance_field")):
+                state = ckpt["models"].get(key)
+                if state is None:
+                    continue
+                own = module.state_dict()
+                for name, value in state.items():
+                    own[name].copy_(torch.as_tensor(value).reshape(own[name].shape))     # in place: parameters stay in the arena
+            opt = ckpt.get("optimizer")
+            if self.arena is not None and isinstance(opt, dict) and opt.get("kind") == "vsrd_b200.arena":
+                self.arena.exp_avg.copy_(opt["exp_avg"])
+                self.arena.exp_avg_sq.copy_(opt["exp_avg_sq"])
+            elif self.arena is None and isinstance(opt, dict) and "state" in opt:
+                self.optimizer.load_state_dict(opt)
+        self.seek(int(ckpt["step"]) + 1)
+
     def run(self) -> Dict[str, torch.Tensor]:
         if self.rays != "draw" or self.inject_samples:
             raise RuntimeError("vsrd_b200: run() draws its own rays and samples; drive step(...) yourself when injecting them")
