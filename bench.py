@@ -244,7 +244,7 @@ def make_models(args, frame, rank, device):
     return detector.to(device), hyper.to(device), encoder.to(device)
 
 
-def main_style_step(vsrd, model_tuple, config, rays_o, rays_d, targets, sched, num_instances):
+def main_style_step(vsrd, model_tuple, config, rays_o, rays_d, targets, sched, num_instances, return_outputs=False):
     """The renderer part of one scripts/main.py step, written against the drop-in API exactly as the
     script composes it (closures of main.py:433-523, 530-578, 629-687)."""
     import torch.nn as nn
@@ -308,10 +308,11 @@ def main_style_step(vsrd, model_tuple, config, rays_o, rays_d, targets, sched, n
                   sdf_std_deviation=sched["std_deviation"], cosine_ratio=sched["cosine_ratio"])
     with torch.no_grad():
         *_, sampled_distances, sampled_weights = render(**kwargs)
-    labels, gradients, _, _ = render(**kwargs, sampled_distances=sampled_distances, sampled_weights=sampled_weights)
+    labels, gradients, fine_distances, _ = render(**kwargs, sampled_distances=sampled_distances, sampled_weights=sampled_weights)
     silhouette = nn.functional.binary_cross_entropy(labels.clamp(1.0e-6, 1.0 - 1.0e-6), targets, reduction="none").mean()
     eikonal = nn.functional.mse_loss(torch.norm(gradients, dim=-1), gradients.new_ones(*gradients.shape[:-1]))
-    return silhouette + 0.01 * eikonal
+    loss = silhouette + 0.01 * eikonal
+    return (loss, labels, gradients, fine_distances) if return_outputs else loss
 
 
 def run_native(args):
