@@ -56,7 +56,7 @@ def parse_args():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--cpu-sample-rays", type=int, default=250)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
-    ap.add_argument("--frames", type=int, default=2, help="whole frames labelled (in flight together) for frames/hour; 0 = skip")
+    ap.add_argument("--frames", type=int, default=4, help="whole frames labelled (in flight together) for frames/hour; 0 = skip")
     ap.add_argument("--frame-steps", type=int, default=3000)
     ap.add_argument("--schedule-frac", type=float, default=0.5,
                     help="operating point of the device-resident leg on the annealing schedule (0.5 = step 1500 of 3000)")
