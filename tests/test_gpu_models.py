@@ -13,6 +13,15 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
+@pytest.fixture(autouse=True)
+def plain_torch_modules():
+    """In this file the nn.Modules are the yardstick: run them as plain PyTorch ops, not through the model kernels."""
+    from vsrd_b200 import functional
+    functional.set_fused_modules(False)
+    yield
+    functional.set_fused_modules(True)
+
+
 def _rel(a, b):
     return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
 
@@ -210,3 +219,43 @@ def test_fused_labeler_step_equals_autograd_step(use_graph):
         moved_any |= travel > 0.0
         assert float((va - vb).norm()) <= 0.25 * travel + 1e-6, (ka, float((va - vb).norm()), travel)
     assert moved_any
+
+
+@pytest.mark.parametrize("n", [1, 8, 32])
+def test_modules_under_autograd_use_the_kernels_and_match_plain_torch(n):
+    """`vsrd.models.*` on CUDA call the model kernels through autograd Functions (what an unchanged scripts/main.py
+    gets): outputs and every parameter gradient against the same modules run as plain PyTorch ops."""
+    from vsrd_b200 import functional
+    detector, hyper = _models(n, seed=9)
+    gen = torch.Generator(device=DEV).manual_seed(1)
+    cot = dict(boxes_3d=torch.randn(1, n, 8, 3, device=DEV, generator=gen), locations=torch.randn(1, n, 3, device=DEV, generator=gen),
+               dimensions=torch.randn(1, n, 3, device=DEV, generator=gen), orientations=torch.randn(1, n, 3, 3, device=DEV, generator=gen))
+    gw = torch.randn(1, n, 1617, device=DEV, generator=gen)
+    params = [detector.locations, detector.dimensions, detector.orientations, detector.embeddings, *hyper.parameters()]
+    results = []
+    for fused in (True, False):
+        functional.set_fused_modules(fused)
+        world = detector()
+        weights = hyper(world["embeddings"])
+        scalar = sum((world[k] * cot[k]).sum() for k in cot) + (weights * gw).sum()
+        grads = torch.autograd.grad(scalar, params)
+        results.append((world, weights, grads))
+    (wa, ha, ga), (wb, hb, gb) = results
+    assert ha.grad_fn is not None and "Hypernetwork" in type(ha.grad_fn).__name__
+    assert "DecodeBoxes" in type(wa["boxes_3d"].grad_fn).__name__
+    for k in cot:
+        assert torch.allclose(wa[k], wb[k], atol=2e-5, rtol=1e-6), k
+    assert torch.allclose(ha, hb, atol=2e-5, rtol=1e-4)
+    for p, a, b in zip(params, ga, gb):
+        assert _rel(a, b) < 2e-4, (tuple(p.shape), _rel(a, b))
+
+
+def test_modules_fall_back_to_plain_torch_for_other_architectures():
+    """A hypernetwork the kernels are not compiled for (other widths) still runs — as the nn.Sequential it is."""
+    import vsrd
+    from vsrd_b200 import functional
+    functional.set_fused_modules(True)
+    hyper = vsrd.models.HyperDistanceField(in_channels=48, out_channels_list=[16] * 4, hyper_in_channels=64,
+                                           hyper_out_channels_list=[128] * 2).to(DEV)
+    out = hyper(torch.rand(1, 3, 64, device=DEV))
+    assert out.shape == (1, 3, 1617) and "Hypernetwork" not in type(out.grad_fn).__name__

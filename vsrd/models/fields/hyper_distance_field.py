@@ -51,4 +51,11 @@ class HyperDistanceField(nn.Module):
         return h
 
     def forward(self, embeddings):
+        if embeddings.is_cuda:
+            # the configs/kitti_360 architecture runs as 5 launches (6 backward) of csrc/vsrd_model.cu under autograd;
+            # any other architecture / batch shape is plain nn.Sequential on the GPU
+            from vsrd_b200 import functional
+            weights = functional.hypernetwork(self, embeddings) if functional.fused_modules() else None
+            if weights is not None:
+                return weights
         return self.hypernetwork(embeddings)

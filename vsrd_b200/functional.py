@@ -159,3 +159,150 @@ def render_step(locations, rotations, half_extents, mlp_weights, ray_positions, 
     return fused_render_loss(locations, rotations, half_extents, mlp_weights, ray_positions, ray_directions,
                              fine, targets, silhouette_weight=silhouette_weight,
                              eikonal_weight=eikonal_weight, **kw)
+
+
+# ---- models under autograd (a3 / a4): the nn.Modules of `vsrd.models` call these on CUDA parameters -----------------
+_fused_modules = True
+
+
+def set_fused_modules(enabled: bool) -> None:
+    """`vsrd.models.BoxParameters3D` / `HyperDistanceField` on CUDA run through the model kernels (default) or as plain
+    PyTorch ops (the reference's own formulation; the yardstick of tests/test_gpu_models.py)."""
+    global _fused_modules
+    _fused_modules = bool(enabled)
+
+
+def fused_modules() -> bool:
+    return _fused_modules
+
+
+def _hyper_layers(module):
+    """[(linear, layer_norm or None)] of a HyperDistanceField.hypernetwork the kernels can run, else None."""
+    from . import _lib
+    blocks = list(module.hypernetwork)
+    if not 2 <= len(blocks) <= _lib.HYPER_MAX_LAYERS:
+        return None
+    layers = []
+    for index, block in enumerate(blocks):
+        linear = block[0]
+        norm = block[1] if len(block) > 1 else None
+        last = index == len(blocks) - 1
+        ok = (isinstance(linear, torch.nn.Linear) and hasattr(linear, "weight_v") and hasattr(linear, "weight_g")
+              and linear.in_features == _lib.HYPER_WIDTH and linear.bias is not None
+              and (last or (isinstance(norm, torch.nn.LayerNorm) and linear.out_features == _lib.HYPER_WIDTH
+                            and norm.elementwise_affine and len(block) == 3
+                            and isinstance(block[2], torch.nn.GELU) and getattr(block[2], "approximate", "none") == "none"))
+              and (not last or len(block) == 1)
+              and linear.weight_v.dtype == torch.float32)
+        if not ok:
+            return None
+        layers.append((linear, norm))
+    return layers
+
+
+def _hyper_tables(tensors, grads=None):
+    """VsrdHyperNet (and VsrdHyperNetGrads) over per-layer tuples (weight_v, weight_g, bias, ln_weight, ln_bias)."""
+    from . import _lib
+    net = _lib.VsrdHyperNet()
+    net.num_layers = len(tensors)
+    table = None
+    if grads is not None:
+        table = _lib.VsrdHyperNetGrads()
+        table.num_layers = len(tensors)
+    for l, (v, g, b, lw, lb) in enumerate(tensors):
+        L = net.layers[l]
+        L.weight_v, L.weight_g, L.bias = v.data_ptr(), g.data_ptr(), b.data_ptr()
+        L.in_features, L.out_features = int(v.shape[1]), int(v.shape[0])
+        if lw is not None:
+            L.ln_weight, L.ln_bias = lw.data_ptr(), lb.data_ptr()
+        if table is not None:
+            gv, gg, gb, glw, glb = grads[l]
+            G = table.layers[l]
+            G.weight_v, G.weight_g, G.bias = gv.data_ptr(), gg.data_ptr(), gb.data_ptr()
+            if glw is not None:
+                G.ln_weight, G.ln_bias = glw.data_ptr(), glb.data_ptr()
+    return net, table
+
+
+class _Hypernetwork(torch.autograd.Function):
+    """HyperDistanceField.forward (hyper_distance_field.py:75-77) as 5 launches, its backward as 6 (csrc/vsrd_model.cu),
+    instead of ~110 ATen launches.  Inputs: embeddings [..., 256], then per layer weight_v, weight_g, bias[, ln.weight, ln.bias]."""
+
+    @staticmethod
+    def forward(ctx, embeddings, has_norm, *flat):
+        tensors, k = [], 0
+        for norm in has_norm:
+            v, g, b = flat[k], flat[k + 1], flat[k + 2]
+            lw, lb = (flat[k + 3], flat[k + 4]) if norm else (None, None)
+            k += 5 if norm else 3
+            tensors.append(tuple(None if t is None else t.detach().contiguous() for t in (v, g, b, lw, lb)))
+        emb = embeddings.detach().contiguous().reshape(-1, embeddings.shape[-1])
+        net, _ = _hyper_tables(tensors)
+        weights, activations = ops.hyper_forward(net, emb)
+        ctx.tensors, ctx.has_norm, ctx.emb, ctx.activations = tensors, has_norm, emb, activations
+        ctx.lead = embeddings.shape[:-1]
+        return weights.reshape(*ctx.lead, weights.shape[-1])
+
+    @staticmethod
+    def backward(ctx, grad_weights):
+        grads = [tuple(None if t is None else torch.empty_like(t) for t in layer) for layer in ctx.tensors]
+        net, table = _hyper_tables(ctx.tensors, grads)
+        g_emb = torch.empty_like(ctx.emb)
+        ops.hyper_backward(net, table, ctx.emb, ctx.activations, grad_weights.contiguous().reshape(ctx.emb.shape[0], -1), g_emb)
+        flat = []
+        for norm, (gv, gg, gb, glw, glb) in zip(ctx.has_norm, grads):
+            flat += [gv, gg, gb] + ([glw, glb] if norm else [])
+        return (g_emb.reshape(*ctx.lead, g_emb.shape[-1]), None, *flat)
+
+
+def hypernetwork(module, embeddings):
+    """`module.hypernetwork(embeddings)` through the kernels, or None when the module / input is not what they are
+    compiled for (other widths, more than 32 embedding rows, non-fp32): the caller then runs the nn.Sequential."""
+    from . import _lib
+    layers = _hyper_layers(module)
+    rows = embeddings.numel() // max(1, embeddings.shape[-1])
+    if (layers is None or embeddings.dtype != torch.float32 or embeddings.shape[-1] != _lib.HYPER_WIDTH
+            or not 1 <= rows <= _lib.MAX_INSTANCES):
+        return None
+    flat, has_norm = [], []
+    for linear, norm in layers:
+        flat += [linear.weight_v, linear.weight_g, linear.bias]
+        has_norm.append(norm is not None)
+        if norm is not None:
+            flat += [norm.weight, norm.bias]
+    return _Hypernetwork.apply(embeddings, tuple(has_norm), *flat)
+
+
+class _DecodeBoxes(torch.autograd.Function):
+    """BoxParameters3D.forward (box_parameters.py:124-146) and its backward as one launch each."""
+
+    @staticmethod
+    def forward(ctx, raw_locations, raw_dimensions, raw_orientations, ranges):
+        lead = raw_locations.shape[:-1]
+        raw = [t.detach().contiguous().reshape(-1, t.shape[-1]) for t in (raw_locations, raw_dimensions, raw_orientations)]
+        loc, dim, rot, boxes = ops.decode_boxes(ranges, *raw)
+        ctx.raw, ctx.ranges, ctx.lead, ctx.decoded = raw, ranges, lead, (dim, rot)
+        return loc.reshape(*lead, 3), dim.reshape(*lead, 3), rot.reshape(*lead, 3, 3), boxes.reshape(*lead, 8, 3)
+
+    @staticmethod
+    def backward(ctx, g_loc, g_dim, g_rot, g_boxes):
+        n = ctx.raw[0].shape[0]
+        dev = ctx.raw[0].device
+        zeros = lambda *shape: torch.zeros(*shape, device=dev, dtype=torch.float32)
+        g_loc = zeros(n, 3) if g_loc is None else g_loc.contiguous().reshape(n, 3)
+        g_dim = zeros(n, 3) if g_dim is None else g_dim.contiguous().reshape(n, 3)
+        g_rot = zeros(n, 9) if g_rot is None else g_rot.contiguous().reshape(n, 9)
+        pair = None
+        if g_boxes is not None:
+            pair = zeros(2, n, 24)
+            pair[0].copy_(g_boxes.reshape(n, 24))
+        out = [torch.empty_like(t) for t in ctx.raw]
+        dim, rot = ctx.decoded
+        ops.decode_boxes_backward(ctx.ranges, *ctx.raw, dim, rot, g_loc, g_dim, g_rot, pair, 1.0, 0.0, *out)
+        return out[0].reshape(*ctx.lead, 3), out[1].reshape(*ctx.lead, 3), out[2].reshape(*ctx.lead, 2), None
+
+
+def decode_boxes(raw_locations, raw_dimensions, raw_orientations, ranges):
+    """Differentiable BoxParameters3D decode on CUDA tensors; `ranges` is a `_lib.VsrdBoxRanges`.
+    Returns (locations [...,3], half extents [...,3], rotations [...,3,3], corners [...,8,3])."""
+    return _DecodeBoxes.apply(raw_locations, raw_dimensions, raw_orientations, ranges)
