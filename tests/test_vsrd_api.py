@@ -186,3 +186,23 @@ def test_box_3d_iou_and_utils():
                                     globals())
     assert made.dtype == torch.float64 and made.shape == (2,)
     assert torch.equal(vsrd.operations.expand_to_4x4(torch.ones(2, 3, 3))[0, 3], torch.tensor([0.0, 0.0, 0.0, 1.0]))
+
+
+def test_gather_rows_reviews_the_base_tensor_instead_of_stacking():
+    """main.py iterates `world_outputs.locations[0]` etc.; the matcher must hand the kernels the base tensor (same
+    values, same gradients) and fall back to torch.stack for anything else."""
+    from vsrd.rendering.renderers import _gather_rows
+    base = torch.rand(1, 5, 3, requires_grad=True)
+    rows = list(base[0] * 1.0)                       # non-leaf base, unbind views — as `detector()` outputs are
+    got = _gather_rows(rows)
+    assert got.shape == (5, 3) and torch.equal(got, torch.stack(rows))
+    assert got._base is rows[0]._base or got is rows[0]._base          # a view, not a copy
+    (got * torch.arange(15.0).reshape(5, 3)).sum().backward()
+    assert torch.equal(base.grad[0], torch.arange(15.0).reshape(5, 3))
+    # not consecutive rows of one tensor: plain stack
+    other = [torch.rand(3) for _ in range(4)]
+    assert torch.equal(_gather_rows(other), torch.stack(other))
+    rev = list(reversed(list(torch.rand(4, 3))))
+    assert torch.equal(_gather_rows(rev), torch.stack(rev))
+    part = list(torch.rand(6, 3))[:4]                # a prefix of a larger tensor
+    assert torch.equal(_gather_rows(part), torch.stack(part))

@@ -88,6 +88,21 @@ def _match_instance(field, index):
     return location, rotation, comp["distance_field"].dimension, partial.args[0], scale, inst.get("num_instances")
 
 
+def _gather_rows(tensors):
+    """`torch.stack(tensors)` — but main.py obtains its per-instance tensors by iterating `world_outputs.locations[0]`
+    etc. (main.py:530-578), i.e. they are consecutive row views of ONE tensor.  Re-viewing that base instead of stacking
+    N selects keeps 3 N autograd nodes (and their zero-fill + copy launches in the backward) out of every step."""
+    first = tensors[0]
+    base = getattr(first, "_base", None)
+    rows = first.numel()
+    if (base is not None and rows > 0 and base.is_contiguous() and base.numel() == rows * len(tensors)
+            and base.requires_grad == first.requires_grad      # a base outside the autograd graph must not replace rows inside it
+            and all(t._base is base and t.is_contiguous() and t.shape == first.shape
+                    and t.storage_offset() == base.storage_offset() + i * rows for i, t in enumerate(tensors))):
+        return base.reshape(len(tensors), *first.shape)
+    return torch.stack(list(tensors), dim=0)
+
+
 def match_union_field(distance_field) -> UnionField:
     """Recover the scene parameters from the closure scripts/main.py hands to the renderer."""
     if isinstance(distance_field, UnionField):
@@ -108,10 +123,10 @@ def match_union_field(distance_field) -> UnionField:
     _expect(all(has_w) or not any(has_w), "mixed box-only / residual instances")
     scale = next((s for s in scales if s is not None), 100.0)
     return UnionField(
-        locations=torch.stack(list(locs), dim=0),
-        rotations=torch.stack(list(rots), dim=0),
-        half_extents=torch.stack(list(dims), dim=0),
-        mlp_weights=torch.stack(list(ws), dim=0) if all(has_w) else None,
+        locations=_gather_rows(locs),
+        rotations=_gather_rows(rots),
+        half_extents=_gather_rows(dims),
+        mlp_weights=_gather_rows(ws) if all(has_w) else None,
         temperature=float(top["temperature"]),
         scale=scale,
         returns_features=returns_features,

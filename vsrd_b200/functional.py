@@ -238,10 +238,11 @@ class _Hypernetwork(torch.autograd.Function):
             tensors.append(tuple(None if t is None else t.detach().contiguous() for t in (v, g, b, lw, lb)))
         emb = embeddings.detach().contiguous().reshape(-1, embeddings.shape[-1])
         net, _ = _hyper_tables(tensors)
-        weights, activations = ops.hyper_forward(net, emb)
-        ctx.tensors, ctx.has_norm, ctx.emb, ctx.activations = tensors, has_norm, emb, activations
         ctx.lead = embeddings.shape[:-1]
-        return weights.reshape(*ctx.lead, weights.shape[-1])
+        out = torch.empty(*ctx.lead, int(tensors[-1][0].shape[0]), device=emb.device, dtype=torch.float32)   # final shape, see _DecodeBoxes
+        _, activations = ops.hyper_forward(net, emb, mlp_weights=out)
+        ctx.tensors, ctx.has_norm, ctx.emb, ctx.activations = tensors, has_norm, emb, activations
+        return out
 
     @staticmethod
     def backward(ctx, grad_weights):
@@ -280,9 +281,11 @@ class _DecodeBoxes(torch.autograd.Function):
     def forward(ctx, raw_locations, raw_dimensions, raw_orientations, ranges):
         lead = raw_locations.shape[:-1]
         raw = [t.detach().contiguous().reshape(-1, t.shape[-1]) for t in (raw_locations, raw_dimensions, raw_orientations)]
-        loc, dim, rot, boxes = ops.decode_boxes(ranges, *raw)
+        # outputs are allocated in their final shape: a re-viewed output would carry a `_base` outside the autograd graph,
+        # which the renderer's closure matcher (vsrd.rendering.renderers._gather_rows) relies on
+        loc, dim, rot, boxes = ops.decode_boxes(ranges, *raw, lead=lead)
         ctx.raw, ctx.ranges, ctx.lead, ctx.decoded = raw, ranges, lead, (dim, rot)
-        return loc.reshape(*lead, 3), dim.reshape(*lead, 3), rot.reshape(*lead, 3, 3), boxes.reshape(*lead, 8, 3)
+        return loc, dim, rot, boxes
 
     @staticmethod
     def backward(ctx, g_loc, g_dim, g_rot, g_boxes):

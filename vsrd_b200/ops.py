@@ -475,13 +475,15 @@ def hyper_backward(net, grads, embeddings: torch.Tensor, activations: torch.Tens
                                                _ptr(gw), _ptr(grad_embeddings), _ptr(scratch), _stream()))
 
 
-def decode_boxes(ranges, raw_locations, raw_dimensions, raw_orientations):
-    """BoxParameters3D.forward on raw [N,3], [N,3], [N,2] -> (locations, half_extents, rotations [N,3,3], boxes_3d [N,8,3])."""
+def decode_boxes(ranges, raw_locations, raw_dimensions, raw_orientations, lead=None):
+    """BoxParameters3D.forward on raw [N,3], [N,3], [N,2] -> (locations, half_extents, rotations [N,3,3], boxes_3d [N,8,3]).
+    `lead`: leading shape of the outputs (default (N,)); they are allocated in that shape, not re-viewed."""
     loc = _f32(raw_locations, "raw_locations").reshape(-1, 3)
     n, dev = loc.shape[0], loc.device
     dim = _f32(raw_dimensions, "raw_dimensions").reshape(n, 3)
     ori = _f32(raw_orientations, "raw_orientations").reshape(n, 2)
-    out = [torch.empty(n, *s, device=dev, dtype=torch.float32) for s in ((3,), (3,), (3, 3), (8, 3))]
+    lead = (n,) if lead is None else tuple(lead)
+    out = [torch.empty(*lead, *s, device=dev, dtype=torch.float32) for s in ((3,), (3,), (3, 3), (8, 3))]
     _lib.check(_lib.load().vsrd_decode_boxes(ctypes.byref(ranges), _ptr(loc), _ptr(dim), _ptr(ori), n,
                                              *[_ptr(t) for t in out], _stream()))
     return tuple(out)
