@@ -607,6 +607,17 @@ def run_native(args):
                          "traffic": (26452480 + 1280) if (args.rays, args.samples, args.instances) == (1000, 100, 8) else None,
                          "traffic_unit": "bytes per launch (ncu --set full, profiles/r01_v8_ncu_summary.txt)",
                          "peak_source": f"{sms} SMs x 128 lanes x 2 x sm_max_mhz {sm_max:.0f} (MEASURED_PEAKS.json clock)",
+                         "bound_note": "issue-bound FP32 work between 3xTF32 mma.sync contractions: DRAM traffic is one pass over "
+                                       "the adjoint buffer (26 MB per launch, 0.5 % of the HBM roofline) and the tensor pipe is "
+                                       "~30 % busy, so the kernel is rated against the FP32 FMA peak (DESIGN.md section 3)",
+                         "forward_fine": {"kernel": "field_forward_mma_kernel<2>", "kernel_ms": per_kernel.get("field_forward_fine"),
+                                          "achieved": (2 * F_MLP * args.instances * args.rays * m_fine
+                                                       / (per_kernel["field_forward_fine"] * 1e-3) / 1e12)
+                                          if per_kernel.get("field_forward_fine") else None,
+                                          "frac": (2 * F_MLP * args.instances * args.rays * m_fine
+                                                   / (per_kernel["field_forward_fine"] * 1e-3) / 1e12 / fma_peak_tflops)
+                                          if per_kernel.get("field_forward_fine") else None,
+                                          "note": "2F credited per (sample, instance); includes the 5 us culling-bound launch"},
                          "kernel_ms": bwd_ms, "algorithmic_flops_per_launch": bwd_flops,
                          "algorithmic_hbm_bytes_per_step": hbm_bytes,
                          "hbm_peak_gbs": peaks.get("hbm_gbs")},
