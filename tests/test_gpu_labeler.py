@@ -199,3 +199,38 @@ def test_checkpoint_round_trip_and_reference_format():
         b.step()
     assert torch.equal(a.boxes()["boxes_3d"], b.boxes()["boxes_3d"])
     assert torch.equal(a.arena.params, b.arena.params)
+
+
+def test_culling_does_not_change_the_optimised_boxes():
+    """A whole (shortened) schedule, temperature annealed 1 -> 0.1, with and without instance culling on identical
+    draws.  Culling perturbs a step at the 1e-9 level (tests/test_gpu_properties.py); over hundreds of Adam steps
+    with importance resampling any rounding-level perturbation is amplified (an importance sample that lands in the
+    neighbouring bin moves a label by ~1e-2), so the two runs end centimetres apart — measured 6 cm after 450 steps;
+    switching only the backward kernel's tile size (a pure summation-order change) drifts 1.1 cm on the same run, and a
+    rerun with identical settings is bit-identical — not bit-identical to each other.  The assertion guards against anything beyond that kind of drift."""
+    from vsrd_b200 import ops, synthetic
+    from vsrd_b200.frame import FrameLabeler, synthetic_frame_inputs
+    frame = synthetic.make_frame(num_instances=6, num_views=5, seed=8)
+    raw = synthetic.perturbed_raw_parameters(frame, seed=8)
+    dev = torch.device("cuda", 0)
+    inputs = synthetic_frame_inputs(frame, dev)
+    outs, skipped = [], []
+    try:
+        for enabled in (True, False):
+            ops.set_culling(enabled)
+            ops.culling_counters(dev, reset=True)
+            lab = FrameLabeler(inputs, num_steps=450, warmup_steps=150, num_rays=512, num_samples=48, seed=3, model_seed=0,
+                               initial_parameters=dict(locations=raw[0].to(dev), dimensions=raw[1].to(dev), orientations=raw[2].to(dev)))
+            outs.append(lab.run()["boxes_3d"].cpu())
+            skipped.append(ops.culling_counters(dev))
+    finally:
+        ops.set_culling(True)
+    (culled, visited), (culled_off, _) = skipped
+    assert visited > 0 and culled > 0.05 * visited and culled_off == 0, skipped
+    moved = float((outs[1] - synthetic.gt_corners(frame)).abs().max())
+    assert torch.isfinite(outs[0]).all() and moved > 0.0
+    drift = float((outs[0] - outs[1]).abs().max())
+    ious = [_iou_3d(outs[0][i], outs[1][i]) for i in range(6)]
+    print(f"culling on/off: max corner drift {drift:.4f} m, min 3D IoU {min(ious):.4f}")
+    assert drift < 0.25, drift
+    assert min(ious) >= 0.9, ious
