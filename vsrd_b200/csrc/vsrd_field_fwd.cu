@@ -322,6 +322,9 @@ __global__ void __launch_bounds__(FwdCfg<MT>::kThreads, 1) field_forward_mma_ker
 
 // min over the instances of the BOX SDF at every sample (the culling bound, see VsrdRays::union_bound)
 __global__ void union_bound_kernel(SceneDev scene, RaysDev rays, float* __restrict__ bound) {
+    __shared__ Instance s_inst[VSRD_MAX_INSTANCES];       // 15 floats per instance, staged once per CTA
+    for (int i = threadIdx.x; i < scene.N; i += blockDim.x) load_instance(scene, i, s_inst[i]);
+    __syncthreads();
     const size_t total = (size_t)rays.R * rays.M;
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
@@ -331,10 +334,8 @@ __global__ void union_bound_kernel(SceneDev scene, RaysDev rays, float* __restri
     sample_position(rays, r, j, x);
     float lowest = INFINITY;
     for (int i = 0; i < scene.N; ++i) {
-        Instance I;
-        load_instance(scene, i, I);
         BoxEval b;
-        box_eval(x, I, b);
+        box_eval(x, s_inst[i], b);
         lowest = fminf(lowest, b.value);
     }
     bound[idx] = lowest;
