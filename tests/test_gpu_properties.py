@@ -206,16 +206,18 @@ torch.save([t.cpu() for t in g], sys.argv[1])
 
 
 def test_backward_m_tile_variants_agree(tmp_path):
-    """VSRD_BWD_MT selects 16- or 32-sample warp tiles in the backward field kernel (read once per process)."""
+    """VSRD_BWD_MT selects the backward field kernel variant (read once per process): 16-sample tiles with (3, default)
+    or without (1) tile pairing, or 32-sample tiles (2)."""
     outs = []
-    for mt in ("1", "2"):
+    for mt in ("3", "1", "2"):
         path = str(tmp_path / f"g{mt}.pt")
         env = dict(os.environ, VSRD_BWD_MT=mt)
         proc = subprocess.run([sys.executable, "-c", _BWD_SCRIPT.format(root=ROOT), path], env=env, capture_output=True, text=True, timeout=600)
         assert proc.returncode == 0, proc.stderr[-2000:]
         outs.append(torch.load(path))
-    for a, b in zip(*outs):
-        assert float((a - b).norm()) <= 1e-5 * float(b.norm()) + 1e-9, float((a - b).norm() / b.norm())
+    for other in outs[1:]:
+        for a, b in zip(outs[0], other):
+            assert float((a - b).norm()) <= 1e-5 * float(b.norm()) + 1e-9, float((a - b).norm() / b.norm())
 
 
 @pytest.mark.parametrize("n,layout,temperature,share", [(8, "street", 0.1, 0.2), (24, "parking", 0.3, 0.2)])
@@ -245,5 +247,5 @@ def test_instance_culling_is_invisible_at_the_parity_bar(F, n, layout, temperatu
     assert torch.equal(fda, fdb)                                          # identical sample placement
     assert float((la - lb).abs().max()) < 1e-9 and float((fwa - fwb).abs().max()) < 1e-9
     assert float((ga - gb).abs().max()) < 1e-6
-    for a, b in zip(gra, grb):
-        assert float((a - b).norm()) <= 1e-6 * float(b.norm()) + 1e-12, float((a - b).norm() / b.norm())
+    for a, b in zip(gra, grb):       # the live-tile list changes which warp sums which tile: fp32 summation-order noise
+        assert float((a - b).norm()) <= 5e-6 * float(b.norm()) + 1e-12, float((a - b).norm() / b.norm())

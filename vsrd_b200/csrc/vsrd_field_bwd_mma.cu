@@ -138,10 +138,14 @@ __device__ __forceinline__ void pose_terms(const float x[3], const Instance& I, 
     p.coef[2] = pi_scale;
 }
 
-template <int MT>
+// PAIR (MT = 1 only): the lane == sample phases (1 and 4) serve TWO 16-sample tiles at once, lanes 0-15 the first and
+// lanes 16-31 the second tile of a pair taken from the live list; the fragment phases (2, 3) run once per half with the
+// one-m-tile register footprint.  Without it half the lanes idle through phases 1 and 4 (~10 % of the instructions).
+template <int MT, int PAIR>
 __global__ void __launch_bounds__(BwdCfg<MT>::kThreads, 1) field_backward_mma_kernel(
         SceneDev scene, RaysDev rays, const float4* __restrict__ adjoint, float* __restrict__ partials,
         int tiles_per_inst) {
+    static_assert(PAIR == 0 || MT == 1, "tile pairs are a variant of the one-m-tile kernel");
     using Cfg = BwdCfg<MT>;
     constexpr int kWarpsB = Cfg::kWarps, kThreadsB = Cfg::kThreads, kRows = Cfg::kRows, kSlots = 2 * MT;
     constexpr int kAccFloat4 = Cfg::kAccFloat4, kAccFrags = Cfg::kAccFrags, kLayerPairs = Cfg::kLayerPairs;
@@ -215,21 +219,25 @@ __global__ void __launch_bounds__(BwdCfg<MT>::kThreads, 1) field_backward_mma_ke
             live_tiles = s_live;
             if (lane == 0 && warp == 0) { tiles_visited += (unsigned)chunk_tiles; tiles_culled += (unsigned)(chunk_tiles - live_tiles); }
         }
+        constexpr int kPerIter = PAIR ? 2 : 1;              // list entries one warp iteration consumes
 #pragma unroll 1
-        for (int k = warp; k < live_tiles; k += kWarpsB) {
-            const long long tile = chunk + (live != nullptr ? (int)s_list[k] : k);
+        for (int k = warp * kPerIter; k < live_tiles; k += kWarpsB * kPerIter) {
+            const int half = PAIR ? (lane >> 4) : 0;        // PAIR: lanes 16..31 own the second tile of the pair
+            const int entry = min(k + half, live_tiles - 1);
+            const bool has_tile = k + half < live_tiles;
+            const long long tile = chunk + (live != nullptr ? (int)s_list[entry] : entry);
             const int base = (int)(tile - (long long)inst * tiles_per_inst) * kRows;
-            const int row = lane & (kRows - 1);             // MT = 1: lanes 16..31 shadow rows 0..15 with zero adjoints
+            const int row = lane & (kRows - 1);             // MT = 1 without PAIR: lanes 16..31 shadow rows 0..15 with zero adjoints
             const int idx = min(base + row, total - 1);
-            const bool valid = lane < kRows && base + row < total;
+            const bool valid = (PAIR ? has_tile : lane < kRows) && base + row < total;
             const int r = idx / rays.M;
             const int j = idx - r * rays.M;
             // ------------------------------------------------------------ 1. lane == sample
             float4 adj = make_float4(0.0f, 0.0f, 0.0f, 0.0f);   // zero adjoints contribute exactly zero
             if (valid) adj = __ldg(adj_inst + idx);
-            if (!__any_sync(kFull, adj.x != 0.0f || adj.y != 0.0f || adj.z != 0.0f || adj.w != 0.0f)) continue;
-            f2 arow[MT][3], adrow[MT][3];                  // pairs = rows (g, g + 8) of each m-tile
-            float ddrow[kSlots];
+            const unsigned nonzero = __ballot_sync(kFull, adj.x != 0.0f || adj.y != 0.0f || adj.z != 0.0f || adj.w != 0.0f);
+            if (nonzero == 0u) continue;
+            float pe_arg[3], pe_tan[3];                     // this lane's sample: PE arguments and their tangents along v
             {
                 float x[3];
                 sample_position(rays, r, j, x);
@@ -240,16 +248,30 @@ __global__ void __launch_bounds__(BwdCfg<MT>::kThreads, 1) field_backward_mma_ke
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     const float vc = I.R[c] * adj.y + I.R[3 + c] * adj.z + I.R[6 + c] * adj.w;
+                    pe_arg[c] = kPiF * (m[c] / scene.scale);
+                    pe_tan[c] = coef[c] * vc;
+                }
+            }
+            float ga[3] = {0.0f, 0.0f, 0.0f}, gad[3] = {0.0f, 0.0f, 0.0f};     // encoding adjoints of this lane's sample
+#pragma unroll 1
+            for (int hh = 0; hh < kPerIter; ++hh) {
+            const int loff = 16 * hh;                       // lanes that hold the samples of this half
+            if (PAIR && ((nonzero >> loff) & 0xffffu) == 0u) continue;
+            f2 arow[MT][3], adrow[MT][3];                  // pairs = rows (g, g + 8) of each m-tile
+            float ddrow[kSlots];
+            {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
                     f2 v[MT];
-                    frag::lanes_to_row_pairs<MT>(kPiF * (m[c] / scene.scale), lane, v);
+                    frag::lanes_to_row_pairs<MT>(pe_arg[c], lane, v, loff);
 #pragma unroll
                     for (int mt = 0; mt < MT; ++mt) arow[mt][c] = v[mt];
-                    frag::lanes_to_row_pairs<MT>(coef[c] * vc, lane, v);
+                    frag::lanes_to_row_pairs<MT>(pe_tan[c], lane, v, loff);
 #pragma unroll
                     for (int mt = 0; mt < MT; ++mt) adrow[mt][c] = v[mt];
                 }
                 f2 v[MT];
-                frag::lanes_to_row_pairs<MT>(adj.x, lane, v);
+                frag::lanes_to_row_pairs<MT>(adj.x, lane, v, loff);
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt) { ddrow[2 * mt] = v[mt].x; ddrow[2 * mt + 1] = v[mt].y; }
             }
@@ -517,17 +539,19 @@ __global__ void __launch_bounds__(BwdCfg<MT>::kThreads, 1) field_backward_mma_ke
                 for (int n = 0; n < 7; ++n)
                     accL[(kAccL0 + n) * 32] = make_float4(D0[n][0].x, D0[n][0].y, D0[n][1].x, D0[n][1].y);
             }
+            // back to lane == sample: the lanes of this half pick up their rows' encoding adjoints
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                float va[kSlots], vd[kSlots];
+#pragma unroll
+                for (int sl = 0; sl < kSlots; ++sl) { va[sl] = abar[sl][c]; vd[sl] = adbar[sl][c]; }
+                const float a_mine = frag::row_slots_to_lanes<MT>(va, lane);
+                const float d_mine = frag::row_slots_to_lanes<MT>(vd, lane);
+                if (!PAIR || half == hh) { ga[c] = a_mine; gad[c] = d_mine; }
+            }
+            }   // halves
             // ------------------------------------------------------------ 4. lane == sample: pose
             {
-                float ga[3], gad[3];
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    float va[kSlots], vd[kSlots];
-#pragma unroll
-                    for (int sl = 0; sl < kSlots; ++sl) { va[sl] = abar[sl][c]; vd[sl] = adbar[sl][c]; }
-                    ga[c] = frag::row_slots_to_lanes<MT>(va, lane);
-                    gad[c] = frag::row_slots_to_lanes<MT>(vd, lane);
-                }
                 float x[3];
                 sample_position(rays, r, j, x);
                 const float dG[3] = {adj.y, adj.z, adj.w};
@@ -547,7 +571,7 @@ __global__ void __launch_bounds__(BwdCfg<MT>::kThreads, 1) field_backward_mma_ke
                     for (int k = 0; k < 3; ++k) pose[6 + 3 * m + k] = p.b.y[m] * p.pbar[k] + dG[m] * p.vbar[k];
                 }
                 if constexpr (Cfg::kPoseInRegs) {
-                    if (lane < kRows) {                    // shadow lanes hold copies of rows 0..15: count each sample once
+                    if (PAIR || lane < kRows) {            // without PAIR the shadow lanes hold copies of rows 0..15: count each sample once
 #pragma unroll
                         for (int m = 0; m < kNumPose; ++m) pose_reg[1 + m] += pose[m];
                     }
@@ -663,8 +687,9 @@ __global__ void reduce_segment_rows_kernel(const float* __restrict__ partials, i
 }
 
 static int g_sms = 0;
-static int g_bwd_mt = 1;       // m-tiles per warp tile: MT = 1 ships (12 warps x 168 registers: 0.782 ms vs 0.810 ms for
-                               // MT = 2, 8 warps x 255 registers, R=1000 S=100 N=8); VSRD_BWD_MT=2 selects the other variant
+static int g_bwd_mt = 3;       // VSRD_BWD_MT: 3 (ships) = one m-tile per warp pass, lane phases shared by a PAIR of tiles, 12 warps x
+                               // 168 registers: 0.738 ms; 1 = the same without pairing: 0.770 ms; 2 = two m-tiles, 8 warps x 255
+                               // registers: 0.810 ms (R=1000 S=100 N=8)
 
 static int setup() {
     if (g_sms) return 0;
@@ -672,18 +697,20 @@ static int setup() {
     if (cudaGetDevice(&dev) != cudaSuccess) return fail("vsrd_b200: no CUDA device%s");
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return fail("vsrd_b200: cudaGetDeviceProperties failed%s");
-    if (cudaFuncSetAttribute(field_backward_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(field_backward_mma_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)BwdCfg<2>::kSmemBytes) != cudaSuccess ||
-        cudaFuncSetAttribute(field_backward_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaFuncSetAttribute(field_backward_mma_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)BwdCfg<1>::kSmemBytes) != cudaSuccess ||
+        cudaFuncSetAttribute(field_backward_mma_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)BwdCfg<1>::kSmemBytes) != cudaSuccess)
         return fail("vsrd_b200: cannot reserve %s of shared memory for field_backward_mma_kernel (built for sm_100a)", "206 KB");
     const char* mt = getenv("VSRD_BWD_MT");
-    if (mt && (mt[0] == '1' || mt[0] == '2')) g_bwd_mt = mt[0] - '0';
+    if (mt && (mt[0] == '1' || mt[0] == '2' || mt[0] == '3')) g_bwd_mt = mt[0] - '0';      // 3 = one m-tile, tile pairs
     g_sms = prop.multiProcessorCount;
     return 0;
 }
 
-template <int MT>
+template <int MT, int PAIR>
 static int launch(const SceneDev& s, const RaysDev& r, const float* adjoint, float* partials,
                   float* gloc, float* grot, float* gdim, float* gW, cudaStream_t st) {
     using Cfg = BwdCfg<MT>;
@@ -692,7 +719,7 @@ static int launch(const SceneDev& s, const RaysDev& r, const float* adjoint, flo
     const long long all_tiles = (long long)s.N * tiles_per_inst;
     const long long want = (all_tiles + Cfg::kWarps - 1) / Cfg::kWarps;
     const int grid = (int)(want < g_sms ? want : g_sms);
-    field_backward_mma_kernel<MT><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(
+    field_backward_mma_kernel<MT, PAIR><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(
         s, r, (const float4*)adjoint, partials, tiles_per_inst);
     VSRD_CHECK_LAUNCH();
     const dim3 rgrid((kGradStride + 127) / 128, (unsigned)s.N);
@@ -705,7 +732,7 @@ static int launch(const SceneDev& s, const RaysDev& r, const float* adjoint, flo
 
 int backward_mma_tile_rows() {
     if (bwd5::setup()) return -1;
-    return bwd5::g_bwd_mt == 1 ? 16 : 32;
+    return bwd5::g_bwd_mt == 2 ? 32 : 16;
 }
 
 int backward_mma_partial_rows(int num_instances) {
@@ -716,8 +743,9 @@ int backward_mma_partial_rows(int num_instances) {
 int launch_field_backward_mma(const SceneDev& s, const RaysDev& r, const float* adjoint, float* partials,
                               float* gloc, float* grot, float* gdim, float* gW, cudaStream_t st) {
     if (bwd5::setup()) return 1;
-    return bwd5::g_bwd_mt == 1 ? bwd5::launch<1>(s, r, adjoint, partials, gloc, grot, gdim, gW, st)
-                               : bwd5::launch<2>(s, r, adjoint, partials, gloc, grot, gdim, gW, st);
+    if (bwd5::g_bwd_mt == 3) return bwd5::launch<1, 1>(s, r, adjoint, partials, gloc, grot, gdim, gW, st);
+    return bwd5::g_bwd_mt == 1 ? bwd5::launch<1, 0>(s, r, adjoint, partials, gloc, grot, gdim, gW, st)
+                               : bwd5::launch<2, 0>(s, r, adjoint, partials, gloc, grot, gdim, gW, st);
 }
 
 }  // namespace vsrd

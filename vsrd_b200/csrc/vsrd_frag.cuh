@@ -457,12 +457,12 @@ __device__ __forceinline__ float rows_to_lanes(const float (&v)[4], int lane) {
 // Tiles of 16 * MT rows: row r (= lane, r < 16 MT) lives in quad (r & 7) as slot (r >> 3); pairs are
 // (slot 2 mt, slot 2 mt + 1) = rows (g, g + 8) of m-tile mt.
 template <int MT>
-__device__ __forceinline__ void lanes_to_row_pairs(float x, int lane, f2 (&v)[MT]) {
+__device__ __forceinline__ void lanes_to_row_pairs(float x, int lane, f2 (&v)[MT], int lane_offset = 0) {
     const int g = lane >> 2;
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
-        v[mt].x = __shfl_sync(kFull, x, 16 * mt + g);
-        v[mt].y = __shfl_sync(kFull, x, 16 * mt + 8 + g);
+        v[mt].x = __shfl_sync(kFull, x, lane_offset + 16 * mt + g);
+        v[mt].y = __shfl_sync(kFull, x, lane_offset + 16 * mt + 8 + g);
     }
 }
 template <int MT>
