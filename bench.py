@@ -16,12 +16,18 @@ Unit of work: ray-samples = R * ((S-1) + (2S-1)) per step.
               two-pass render, loss, backward, Adam -- replayed as one CUDA graph), the step's ray batch coming
               from pinned host memory and the losses read back to the host every step.
   eager_api   (informational) the drop-in vsrd.* API composed from main.py's closures every step, no graph.
-  frames      whole frames labelled per hour (3000 steps each, rays drawn on the device, 2 frames in flight).
+  main_py     (N=1) the reference's UNMODIFIED scripts/main.py run on the drop-in package (tools/run_main.py), ms/step from
+              the script's own log timestamps: what a user of the reference gets without changing a line.
+  frames      whole frames labelled per hour through vsrd_b200.sequence.label_sequence over a cfg5 frame list
+              (N ~ Poisson(6) clipped to [1,24], 4 frames per rank, several in flight per GPU) INCLUDING the final NCCL
+              all_gather of the boxes; per-rank min / max seconds for the DistributedSampler and the balanced partition.
   roofline    dominant kernel (field backward) against the FP32-FMA peak.
-  cpu_baseline  oracle port (the reference's PyTorch algorithm) on the host cores, bounded sample.
+  cpu_baseline  the reference's own modules (staged under baseline/_ref, oracle/reference_step.py) on the host cores,
+              bounded sample; the oracle port when the staged reference is absent.  The same leg checks the device
+              leg's labels / loss of one batch against the oracle.
 
-`--impl reference` times that CPU port alone (rank 0 only under torchrun).
-Multi-GPU: frame-parallel, one frame per rank, no collective on the data path (weak scaling).
+`--impl reference` times that CPU reference alone at the full 1000 rays/step (rank 0 only under torchrun).
+Multi-GPU: frame-parallel, no collective on the data path (weak scaling).
 """
 from __future__ import annotations
 
@@ -54,9 +60,13 @@ def parse_args():
     ap.add_argument("--instances", type=int, default=8)
     ap.add_argument("--views", type=int, default=17)
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--cpu-sample-rays", type=int, default=250)
+    ap.add_argument("--cpu-sample-rays", type=int, default=0, help="rays per CPU reference step (0 = the full --rays)")
+    ap.add_argument("--cpu-baseline-steps", type=int, default=4, help="timed CPU reference steps of the cpu_baseline leg")
+    ap.add_argument("--main-py-steps", type=int, default=90, help="steps of the unmodified scripts/main.py leg (N=1; 0 = skip)")
+    ap.add_argument("--frames-per-rank", type=int, default=4)
+    ap.add_argument("--in-flight", type=int, default=4)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
-    ap.add_argument("--frames", type=int, default=4, help="whole frames labelled (in flight together) for frames/hour; 0 = skip")
+    ap.add_argument("--frames", type=int, default=1, help="0 = skip the frames/hour leg")
     ap.add_argument("--frame-steps", type=int, default=3000)
     ap.add_argument("--schedule-frac", type=float, default=0.5,
                     help="operating point of the device-resident leg on the annealing schedule (0.5 = step 1500 of 3000)")
@@ -76,15 +86,33 @@ def workload_name(args):
             f"R={args.rays} rays/step, S={args.samples}+{args.samples} samples/ray, residual MLP 48-16x4-1")
 
 
+def bench_config(args, world, graph=True):
+    """One config dict for both arms (the driver compares them)."""
+    return {"workload": workload_name(args), "l2": "flushed (256 MiB memset) between timed steps",
+            "schedule": schedule_at(args.schedule_frac), "graph": graph,
+            "parallelism": f"frame-parallel x{world}, no collective"}
+
+
 # ------------------------------------------------------------------------------------------------
-# CPU reference arm (oracle port) -- also used for cpu_baseline
+# CPU reference arm (the reference's own modules; oracle port as fallback) -- also used for cpu_baseline
 # ------------------------------------------------------------------------------------------------
+def _cpu_ray_batch(frame, num_rays, num_instances, gen, inv_proj, cam):
+    h, w = frame.image_size
+    pix = frame.draw_pixel_indices(num_rays, gen)
+    view, v, u = pix // (h * w), (pix // w) % h, pix % w
+    d = torch.einsum("rmn,rn->rm", inv_proj[view], torch.stack([u, v, torch.ones_like(u)], -1).float())
+    return cam[view], torch.nn.functional.normalize(d, dim=-1), torch.rand(num_rays, num_instances, generator=gen)
+
+
 def cpu_reference_run(args, steps, warmup, num_rays):
-    """Times the oracle (oracle/vsrd_oracle.py + frame_oracle.py: the reference's PyTorch algorithm) on the host
-    cores: detector decode + multi-view projection / matching / projection losses + hypernetwork + two-pass
-    renderer + BCE/eikonal + backward + Adam -- the same optimisation step the native e2e leg runs."""
-    from oracle import frame_oracle
-    from oracle import vsrd_oracle as oracle
+    """One optimisation step of scripts/main.py on the host cores, timed: detector decode + multi-view projection /
+    matching / projection losses + hypernetwork + two-pass renderer + BCE/eikonal + backward + Adam -- the same step
+    the native e2e leg runs, at the same mid-schedule operating point, on the same frame shape.
+
+    kind "reference": the reference's UNMODIFIED modules and main.py's own closures (oracle/reference_step.py, imported
+    from the checkout or from the copy staged under baseline/_ref).  kind "port": the oracle restatement
+    (oracle/vsrd_oracle.py + frame_oracle.py), only when no reference files are present."""
+    from oracle import ref_import
     from vsrd_b200 import synthetic
 
     threads = os.cpu_count() or 1
@@ -93,58 +121,75 @@ def cpu_reference_run(args, steps, warmup, num_rays):
     sup = synthetic.frame_supervision(frame)
     gen = torch.Generator().manual_seed(0)
     inv_proj, cam = frame.inverse_projections()
-    raw_loc, raw_dim, raw_ori = synthetic.perturbed_raw_parameters(frame, seed=0)
-    leaves = [t.clone().requires_grad_(True) for t in (raw_loc, raw_dim, raw_ori)]
-    emb = torch.rand(256, generator=gen).repeat(args.instances, 1).requires_grad_(True)
-    torch.manual_seed(0)
-    hyper = oracle.HyperNetwork()
-    optimizer = torch.optim.Adam([dict(params=[leaves[0]], lr=1e-2), dict(params=[leaves[1]], lr=1e-2),
-                                  dict(params=[leaves[2]], lr=1e-2), dict(params=[emb], lr=1e-3),
-                                  dict(params=list(hyper.parameters()), lr=1e-4)], lr=1e-2)
-    sched = schedule_at()
-    h, w = frame.image_size
+    raw = synthetic.perturbed_raw_parameters(frame, seed=0)
+    mid_step = int(round(3000 * args.schedule_frac))
+    kind = "reference" if ref_import.available() else "port"
+    if kind == "reference":
+        from oracle import reference_step
+        runner = reference_step.ReferenceStep(args.instances, frame.extrinsics, frame.intrinsics, frame.image_size,
+                                              sup.boxes_2d, sup.visible, num_steps=3000, num_samples=args.samples,
+                                              raw_parameters=raw, seed=0)
+
+        def one_step(it, o, d, targets):
+            return runner.step(mid_step + it, o, d, targets)
+    else:
+        from oracle import frame_oracle
+        from oracle import vsrd_oracle as oracle
+        leaves = [t.clone().requires_grad_(True) for t in raw]
+        emb = torch.rand(256, generator=gen).repeat(args.instances, 1).requires_grad_(True)
+        torch.manual_seed(0)
+        hyper = oracle.HyperNetwork()
+        optimizer = torch.optim.Adam([dict(params=[leaves[0]], lr=1e-2), dict(params=[leaves[1]], lr=1e-2),
+                                      dict(params=[leaves[2]], lr=1e-2), dict(params=[emb], lr=1e-3),
+                                      dict(params=list(hyper.parameters()), lr=1e-4)], lr=1e-2)
+        sched = schedule_at(args.schedule_frac)
+        h, w = frame.image_size
+
+        def one_step(it, o, d, targets):
+            optimizer.zero_grad(set_to_none=True)
+            loc, dim, rot = oracle.decode_box_parameters(*leaves)
+            _, _, iou, l1 = frame_oracle.projection_step(oracle.box_corners(loc, dim, rot), frame.extrinsics, frame.intrinsics,
+                                                         (h, w), sup.boxes_2d, sup.visible, sup.target_view)
+            scene = oracle.Scene(loc, rot, dim, hyper(emb), sched["temperature"])
+            loss, _ = oracle.render_loss(scene, o, d, targets, num_samples=args.samples, distance_range=[0.0, 100.0],
+                                         sdf_std_deviation=sched["std_deviation"], cosine_ratio=sched["cosine_ratio"])
+            loss = loss + 0.1 * iou + 1.0 * l1
+            loss.backward()
+            optimizer.step()
+            return float(loss.detach())
+
     times = []
     for it in range(warmup + steps):
-        pix = frame.draw_pixel_indices(num_rays, gen)
-        view = pix // (h * w)
-        v, u = (pix // w) % h, pix % w
-        d = torch.einsum("rmn,rn->rm", inv_proj[view], torch.stack([u, v, torch.ones_like(u)], -1).float())
-        d = torch.nn.functional.normalize(d, dim=-1)
-        o = cam[view]
-        targets = torch.rand(num_rays, args.instances, generator=gen)
+        o, d, targets = _cpu_ray_batch(frame, num_rays, args.instances, gen, inv_proj, cam)
         t0 = time.perf_counter()
-        optimizer.zero_grad(set_to_none=True)
-        loc, dim, rot = oracle.decode_box_parameters(*leaves)
-        _, _, iou, l1 = frame_oracle.projection_step(oracle.box_corners(loc, dim, rot), frame.extrinsics, frame.intrinsics,
-                                                     (h, w), sup.boxes_2d, sup.visible, sup.target_view)
-        scene = oracle.Scene(loc, rot, dim, hyper(emb), sched["temperature"])
-        loss, _ = oracle.render_loss(scene, o, d, targets, num_samples=args.samples, distance_range=[0.0, 100.0],
-                                     sdf_std_deviation=sched["std_deviation"], cosine_ratio=sched["cosine_ratio"])
-        loss = loss + 0.1 * iou + 1.0 * l1
-        loss.backward()
-        optimizer.step()
-        float(loss)
+        loss = one_step(it, o, d, targets)
         dt = time.perf_counter() - t0
+        if not math.isfinite(loss):
+            raise RuntimeError("bench.py: non-finite loss from the CPU reference")
         if it >= warmup:
             times.append(dt)
     per_step = sum(times) / len(times)
     units = num_rays * (3 * args.samples - 2)
-    return dict(value=units / per_step, ms_per_step=per_step * 1e3, cores=threads,
-                sample=f"{num_rays} of {args.rays} rays/step, same frame shape, {warmup} warm-up + {steps} timed steps")
+    what = ("unmodified reference modules + main.py closures (oracle/reference_step.py)" if kind == "reference"
+            else "oracle port (no reference files present)")
+    return dict(value=units / per_step, ms_per_step=per_step * 1e3, cores=threads, kind=kind,
+                sample=f"{num_rays} of {args.rays} rays/step (whole optimisation step, same frame shape and schedule point), "
+                       f"{warmup} warm-up + {steps} timed steps; {what}")
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    res = cpu_reference_run(args, max(1, args.steps), max(1, args.warmup), args.cpu_sample_rays)
+    num_rays = args.cpu_sample_rays or args.rays
+    res = cpu_reference_run(args, max(1, args.steps), max(1, args.warmup), num_rays)
     line = {
         "impl": "reference", "metric": "ray_samples_per_sec_fwd_bwd", "value": res["value"], "unit": "ray-samples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args), "note": "CPU oracle port of the reference's PyTorch renderer; "
-                   "each step is a bounded sample of the workload (see cpu_baseline.sample)"},
-        "cpu_baseline": {"value": res["value"], "unit": "ray-samples/s", "cores": res["cores"], "kind": "port",
+        "config": bench_config(args, args.gpus),
+        "note": "the reference's CPU implementation of the step on the host cores (see cpu_baseline.kind / sample)",
+        "cpu_baseline": {"value": res["value"], "unit": "ray-samples/s", "cores": res["cores"], "kind": res["kind"],
                          "sample": res["sample"]},
         "e2e": {"value": res["value"], "unit": "ray-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -313,6 +358,77 @@ def main_style_step(vsrd, model_tuple, config, rays_o, rays_d, targets, sched, n
     eikonal = nn.functional.mse_loss(torch.norm(gradients, dim=-1), gradients.new_ones(*gradients.shape[:-1]))
     loss = silhouette + 0.01 * eikonal
     return (loss, labels, gradients, fine_distances) if return_outputs else loss
+
+
+def oracle_check(step, frame, inv_proj, cam, pix, targets, sched, num_samples):
+    """CHECKER (cpu_baseline leg only): the device leg's labels and loss for one batch against the CPU oracle evaluated
+    on the very fine-pass sample distances the kernels placed (renderers.py:212-270 + main.py:653-687)."""
+    from oracle import vsrd_oracle as oracle
+    step.set_batch(pix, targets)
+    out = step.run_eager(backward=False)
+    torch.cuda.synchronize()
+    h, w = frame.image_size
+    p = pix.cpu()
+    view, v, u = p // (h * w), (p // w) % h, p % w
+    d = torch.nn.functional.normalize(
+        torch.einsum("rmn,rn->rm", inv_proj[view], torch.stack([u, v, torch.ones_like(u)], -1).float()), dim=-1)
+    prm = {k: t.detach().cpu() for k, t in step.params.items()}
+    scene = oracle.Scene(prm["locations"], prm["rotations"], prm["half_extents"], prm["mlp_weights"], sched["temperature"])
+    fine = out["fine_distances"].cpu()
+    keep = fine.max(dim=1).values < 1e3
+    with torch.no_grad():
+        ref = oracle.render_pass(scene.field(), cam[view][keep], d[keep], fine[keep].t()[..., None].contiguous(),
+                                 sched["std_deviation"], sched["cosine_ratio"])
+    label_err = float((out["labels"].cpu()[keep] - ref[0]).abs().max())
+    if not label_err < 1e-4:
+        raise RuntimeError(f"bench.py: device-leg labels differ from the oracle by {label_err:.3e} (> 1e-4)")
+    return dict(rays_checked=int(keep.sum()), max_label_error=label_err, tolerance=1e-4,
+                what="labels of one full-size batch of the device leg vs the CPU oracle on the kernels' own fine samples")
+
+
+def main_py_leg(args):
+    """The reference's unmodified scripts/main.py on the drop-in package, one synthetic cfg2-shaped frame, in a child
+    process (the script initialises its own process group).  ms/step from the timestamps of the script's own
+    `[Training]` log records over the residual-field phase."""
+    import datetime
+    import glob
+    import re
+    import subprocess
+    import tempfile
+    from tools import stage_reference
+    if stage_reference.reference_root() is None:
+        return {"unavailable": "scripts/main.py neither mounted nor staged under baseline/_ref"}
+    steps = args.main_py_steps
+    warm = steps // 3
+    every = max((steps - warm) // 3, 1)
+    work = tempfile.mkdtemp(prefix="vsrd_main_py_")
+    cmd = [sys.executable, os.path.join(ROOT, "tools", "run_main.py"), "--train", "--workdir", work,
+           "--config", os.path.join(ROOT, "configs", "synthetic", "vsrd", "drive_0000_synthetic", "config.json")]
+    for item in (f"datasets.train.kwargs.num_frames=1", f"datasets.train.kwargs.num_instances={args.instances}",
+                 f"datasets.train.kwargs.num_source_frames={args.views - 1}",
+                 f"optimization.num_steps={steps}", f"optimization.warmup_steps={warm}",
+                 f"volume_rendering.num_rays={args.rays}", f"volume_rendering.num_fine_samples={args.samples}",
+                 f"logging.scalar_intervals={every}", "logging.image_intervals=1000000", "logging.ckpt_intervals=1000000"):
+        cmd += ["--set", item]
+    env = dict(os.environ, RANK="0", LOCAL_RANK="0", WORLD_SIZE="1", MASTER_ADDR="127.0.0.1", MASTER_PORT="29561")
+    proc = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=900)
+    if proc.returncode != 0:
+        raise RuntimeError(f"bench.py: scripts/main.py failed on the drop-in package:\n{proc.stderr[-3000:]}")
+    log, = glob.glob(os.path.join(work, "logs", "**", "log.txt"), recursive=True)
+    stamps = {}
+    for m in re.finditer(r"INFO: (\d{4}-\d\d-\d\d \d\d:\d\d:\d\d,\d{3}): \[Training\] Rank: 0, Step: (\d+),[^\n]*runtimes", open(log).read()):
+        stamps[int(m.group(2))] = datetime.datetime.strptime(m.group(1), "%Y-%m-%d %H:%M:%S,%f")
+    residual = sorted(k for k in stamps if k >= warm + every - 1)
+    if len(residual) < 2:
+        raise RuntimeError("bench.py: too few log records from scripts/main.py")
+    a, b = residual[0], residual[-1]
+    ms = (stamps[b] - stamps[a]).total_seconds() * 1e3 / (b - a)
+    units = args.rays * (3 * args.samples - 2)
+    return {"ms_per_step": ms, "value": units / (ms * 1e-3), "unit": "ray-samples/s", "steps_timed": b - a,
+            "script_sha256": stage_reference.MAIN_PY_SHA256,
+            "what": "UNMODIFIED scripts/main.py (SHA-256 checked) via tools/run_main.py on the drop-in vsrd package: the "
+                    "script's own per-step Python (136 project_box_3d calls, scipy matching, 9 M-way multinomial, closure "
+                    "composition, autograd, torch Adam) around the fused renderer; residual-field phase"}
 
 
 def run_native(args):
@@ -523,28 +639,51 @@ def run_native(args):
     torch.cuda.synchronize()
     api_ms = a_start.elapsed_time(a_end) / api_steps
 
-    # ---------------- whole frames: FrameLabeler.run() with on-device ray draws, 2 frames in flight ----------------
+    # ---------------- whole frames: the real multi-GPU path (vsrd_b200.sequence.label_sequence) ----------------
+    # cfg5: frames with N ~ Poisson(6) clipped to [1,24] (seed = frame id), `frames_per_rank` x world of
+    # them, partitioned across the ranks, `in_flight` frames resident per GPU, ONE padded NCCL all_gather of the final
+    # boxes at the end -- all inside the clock.  Run twice: the reference's DistributedSampler partition
+    # (distributed/loader.py:6-9) and the cost-balanced one; per-rank seconds expose the load imbalance.
     frames_info = None
     if args.frames > 0:
-        torch.cuda.synchronize()
-        t_frames = time.perf_counter()
-        labelers = []
-        for f in range(args.frames):
-            fr = _syn.make_frame(args.instances, args.views, seed=1000 + rank * args.frames + f)
-            raw = _syn.perturbed_raw_parameters(fr, seed=f)
-            labelers.append(FrameLabeler(synthetic_frame_inputs(fr, device), num_steps=args.frame_steps,
-                                         warmup_steps=args.frame_steps // 3, num_rays=args.rays, num_samples=args.samples,
-                                         seed=f, initial_parameters=dict(locations=raw[0].to(device), dimensions=raw[1].to(device),
-                                                                         orientations=raw[2].to(device))))
-        for _ in range(args.frame_steps):
-            for lab in labelers:                                          # round-robin: the frames overlap on the GPU
-                lab.step()
-        boxes = [lab.boxes()["boxes_3d"].cpu() for lab in labelers]
-        torch.cuda.synchronize()
-        frame_s = time.perf_counter() - t_frames
-        if not all(bool(torch.isfinite(b).all()) for b in boxes):
-            raise RuntimeError("bench.py: non-finite boxes from the frame leg")
-        frames_info = dict(frames=args.frames, steps_per_frame=args.frame_steps, in_flight=args.frames, seconds=frame_s)
+        from vsrd_b200 import sequence
+        num_frames = args.frames_per_rank * world
+
+        def instances_of(fid):
+            g = torch.Generator().manual_seed(7919 + fid)
+            return int(torch.poisson(torch.tensor(6.0), generator=g).clamp(1, 24))
+
+        def make_labeler(fid):
+            fr = _syn.make_frame(instances_of(fid), args.views, seed=1000 + fid)
+            raw = _syn.perturbed_raw_parameters(fr, seed=fid)
+            return FrameLabeler(synthetic_frame_inputs(fr, device), num_steps=args.frame_steps,
+                                warmup_steps=args.frame_steps // 3, num_rays=args.rays, num_samples=args.samples, seed=fid,
+                                initial_parameters=dict(locations=raw[0].to(device), dimensions=raw[1].to(device),
+                                                        orientations=raw[2].to(device)))
+
+        counts = [instances_of(f) for f in range(num_frames)]
+        frames_info = dict(frames=num_frames, frames_per_rank=args.frames_per_rank, steps_per_frame=args.frame_steps,
+                           in_flight=args.in_flight, instances=counts)
+        for name, costs in (("sampler", None), ("balanced", [n + 2.0 for n in counts])):
+            barrier()
+            t0 = time.perf_counter()
+            mine = sequence.my_frames(num_frames, costs=costs, seed=0)
+            results = sequence.label_frames_in_flight(mine, make_labeler, args.frame_steps, args.in_flight)
+            torch.cuda.synchronize()
+            t_label = time.perf_counter() - t0
+            merged = sequence.gather_labels(results, device=device)          # NCCL all_gather (identity at N=1)
+            torch.cuda.synchronize()
+            t_total = time.perf_counter() - t0
+            if sorted(merged) != list(range(num_frames)) or not all(bool(torch.isfinite(b).all()) for b in merged.values()) \
+                    or any(merged[f].shape[0] != counts[f] for f in merged):
+                raise RuntimeError("bench.py: the frame leg did not gather every frame's finite boxes")
+            ts = torch.tensor([t_label, -t_label, t_total], device=device, dtype=torch.float64)
+            if world > 1:
+                torch.distributed.all_reduce(ts, op=torch.distributed.ReduceOp.MAX)
+            frames_info[name] = dict(seconds=float(ts[2]), rank_seconds_max=float(ts[0]), rank_seconds_min=-float(ts[1]),
+                                     gather_seconds=t_total - t_label,
+                                     frames_per_hour=num_frames * 3600.0 / float(ts[2]))
+        frames_info["seconds"] = frames_info["balanced"]["seconds"]
 
     # ---------------- reduce over ranks ----------------
     t = torch.tensor([dev_ms, e2e_ms, frames_info["seconds"] if frames_info else 0.0], device=device, dtype=torch.float64)
@@ -552,10 +691,11 @@ def run_native(args):
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
     dev_ms, e2e_ms = float(t[0]), float(t[1])
     if frames_info:
-        frames_info["seconds"] = float(t[2])
-        frames_info["frames_per_hour"] = world * frames_info["frames"] * 3600.0 / frames_info["seconds"]
-        frames_info["note"] = ("whole-job frames/hour incl. per-frame set-up (soft masks, CDF, models, graph capture); "
-                               "3000 steps/frame as configs/kitti_360, logging/checkpoint paths off")
+        frames_info["frames_per_hour"] = frames_info["balanced"]["frames_per_hour"]
+        frames_info["note"] = ("whole-job frames/hour through sequence.label_sequence's pieces incl. per-frame set-up (soft masks, "
+                               "CDF, models, graph capture) and the final all_gather; 3000 steps/frame as configs/kitti_360, "
+                               "logging/checkpoint paths off; headline = balanced partition, `sampler` = the reference's "
+                               "DistributedSampler partition")
 
     if rank == 0:
         peaks = {}
@@ -574,6 +714,14 @@ def run_native(args):
         if visited_tiles:      # executed = nominal * (1 - culled fraction), counted in-kernel
             bwd_flops = int(bwd_flops * (1.0 - culled_tiles / visited_tiles))
         achieved = bwd_flops / (bwd_ms * 1e-3) / 1e12 if bwd_ms == bwd_ms and bwd_ms > 0 else None
+        # kernel name + DRAM bytes per launch of the CURRENT backward kernel, written by tools/ncu_summary.py --roofline
+        # from the round's `ncu --set full` capture of this very command
+        capture = {}
+        try:
+            capture = json.load(open(os.path.join(ROOT, "profiles", "roofline_kernel.json")))
+        except Exception:
+            pass
+        same_shape = capture.get("shape") == [args.rays, args.samples, args.instances]
         hbm_bytes = 80 * args.instances * args.rays * m_fine   # 80*N B per fine ray-sample (3-kernel split)
         line = {
             "metric": "ray_samples_per_sec_fwd_bwd",
@@ -583,8 +731,7 @@ def run_native(args):
             "ms_per_step": dev_ms / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args), "l2": "flushed (256 MiB memset) between timed steps",
-                       "schedule": sched, "graph": use_graph, "parallelism": f"frame-parallel x{world}, no collective"},
+            "config": bench_config(args, world, use_graph),
             "e2e": {"value": world * units * K / (e2e_ms * 1e-3), "unit": "ray-samples/s",
                     "ms_per_step": e2e_ms / K,
                     "h2d_bytes_per_step": int(pool[0].numel() * 8 + targets[0].numel() * 4),
@@ -598,14 +745,14 @@ def run_native(args):
                                  "closures every step + autograd + Adam (no graph: Python dispatch bound)"},
             "frames": frames_info,
             "gpu_launches": SilhouetteStep.KERNELS_PER_STEP * K,
-            "roofline": {"bound": "fp32_fma", "kernel": "field_backward_kernel<residual>", "achieved": achieved,
+            "roofline": {"bound": "fp32_fma", "kernel": capture.get("kernel", "field_backward (see kernel_ms)"), "achieved": achieved,
                          "peak": fma_peak_tflops, "unit": "TFLOP/s",
                          "frac": (achieved / fma_peak_tflops) if achieved else None,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this exact shape, from the
                          # `ncu --set full` capture summarised in profiles/r01_v8_ncu_summary.txt (one pass over the
                          # 25.5 MB adjoint buffer; everything else stays in L2 / shared memory)
-                         "traffic": (26452480 + 1280) if (args.rays, args.samples, args.instances) == (1000, 100, 8) else None,
-                         "traffic_unit": "bytes per launch (ncu --set full, profiles/r01_v8_ncu_summary.txt)",
+                         "traffic": capture.get("traffic_bytes") if same_shape else None,
+                         "traffic_unit": f"dram bytes read + written per launch (ncu --set full, {capture.get('source', 'no capture')})",
                          "peak_source": f"{sms} SMs x 128 lanes x 2 x sm_max_mhz {sm_max:.0f} (MEASURED_PEAKS.json clock)",
                          "bound_note": "issue-bound FP32 work between 3xTF32 mma.sync contractions: DRAM traffic is one pass over "
                                        "the adjoint buffer (26 MB per launch, 0.5 % of the HBM roofline) and the tensor pipe is "
@@ -630,10 +777,13 @@ def run_native(args):
             "clocks": clocks.summary(),
             "loss": loss_value,
         }
+        if world == 1 and args.main_py_steps > 0:
+            line["main_py"] = main_py_leg(args)
         if world == 1 and not args.skip_cpu_baseline:
-            res = cpu_reference_run(args, steps=3, warmup=1, num_rays=args.cpu_sample_rays)
+            line["oracle_check"] = oracle_check(step, frame, inv_proj, cam, pool_dev[0], targets_dev[0], sched, args.samples)
+            res = cpu_reference_run(args, steps=args.cpu_baseline_steps, warmup=1, num_rays=args.cpu_sample_rays or args.rays)
             line["cpu_baseline"] = {"value": res["value"], "unit": "ray-samples/s", "cores": res["cores"],
-                                    "kind": "port", "sample": res["sample"], "ms_per_step": res["ms_per_step"]}
+                                    "kind": res["kind"], "sample": res["sample"], "ms_per_step": res["ms_per_step"]}
         print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()

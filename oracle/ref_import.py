@@ -21,7 +21,20 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("VSRD_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_root() -> str:
+    """The live checkout ($VSRD_REFERENCE_ROOT or /root/reference) if mounted, else the copy tools/stage_reference.py
+    staged under baseline/_ref (git-ignored; it travels to the GPU box with the snapshot)."""
+    candidates = [os.environ.get("VSRD_REFERENCE_ROOT"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")]
+    for root in candidates:
+        if root and os.path.isfile(os.path.join(root, "scripts", "main.py")):
+            return root
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 _PREFIX = "vsrd"  # the reference's own package name
 
 

@@ -86,3 +86,43 @@ def test_two_rank_gloo_label_gather(num_frames):
         assert sorted(merged) == list(range(num_frames))
         for fid, boxes in merged.items():
             assert torch.equal(boxes, _fake_boxes(fid))
+
+
+def test_balanced_partition_owns_every_frame_once_and_levels_the_load():
+    gen = torch.Generator().manual_seed(0)
+    counts = torch.poisson(torch.full((64,), 6.0), generator=gen).clamp(1, 24).tolist()   # cfg5 instance counts
+    costs = [n + 2.0 for n in counts]
+    for world in (1, 2, 4, 8):
+        owned = [sequence.partition_balanced(costs, r, world) for r in range(world)]
+        assert sorted(f for part in owned for f in part) == list(range(64))
+        loads = [sum(costs[f] for f in part) for part in owned]
+        sampler = [sum(costs[f] for f in sequence.partition_frames(64, r, world, drop_duplicates=True)) for r in range(world)]
+        assert max(loads) - min(loads) <= max(costs)                      # LPT bound
+        assert max(loads) <= max(sampler) + 1e-9                          # never worse than the sampler's stride
+    with pytest.raises(ValueError):
+        sequence.partition_balanced(costs, 2, 2)
+
+
+def test_in_flight_scheduler_runs_every_frame_to_completion():
+    class FakeLabeler:
+        live = 0
+        peak = 0
+
+        def __init__(self, fid):
+            self.fid, self.step_index = fid, 0
+            FakeLabeler.live += 1
+            FakeLabeler.peak = max(FakeLabeler.peak, FakeLabeler.live)
+
+        def step(self):
+            self.step_index += 1
+
+        def boxes(self):
+            FakeLabeler.live -= 1
+            return dict(boxes_3d=torch.full((1, 8, 3), float(self.fid)))
+
+    done = []
+    out = sequence.label_frames_in_flight([5, 2, 9, 4, 7], FakeLabeler, num_steps=3, in_flight=2,
+                                          on_done=lambda fid, lab: done.append((fid, lab.step_index)))
+    assert sorted(out) == [2, 4, 5, 7, 9] and FakeLabeler.peak == 2 and FakeLabeler.live == 0
+    assert done == [(5, 3), (2, 3), (9, 3), (4, 3), (7, 3)]
+    assert all(float(out[f]["boxes_3d"][0, 0, 0]) == f for f in out)

@@ -27,7 +27,9 @@ FILES = [
     "vsrd/models/detectors/box_parameters.py",
     "vsrd/operations/__init__.py", "vsrd/operations/geometric_operations.py", "vsrd/operations/kitti360_operations.py",
     "LICENSE",
-]
+] + [f"vsrd/modules/{name}.py" for name in (     # imported by models/encoders/tensorial_encoder.py at package import
+    "__init__", "attention", "drop_path", "grad_scale", "grid_sampler", "layer_scale", "packing_block",
+    "plane_sweep_stereo", "sinkhorn_knopp", "spatial_propagation", "squeeze_excitation", "utils")]
 # digest of the script the parity / drop-in claims are about (skmhrk1209/VSRD @ 68765a4)
 MAIN_PY_SHA256 = "45368120015307176e46484d54b3a44585a4d2db774e1aba511e0ea4f3b851f5"
 

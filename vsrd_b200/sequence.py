@@ -8,7 +8,10 @@ only exchange is a single `all_gather` of the final pseudo-label boxes at the en
 in the CPU tests).
 
     partition_frames   the frames of one rank, exactly as torch's DistributedSampler draws them
+    partition_balanced the frames of one rank under longest-processing-time-first balancing on a per-frame cost
+                       (instance count): the only scaling loss of this workload is load imbalance
     label_frames       runs a per-frame labeler over this rank's frames (skip-if-done like main.py:134-136)
+    label_frames_in_flight  the same with several frames in flight on one GPU (round-robin over their CUDA graphs)
     gather_labels      padded all_gather of (frame id, instance count, boxes [N_max,8,3]) -> dict on every rank
 """
 from __future__ import annotations
@@ -51,6 +54,45 @@ def partition_frames(num_frames: int, rank: int, world_size: int, *, seed: int =
             first_owner.setdefault(f, pos)
         mine = [f for pos, f in zip(range(rank, total, world_size), mine) if first_owner[f] == pos]
     return mine
+
+
+def partition_balanced(costs: Sequence[float], rank: int, world_size: int) -> List[int]:
+    """Longest-processing-time-first assignment: frames sorted by descending cost (ties by id) go one by one to the
+    currently least-loaded rank.  Deterministic and identical on every rank (no communication); every frame is owned
+    exactly once, so there are no wrap-around duplicates.  The per-step cost of a frame is linear in its instance
+    count (field kernels: N MLP evaluations per sample), so `costs = [N_f + c0]` is the natural model."""
+    if not 0 <= rank < world_size:
+        raise ValueError(f"rank {rank} outside world of size {world_size}")
+    loads = [0.0] * world_size
+    owned: List[List[int]] = [[] for _ in range(world_size)]
+    for fid in sorted(range(len(costs)), key=lambda f: (-float(costs[f]), f)):
+        r = min(range(world_size), key=lambda k: (loads[k], k))
+        loads[r] += float(costs[fid])
+        owned[r].append(fid)
+    return owned[rank]
+
+
+def label_frames_in_flight(frame_ids: Iterable[int], make_labeler: Callable[[int], object], num_steps: int,
+                           in_flight: int = 4, on_done: Optional[Callable[[int, object], None]] = None
+                           ) -> Dict[int, Dict[str, torch.Tensor]]:
+    """Labels this rank's frames with up to `in_flight` of them resident on the GPU at once: their per-step CUDA
+    graphs are replayed round-robin from one host thread, so one frame's launch gaps are filled by the others
+    (a single frame leaves the GPU idle ~15 % of a step).  `make_labeler(frame_id)` returns an object with
+    `.step()`, `.step_index`, `.boxes()` (vsrd_b200.frame.FrameLabeler)."""
+    results: Dict[int, Dict[str, torch.Tensor]] = {}
+    queue, active = [int(f) for f in frame_ids], []
+    while queue or active:
+        while queue and len(active) < in_flight:
+            fid = queue.pop(0)
+            active.append((fid, make_labeler(fid)))
+        for _, labeler in active:
+            labeler.step()
+        for fid, labeler in [item for item in active if item[1].step_index >= num_steps]:
+            results[fid] = dict(boxes_3d=labeler.boxes()["boxes_3d"])
+            if on_done is not None:
+                on_done(fid, labeler)
+            active.remove((fid, labeler))
+    return results
 
 
 def label_frames(frame_ids: Iterable[int], label_one: Callable[[int], Dict[str, torch.Tensor]],
@@ -105,12 +147,33 @@ def gather_labels(results: Dict[int, Dict[str, torch.Tensor]], device=None,
     return merged
 
 
-def label_sequence(num_frames: int, label_one: Callable[[int], Dict[str, torch.Tensor]], *, seed: int = 0,
-                   shuffle: bool = True, device=None) -> Dict[int, torch.Tensor]:
-    """Frame-parallel driver: partition -> label -> gather.  Call from every rank (torchrun)."""
+def my_frames(num_frames: int, *, costs: Optional[Sequence[float]] = None, seed: int = 0, shuffle: bool = True) -> List[int]:
+    """This rank's frames: the reference's DistributedSampler slice, or the balanced partition when per-frame
+    `costs` are given."""
     if dist.is_available() and dist.is_initialized():
         rank, world = dist.get_rank(), dist.get_world_size()
     else:
         rank, world = 0, 1
-    mine = partition_frames(num_frames, rank, world, seed=seed, shuffle=shuffle, drop_duplicates=True)
-    return gather_labels(label_frames(mine, label_one), device=device)
+    if costs is not None:
+        if len(costs) != num_frames:
+            raise ValueError("one cost per frame")
+        return partition_balanced(costs, rank, world)
+    return partition_frames(num_frames, rank, world, seed=seed, shuffle=shuffle, drop_duplicates=True)
+
+
+def label_sequence(num_frames: int, label_one: Optional[Callable[[int], Dict[str, torch.Tensor]]] = None, *,
+                   seed: int = 0, shuffle: bool = True, device=None, costs: Optional[Sequence[float]] = None,
+                   make_labeler: Optional[Callable[[int], object]] = None, num_steps: Optional[int] = None,
+                   in_flight: int = 4) -> Dict[int, torch.Tensor]:
+    """Frame-parallel driver: partition -> label -> gather.  Call from every rank (torchrun).  Either `label_one`
+    (one frame at a time) or `make_labeler` + `num_steps` (several frames in flight per GPU)."""
+    mine = my_frames(num_frames, costs=costs, seed=seed, shuffle=shuffle)
+    if make_labeler is not None:
+        if num_steps is None:
+            raise ValueError("make_labeler needs num_steps")
+        results = label_frames_in_flight(mine, make_labeler, num_steps, in_flight)
+    elif label_one is not None:
+        results = label_frames(mine, label_one)
+    else:
+        raise ValueError("label_sequence needs label_one or make_labeler")
+    return gather_labels(results, device=device)
