@@ -69,3 +69,119 @@ def test_main_py_composition_through_the_drop_in_api_matches_the_oracle():
         if denom > 1e-9:
             rel = float((a.detach().cpu().double().reshape(b.shape) - b).norm()) / denom
             assert rel < 5e-3, (tuple(p.shape), rel)
+
+
+def _gpu_scene(n=3, seed=5):
+    import vsrd
+    from vsrd_b200 import synthetic
+    dev = torch.device("cuda", 0)
+    frame = synthetic.make_frame(num_instances=n, num_views=2, image_size=(94, 352), seed=seed, intrinsics_scale=0.25)
+    torch.manual_seed(1)
+    detector = vsrd.models.BoxParameters3D(batch_size=1, num_instances=n)
+    raw = synthetic.perturbed_raw_parameters(frame, seed=seed)
+    with torch.no_grad():
+        detector.locations.copy_(raw[0].reshape(1, n, 3)); detector.dimensions.copy_(raw[1].reshape(1, n, 3))
+        detector.orientations.copy_(raw[2].reshape(1, n, 2))
+        detector.embeddings.copy_(torch.rand(1, n, 256))
+    hyper = vsrd.models.HyperDistanceField(in_channels=48, out_channels_list=[16] * 4, hyper_in_channels=256,
+                                           hyper_out_channels_list=[256] * 4)
+    encoder = vsrd.models.SinusoidalEncoder(num_frequencies=8)
+    models = vsrd.utils.Dict(detector=detector.to(dev), hyper_distance_field=hyper.to(dev), positional_encoder=encoder.to(dev))
+    config = vsrd.utils.Dict.apply(dict(volume_rendering=dict(distance_range=[0.0, 100.0])))
+    world = models.detector()
+    gen = torch.Generator().manual_seed(0)
+    pix = frame.draw_pixel_indices(64, gen)
+    h, w = frame.image_size
+    inv_proj, cam = frame.inverse_projections()
+    view, v, u = pix // (h * w), (pix // w) % h, pix % w
+    dirs = torch.nn.functional.normalize(
+        torch.einsum("rmn,rn->rm", inv_proj[view], torch.stack([u, v, torch.ones_like(u)], -1).float()), dim=-1)
+    return n, models, config, world, models.hyper_distance_field(world["embeddings"]), cam[view].contiguous().to(dev), dirs.to(dev)
+
+
+def test_a_lookalike_closure_is_rejected():
+    """a `residual_distance_field` with main.py's names but WITHOUT its |x| fold (main.py:437-438)
+    must not be dispatched to kernels that apply the fold: the behavioural probe catches it."""
+    import vsrd
+    from tests.test_vsrd_api import compose_like_main
+    from vsrd.rendering import UnsupportedFieldError, renderers
+    n, models, config, world, weights, origins, dirs = _gpu_scene()
+    args = (world["locations"][0], world["dimensions"][0], world["orientations"][0])
+    kwargs = dict(ray_positions=origins, ray_directions=dirs, distance_range=[0.0, 100.0], num_samples=16,
+                  sdf_std_deviation=0.5, cosine_ratio=0.5)
+    good = compose_like_main(*args, weights[0], 0.5, models, config, n)
+    with torch.no_grad():
+        vsrd.rendering.hierarchical_volumetric_rendering(distance_field=good, **kwargs)      # accepted (and cached)
+
+    import functools
+    import torch.nn as nn
+    sdfs = vsrd.rendering.sdfs
+
+    def residual_distance_field(distance_field):          # same free-variable names, different function: no |x| fold
+        def wrapper(positions):
+            positions = positions / max(config.volume_rendering.distance_range)
+            return torch.sigmoid(distance_field(models.positional_encoder(positions)) - 1.0)
+        return wrapper
+
+    def residual_composition(distance_field, residual_distance_field):
+        def wrapper(positions):
+            return distance_field(positions) + residual_distance_field(positions)
+        return wrapper
+
+    def instance_field(distance_field, instance_label):
+        def wrapper(positions):
+            distances = distance_field(positions)
+            return distances, nn.functional.one_hot(instance_label, n).expand(*distances.shape[:-1], -1)
+        return wrapper
+
+    def soft_union(distance_fields, temperature):
+        def wrapper(positions):
+            distances, labels = map(torch.stack, zip(*[f(positions) for f in distance_fields]))
+            w = nn.functional.softmin(distances / temperature, dim=0)
+            return torch.sum(distances * w, dim=0), torch.sum(labels * w, dim=0)
+        return wrapper
+
+    fields = [sdfs.translation(sdfs.rotation(instance_field(
+        residual_composition(sdfs.box(args[1][i]), residual_distance_field(
+            functools.partial(models.hyper_distance_field.distance_field, weights[0][i] * 40.0))),
+        torch.tensor(i, device="cuda")), args[2][i]), args[0][i]) for i in range(n)]
+    with pytest.raises(UnsupportedFieldError, match="computes something else"):
+        with torch.no_grad():
+            vsrd.rendering.hierarchical_volumetric_rendering(distance_field=soft_union(fields, 0.5), **kwargs)
+
+
+def test_verbatim_main_py_closures_run_on_the_kernels():
+    """The closure factories compiled verbatim from scripts/main.py's AST (staged reference; skipped if absent) around
+    this package's leaves: accepted by the behavioural probe, rendered by the kernels, equal to the Python evaluation of
+    the very same closure at arbitrary points; `hard_union` + sphere tracing works under no_grad and refuses
+    `differentiable=True` with gradients on (the photometric branch is not built)."""
+    import operator
+    import vsrd
+    from oracle import ref_import
+    from tests.test_vsrd_api import _verbatim_field
+    from vsrd.rendering import UnsupportedFieldError
+    from vsrd_b200 import surface
+    if not ref_import.available():
+        pytest.skip("scripts/main.py neither mounted nor staged")
+    n, models, config, world, weights, origins, dirs = _gpu_scene()
+    scene = (n, models, config, world, weights)
+    field = _verbatim_field(scene, residual=True, temperature=0.5)
+    labels, grads, dist, w = vsrd.rendering.hierarchical_volumetric_rendering(
+        distance_field=field, ray_positions=origins, ray_directions=dirs, distance_range=[0.0, 100.0], num_samples=16,
+        sdf_std_deviation=0.5, cosine_ratio=0.5)
+    assert labels.shape == (64, n) and labels.requires_grad
+    pts = (torch.randn(200, 3, device="cuda") * 2.0 + world["locations"][0][0].detach())
+    with torch.no_grad():
+        want_sdf, want_labels = field(pts)
+        got_sdf, _, got_labels = surface.union_field(vsrd.rendering.match_union_field(field), pts, want_weights=True)
+    assert (want_sdf - got_sdf).abs().max() < 1e-4 and (want_labels - got_labels).abs().max() < 1e-4
+    hard = _verbatim_field(scene, residual=True, union="hard_union")
+    traced = vsrd.utils.compose(hard, operator.itemgetter(0))
+    with torch.no_grad():
+        pos, conv = vsrd.rendering.sphere_tracing(traced, origins, dirs, num_iterations=64, convergence_criteria=1e-2,
+                                                  bounding_radius=100.0, initialization=False)
+        assert conv.any()
+        hard_sdf = traced(pos[conv.squeeze(-1)])
+    assert hard_sdf.abs().max() < 5e-2                      # converged positions lie on the hard union's surface
+    with pytest.raises(UnsupportedFieldError, match="photometric"):
+        vsrd.rendering.sphere_tracing(traced, origins, dirs, num_iterations=4, convergence_criteria=1e-2, differentiable=True)

@@ -222,3 +222,32 @@ def test_step_state_drives_the_kernels(ops):
     la, ga, wa, _ = ops.composite_forward(scene_v, rays, fa, s["std_deviation"], s["cosine_ratio"])
     lb, gb, wb, _ = ops.composite_forward(scene_s, rays, fb, 55.0, 0.123)
     assert torch.equal(la, lb) and torch.equal(ga, gb) and torch.equal(wa, wb)
+
+
+def test_vsrd_losses_projection_losses_match_the_frame_oracle():
+    """`vsrd.losses.projection_losses` (the public face of projection_step_kernel) against the restatement of
+    main.py:339-415, values and gradient w.r.t. the world boxes."""
+    import vsrd
+    from vsrd_b200 import synthetic
+    frame = synthetic.make_frame(num_instances=5, num_views=5, seed=12)
+    sup = synthetic.frame_supervision(frame)
+    raw = synthetic.perturbed_raw_parameters(frame, seed=12)
+    loc, dim, rot = oracle_decode(raw)
+    from oracle import vsrd_oracle as vo
+    boxes = vo.box_corners(loc, dim, rot)
+    want_boxes = boxes.clone().double().requires_grad_(True)
+    _, gt_idx, iou, l1 = fo.projection_step(want_boxes, frame.extrinsics.double(), frame.intrinsics.double(), frame.image_size,
+                                            sup.boxes_2d.double(), sup.visible, sup.target_view)
+    want_grad, = torch.autograd.grad(0.1 * iou + l1, want_boxes)
+    got_boxes = boxes.cuda().requires_grad_(True)
+    g_iou, g_l1, g_idx = vsrd.losses.projection_losses(got_boxes, frame.extrinsics.cuda(), frame.intrinsics.cuda(), frame.image_size,
+                                                      sup.boxes_2d.cuda(), sup.visible.cuda(), sup.target_view)
+    got_grad, = torch.autograd.grad(0.1 * g_iou + g_l1, got_boxes)
+    assert g_idx.cpu().tolist() == gt_idx.tolist()
+    assert abs(float(g_iou) - float(iou)) < 1e-5 and abs(float(g_l1) - float(l1)) < 1e-4 * max(1.0, float(l1))
+    assert float((got_grad.cpu().double() - want_grad).norm() / want_grad.norm()) < 1e-4
+
+
+def oracle_decode(raw):
+    from oracle import vsrd_oracle as vo
+    return vo.decode_box_parameters(*raw)

@@ -23,6 +23,8 @@ def compose_like_main(locations, dimensions, orientations, weights, temperature,
 
     def residual_distance_field(distance_field):
         def wrapper(positions):
+            x, y, z = torch.unbind(positions, dim=-1)
+            positions = torch.stack([torch.abs(x), y, z], dim=-1)                  # main.py:437-438
             positions = positions / max(config.volume_rendering.distance_range)
             return torch.sigmoid(distance_field(models.positional_encoder(positions)) - 1.0)
         return wrapper
@@ -206,3 +208,51 @@ def test_gather_rows_reviews_the_base_tensor_instead_of_stacking():
     assert torch.equal(_gather_rows(rev), torch.stack(rev))
     part = list(torch.rand(6, 3))[:4]                # a prefix of a larger tensor
     assert torch.equal(_gather_rows(part), torch.stack(part))
+
+
+def _verbatim_field(scene, residual, union="soft_union", temperature=0.37):
+    """main.py's own closure factories, compiled verbatim from the script's AST (oracle/ref_import.py; test
+    infrastructure), composed around THIS package's sdfs leaves and models exactly as main.py:530-578 does."""
+    from oracle import ref_import
+    n, models, config, world, weights = scene
+    closures = ref_import.main_closures(dict(torch=torch, nn=nn, config=config, models=models, num_instances=n))
+    locations, dimensions, orientations = world["locations"][0], world["dimensions"][0], world["orientations"][0]
+    fields = []
+    for label in range(n):
+        inner = vsrd.rendering.sdfs.box(dimensions[label])
+        if residual:
+            inner = closures["residual_composition"](
+                distance_field=inner,
+                residual_distance_field=closures["residual_distance_field"](
+                    distance_field=functools.partial(models.hyper_distance_field.distance_field, weights[0][label])))
+        inst = closures["instance_field"](distance_field=inner, instance_label=dimensions.new_tensor(label, dtype=torch.long))
+        fields.append(vsrd.rendering.sdfs.translation(vsrd.rendering.sdfs.rotation(inst, orientations[label]), locations[label]))
+    if union == "hard_union":
+        return closures["hard_union"](fields)
+    return closures["soft_union"](distance_fields=fields, temperature=temperature)
+
+
+def _reference_available():
+    from oracle import ref_import
+    return ref_import.available()
+
+
+@pytest.mark.skipif(not _reference_available(), reason="scripts/main.py neither mounted nor staged")
+@pytest.mark.parametrize("residual", [False, True])
+def test_matcher_recovers_scene_from_the_verbatim_main_py_closures(scene, residual):
+    n, models, config, world, weights = scene
+    field = _verbatim_field(scene, residual)
+    u = match_union_field(field)
+    assert u.temperature == pytest.approx(0.37) and u.scale == 100.0 and not u.hard and len(u.code_key) >= 2
+    assert torch.equal(u.locations, world["locations"][0]) and torch.equal(u.half_extents, world["dimensions"][0])
+    assert torch.equal(u.rotations, world["orientations"][0])
+    assert (u.mlp_weights is not None) == residual
+    if residual:
+        assert torch.equal(u.mlp_weights, weights[0])
+    hard = match_union_field(_verbatim_field(scene, residual, union="hard_union"))
+    assert hard.hard and hard.temperature == 1e-6
+    logged = match_union_field(vsrd.utils.compose(field, operator.itemgetter(0)))      # main.py:1030
+    assert not logged.returns_features
+    # the verbatim closure itself evaluates on this package's leaves (plain PyTorch on the CPU)
+    sdf, labels = field(torch.randn(5, 3) * 3.0 + world["locations"][0][0].detach())
+    assert sdf.shape == (5, 1) and labels.shape == (5, n)

@@ -6,6 +6,7 @@ readers and preprocessing transforms are out of scope."""
 from . import configuration  # noqa: F401
 from . import datasets  # noqa: F401
 from . import distributed  # noqa: F401
+from . import losses  # noqa: F401
 from . import models  # noqa: F401
 from . import operations  # noqa: F401
 from . import rendering  # noqa: F401

@@ -9,8 +9,13 @@ that scripts/main.py composes every step (main.py:433-618):
 `translation` / `rotation` / `box` are ours (tagged objects, vsrd/rendering/sdfs.py); the wrappers
 in between are main.py's own nested functions.  `match_union_field` walks their `__closure__` cells
 (free-variable names as in the script) to recover (t_i, R_i, dim_i, W_i, temperature, scale) and the
-whole field then runs inside the kernels.  A field that does not have this structure is an error:
-there is deliberately no eager fallback.
+whole field then runs inside the kernels.  Names alone prove nothing about what a wrapper computes, so
+before a set of wrapper code objects is trusted `verify_union_field` evaluates the caller's own Python
+closure at probe points around every instance (both signs of the local x axis, inside and outside the
+boxes) and compares distances and soft labels with the kernels' result; a look-alike closure (e.g. a
+residual field without main.py:437's |x| fold) is rejected.  The verdict is cached per set of code
+objects — main.py re-creates its closures every step from the same code.  A field that does not have
+this structure is an error: there is deliberately no eager fallback.
 """
 from __future__ import annotations
 
@@ -41,6 +46,11 @@ class UnionField:
     temperature: float
     scale: float
     returns_features: bool = True      # False when wrapped in compose(field, itemgetter(0))
+    hard: bool = False                 # main.py:494-509 hard_union (argmin) instead of the soft-min blend
+    code_key: tuple = ()               # identities of the wrapper code objects the parameters were read from
+
+
+_seen_codes: list = []      # code objects visited by the current match (filled by _closure)
 
 
 def _closure(fn) -> dict:
@@ -48,6 +58,7 @@ def _closure(fn) -> dict:
     cells = getattr(fn, "__closure__", None)
     if code is None or cells is None:
         raise UnsupportedFieldError(f"vsrd_b200: cannot introspect {fn!r}: not a Python closure")
+    _seen_codes.append(code)
     return {name: cell.cell_contents for name, cell in zip(code.co_freevars, cells)}
 
 
@@ -76,6 +87,10 @@ def _match_instance(field, index):
     _expect({"distance_field", "residual_distance_field"} <= set(comp), "expected residual_composition(...)")
     _expect(isinstance(comp["distance_field"], sdfs.BoxSDF), "expected sdfs.box(...) inside residual_composition")
     res = _closure(comp["residual_distance_field"])                  # main.py:433-449 residual_distance_field.wrapper
+    # `config` / `models` are free variables of train() in the live script and globals when the factories are compiled
+    # at module level (tests, oracle/ref_import.main_closures)
+    scope = getattr(comp["residual_distance_field"], "__globals__", {})
+    res = {**{k: scope[k] for k in ("config", "models") if k in scope}, **res}
     _expect({"distance_field", "config", "models"} <= set(res), "expected residual_distance_field(...)")
     partial = res["distance_field"]
     _expect(isinstance(partial, functools.partial) and len(partial.args) == 1 and not partial.keywords,
@@ -112,11 +127,15 @@ def match_union_field(distance_field) -> UnionField:
     if composed is not None:
         _expect(len(composed) == 2 and isinstance(composed[1], operator.itemgetter), "unsupported compose chain")
         distance_field, returns_features = composed[0], False
-    top = _closure(distance_field)                                   # main.py:477-492 soft_union.wrapper
-    _expect({"distance_fields", "temperature"} <= set(top), "expected soft_union(distance_fields, temperature)")
+    del _seen_codes[:]
+    top = _closure(distance_field)                                   # main.py:477-492 soft_union / :494-509 hard_union
+    _expect("distance_fields" in top, "expected soft_union(distance_fields, temperature) or hard_union(distance_fields)")
+    hard = "temperature" not in top
     fields: List = list(top["distance_fields"])
     _expect(len(fields) >= 1, "empty union")
     parts = [_match_instance(f, i) for i, f in enumerate(fields)]
+    code_key = tuple(sorted({id(c) for c in _seen_codes}))
+    _code_refs.update({id(c): c for c in _seen_codes})               # keep them alive so ids stay unique
     locs, rots, dims, ws, scales, counts = zip(*parts)
     _expect(all(c is None or int(c) == len(fields) for c in counts), "num_instances does not match the union size")
     has_w = [w is not None for w in ws]
@@ -127,10 +146,47 @@ def match_union_field(distance_field) -> UnionField:
         rotations=_gather_rows(rots),
         half_extents=_gather_rows(dims),
         mlp_weights=_gather_rows(ws) if all(has_w) else None,
-        temperature=float(top["temperature"]),
+        # hard_union = the temperature -> 0 limit of the soft-min: at 1e-6 the blend weights are exactly one-hot in fp32
+        # unless two instance distances differ by < 1e-4 m, where argmin itself is arbitrary
+        temperature=1e-6 if hard else float(top["temperature"]),
         scale=scale,
         returns_features=returns_features,
+        hard=hard,
+        code_key=code_key,
     )
+
+
+_code_refs: dict = {}
+_verified: set = set()
+
+
+def verify_union_field(distance_field, field: UnionField, probes_per_instance: int = 12) -> None:
+    """Behavioural check of the matched closure, once per set of wrapper code objects (see module docstring)."""
+    key = (field.code_key, field.mlp_weights is not None, field.returns_features, field.hard)
+    if not field.code_key or key in _verified:
+        return
+    from vsrd_b200 import surface
+    with torch.no_grad():
+        n = field.locations.shape[0]
+        gen = torch.Generator().manual_seed(1234)
+        local = (torch.rand(n, probes_per_instance, 3, generator=gen) * 2.0 - 1.0) * 1.6
+        local[:, 0] = 0.05                                                     # one probe near every centre
+        local = local.to(field.locations) * field.half_extents.detach()[:, None, :]
+        points = (local @ field.rotations.detach().transpose(-2, -1) + field.locations.detach()[:, None, :]).reshape(-1, 3)
+        want = distance_field(points)
+        sdf, _, weights = surface.union_field(field, points, want_weights=True)
+        if field.returns_features:
+            want_sdf, want_labels = want[0], want[1].to(sdf.dtype)
+        else:
+            want_sdf, want_labels = want, None
+        _expect(tuple(want_sdf.shape) == tuple(sdf.shape), "the closure does not return distances of shape [..., 1]")
+        err = float((want_sdf - sdf).abs().max())
+        if want_labels is not None and not field.hard:
+            _expect(tuple(want_labels.shape) == tuple(weights.shape), "the closure does not return [..., N] instance labels")
+            err = max(err, float((want_labels - weights).abs().max()))
+        _expect(err < 2e-4, f"the closure computes something else than main.py's field: it differs from the kernels by {err:.3e} "
+                            f"at the probe points")
+    _verified.add(key)
 
 
 def hierarchical_volumetric_rendering(
@@ -149,6 +205,7 @@ def hierarchical_volumetric_rendering(
     sampled_weights [M, ..., 1])` with M = S-1 on the first pass and 2S-1 when the previous pass's
     `sampled_distances` / `sampled_weights` are fed back (importance resampling)."""
     field = match_union_field(distance_field)
+    verify_union_field(distance_field, field)
     lead = ray_directions.shape[:-1]
     dirs = ray_directions.reshape(-1, 3)
     num_rays = dirs.shape[0]
@@ -204,6 +261,13 @@ def sphere_tracing(
     `(ray_positions [..., 3], convergence_masks [..., 1])`.  The iteration loop runs on the device."""
     from vsrd_b200 import surface
     field = match_union_field(distance_field)
+    verify_union_field(distance_field, field)
+    if differentiable and torch.is_grad_enabled() and any(
+            t is not None and t.requires_grad for t in (field.locations, field.rotations, field.half_extents, field.mlp_weights)):
+        raise UnsupportedFieldError(
+            "vsrd_b200: differentiable sphere tracing (the photometric_loss branch, scripts/main.py:689-853) is not built: "
+            "the surface kernels return detached positions; keep loss_weights.photometric_loss at 0.0 (as every shipped "
+            "config does) or call under torch.no_grad()")
     return surface.sphere_trace(field, ray_positions, ray_directions, num_iterations, convergence_criteria,
                                 foreground_masks=foreground_masks, bounding_radius=bounding_radius,
                                 initialization=initialization, differentiable=differentiable)
@@ -213,4 +277,5 @@ def surface_normal(distance_field, surface_positions, finite_difference_epsilon=
     """`vsrd.rendering.surface_normal` (rendering/renderers.py:79-113): unit normals of the union field."""
     from vsrd_b200 import surface
     field = match_union_field(distance_field)
+    verify_union_field(distance_field, field)
     return surface.surface_normals(field, surface_positions, finite_difference_epsilon)

@@ -16,6 +16,9 @@ def quadrature_sampler(bins, deterministic=False):
     lead = bins.shape[:-1]
     flat = bins.reshape(-1, bins.shape[-1])
     num_rays = flat.shape[0]
+    if num_rays > 1 and flat.stride(0) != 0 and not bool((flat == flat[:1]).all()):
+        raise RuntimeError("vsrd_b200: quadrature_sampler needs the same bin edges on every ray (the renderer's "
+                           "`linspace(*distance_range).expand(...)`, renderers.py:191-192)")
     jitter = torch.full((num_rays, flat.shape[1] - 1), 0.5, device=bins.device) if deterministic else None
     out = ops.place_coarse(flat[0].float(), num_rays, jitter, _seed())
     return out.reshape(*lead, -1).to(bins.dtype)

@@ -85,8 +85,10 @@ def sphere_trace(field, ray_positions: torch.Tensor, ray_directions: torch.Tenso
             break
     if differentiable:
         # renderers.py:57-71: one Newton step along the ray at the converged positions.  The kernels return the
-        # spatial gradient with the value, so no autograd call is needed; the result is detached (main.py only
-        # ever calls this with differentiable=False, :1038).
+        # spatial gradient with the value, so no autograd call is needed.  The result is DETACHED: main.py's photometric
+        # branch (:742-754, differentiable=True, loss weight 0.0 in every shipped config) would get no gradient, so
+        # vsrd.rendering.sphere_tracing refuses that call when a field parameter requires grad; the logging call
+        # (:1026-1038) uses differentiable=False.
         per_instance = ops.field_points(scene, pos)
         out, _ = ops.union_points(scene, per_instance)
         step = -out[:, :1] / torch.sum(out[:, 1:] * dirs, dim=-1, keepdim=True)
