@@ -16,7 +16,7 @@ def _iou_3d(a, b):
     import math
     import vsrd
     rot = vsrd.operations.rotation_matrix_x(torch.tensor(-math.pi / 2.0))
-    return float(vsrd.operations.box_3d_iou(a @ rot.T, b @ rot.T)[0])
+    return float(vsrd.operations.box_3d_iou_exact(a @ rot.T, b @ rot.T)[0])
 
 
 SMALL = dict(num_instances=3, num_views=3, image_size=(94, 352), intrinsics_scale=0.25)

@@ -167,18 +167,56 @@ def test_project_box_3d_matches_reference_fixtures():
     assert torch.equal(got[2], torch.zeros(2, 2))       # box behind the camera
 
 
-def test_box_3d_iou_and_utils():
+def _random_box_pairs(count, seed=0, dtype=np.float32):
+    """Box pairs exactly as scripts/main.py:892-899 hands them to `box_3d_iou`: corners in the order of
+    `BoxParameters3D.decode_box_3d` (box_parameters.py:73-91; camera frame, y down) rotated by
+    `rotation_matrix_x(-pi/2)` so that Z is up.  Ordinary overlaps, near-coincident pairs and distant pairs."""
+    rng = np.random.default_rng(seed)
+    signs = np.array([[-1, -1, 1], [1, -1, 1], [1, -1, -1], [-1, -1, -1], [-1, 1, 1], [1, 1, 1], [1, 1, -1], [-1, 1, -1]], float)
+    to_z_up = np.array([[1.0, 0.0, 0.0], [0.0, 0.0, 1.0], [0.0, -1.0, 0.0]])            # rotation_matrix_x(-pi/2)
+
+    def box(centre, half, yaw):
+        c, s = np.cos(yaw), np.sin(yaw)
+        rot_y = np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]])
+        return (((signs * half) @ rot_y.T + centre) @ to_z_up.T).astype(dtype)
+
+    pairs = []
+    for k in range(count):
+        half = rng.uniform([0.75, 0.75, 1.5], [1.0, 1.0, 2.5])
+        centre, yaw = rng.uniform([-20, 0, 5], [20, 1.5, 60]), rng.uniform(-np.pi, np.pi)
+        spread = [0.02, 0.5, 3.0][k % 3]
+        other = box(centre + rng.normal(0, spread, 3) * [1, 0.2, 1], half * rng.uniform(0.9, 1.1, 3), yaw + rng.normal(0, 0.2 * spread))
+        pairs.append((box(centre, half, yaw), other))
+    return pairs
+
+
+def test_box_3d_iou_is_value_identical_to_the_reference_and_exact_variant_is_exact():
+    """tests/golden/box_iou.npz: the reference's `box_3d_iou` (kitti360_operations.py:84-117, imported unmodified by
+    tests/golden/make_golden_box_iou.py) on 300 random pairs, float32 and float64 corners."""
+    golden = np.load(os.path.join(GOLDEN_DIR, "box_iou.npz"))
+    for dtype, key in ((np.float32, "f32"), (np.float64, "f64")):
+        pairs = _random_box_pairs(300, seed=7, dtype=dtype)
+        got = np.array([[float(v) for v in vsrd.operations.box_3d_iou(torch.from_numpy(a), torch.from_numpy(b))] for a, b in pairs])
+        assert np.array_equal(got, golden[key]), np.abs(got - golden[key]).max()
+    exact = np.array([[float(v) for v in vsrd.operations.box_3d_iou_exact(a, b)] for a, b in _random_box_pairs(300, seed=7, dtype=np.float64)])
+    # the reference's +0.01 fudge (:29) is visible against the exact clip, worst on near-coincident pairs
+    gap = np.abs(exact - golden["f64"])[:, 0]
+    assert 0.01 < gap.max() and np.median(gap) < 0.02
+
     b = np.array([[-1, -1, 1], [1, -1, 1], [1, 1, 1], [-1, 1, 1], [-1, -1, -1], [1, -1, -1], [1, 1, -1], [-1, 1, -1]], float)
-    iou, bev = vsrd.operations.box_3d_iou(b, b)
+    iou, bev = vsrd.operations.box_3d_iou_exact(b, b)
     assert float(iou) == pytest.approx(1.0) and float(bev) == pytest.approx(1.0)
-    iou, bev = vsrd.operations.box_3d_iou(b, b + np.array([1.0, 0, 0]))
+    iou, bev = vsrd.operations.box_3d_iou_exact(b, b + np.array([1.0, 0, 0]))
     assert float(iou) == pytest.approx(1 / 3) and float(bev) == pytest.approx(1 / 3)
-    iou, _ = vsrd.operations.box_3d_iou(b, b + np.array([5.0, 0, 0]))
+    iou, _ = vsrd.operations.box_3d_iou_exact(b, b + np.array([5.0, 0, 0]))
     assert float(iou) == 0.0
     c, s = np.cos(0.3), np.sin(0.3)
     rot = b @ np.array([[c, -s, 0], [s, c, 0], [0, 0, 1]]).T
-    iou_rot, _ = vsrd.operations.box_3d_iou(b, rot)
+    iou_rot, _ = vsrd.operations.box_3d_iou_exact(b, rot)
     assert 0.5 < float(iou_rot) < 1.0
+
+
+def test_utils_smoke():
 
     d = vsrd.utils.Dict.apply({"a": {"b": 1}, "c": [{"d": 2}]})
     assert d.a.b == 1 and d.c[0].d == 2
