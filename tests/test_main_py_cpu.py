@@ -61,3 +61,13 @@ def test_unmodified_main_py_runs_on_the_drop_in_glue(tmp_path, monkeypatch):
     assert text.count("[Training]") == 6 and "runtimes" in text and "losses/eikonal_loss" in text
     events = glob.glob(os.path.join(os.path.dirname(logs[0]), "events.out.tfevents.*"))
     assert events, "tensorboard scalars / images were not written"
+
+    # ---- checkpoint -> pseudo-label JSON with confidences (tools/make_predictions.py = tools/kitti_360/make_predictions.py)
+    import subprocess
+    ckpt_root = base.replace("configs", "ckpts")
+    proc = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "make_predictions.py"), "--config", config,
+                           "--ckpt-root", ckpt_root, "--out", str(tmp_path / "predictions")], capture_output=True, text=True)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    assert json.loads(proc.stdout.strip().splitlines()[-1])["prediction_files"] == 3          # target + 2 source frames
+    record = json.load(open(glob.glob(str(tmp_path / "predictions" / "*" / "+0.json"))[0]))
+    assert len(record["boxes_3d"]["car"]) == len(record["confidences"]["car"]) == len(ckpt["models"]["detector"]["locations"][0])
