@@ -338,7 +338,7 @@ def main_style_step(vsrd, model_tuple, config, rays_o, rays_d, targets, sched, n
                             residual_distance_field=residual_distance_field(
                                 distance_field=functools.partial(hyper.distance_field, w_i)),
                         ),
-                        instance_label=i,
+                        instance_label=dimension.new_tensor(i, dtype=torch.long),     # main.py:543
                     ),
                     orientation),
                 location)

@@ -56,7 +56,7 @@ def compose_like_main(locations, dimensions, orientations, weights, temperature,
                 distance_field=inner,
                 residual_distance_field=residual_distance_field(
                     distance_field=functools.partial(models.hyper_distance_field.distance_field, weights[i])))
-        inst = instance_field(distance_field=inner, instance_label=torch.tensor(i))
+        inst = instance_field(distance_field=inner, instance_label=dimensions.new_tensor(i, dtype=torch.long))   # main.py:543
         fields.append(sdfs.translation(sdfs.rotation(inst, orientations[i]), locations[i]))
     return soft_union(distance_fields=fields, temperature=temperature)
 

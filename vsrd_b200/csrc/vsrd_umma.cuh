@@ -1,0 +1,132 @@
+// tcgen05 / TMEM building blocks for the field kernels (sm_100a only; inline PTX, no CUTLASS dependency).
+//
+// The residual MLP is 48-16-16-16-16-1 per (sample, instance): far too small for a warp-specialised GEMM pipeline,
+// but a perfect fit for "one thread == one sample" with the 16-wide contractions done by the 5th-generation tensor
+// core on 128-sample tiles:
+//
+//   registers --tcgen05.st--> TMEM A operand [128 lanes x K columns]  (lane = sample, fp32 containers, kind::tf32)
+//   shared memory B operand (weights, K-major, no swizzle: 8-row x 16-byte core matrices)
+//   tcgen05.mma.cta_group::1.kind::tf32  D[128 x N] (+)= A[128 x 8] * B[N x 8]^T      (one elected thread issues)
+//   tcgen05.commit -> mbarrier;  tcgen05.ld D -> registers of the SAME thread that owns the sample
+//
+// so LayerNorm / GELU need no cross-lane traffic at all and the MMA issue slots leave the SIMT pipes.
+// Error-compensated 3xTF32 (a_hi b_hi + a_lo b_hi + a_hi b_lo, operands pre-split) keeps the contractions at fp32
+// accuracy (single-pass TF32 alone would cost 7e-5 of the 1e-4 silhouette budget).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vsrd {
+namespace umma {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- TMEM allocation (one warp; power-of-two column count >= 32) ----------------------------------------------
+template <int kCols>
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(smem_slot)), "n"(kCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int kCols>
+__device__ __forceinline__ void tmem_free(uint32_t base) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(base), "n"(kCols) : "memory");
+}
+
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// generic-proxy writes to shared memory (st.shared of operands) -> visible to the async proxy (tcgen05.mma reads)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- TMEM <-> registers: 32 lanes x 32 bit, 16 consecutive columns; the warp touches lanes 32*(warp%4).. only ----
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 :: "r"(taddr),
+                    "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+                    "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+                    "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+                    "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "r"(taddr),
+                    "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+                    "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+                 : "memory");
+}
+
+// ---- descriptors -------------------------------------------------------------------------------------------------
+// Instruction descriptor, kind::tf32, fp32 accumulate, A and B K-major (bit layout: cute/arch/mma_sm100_desc.hpp
+// InstrDescriptor: c_format [4,6) = 1 (F32), a_format [7,10) = b_format [10,13) = 2 (TF32), a_major bit 15,
+// b_major bit 16 (0 = K-major, 1 = MN-major), n_dim [17,23) = N >> 3, m_dim [24,29) = M >> 4).
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n, bool a_mn_major = false, bool b_mn_major = false) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16)
+         | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+// Shared-memory matrix descriptor, SWIZZLE_NONE (SmemDescriptor: start address >> 4 in [0,14), leading byte offset >> 4
+// in [16,30), stride byte offset >> 4 in [32,46), version = 1 in [46,48), layout type [61,64) = 0).
+//   K-major operand : core matrix = 8 rows (MN) x 16 bytes (4 tf32 along K), 128 contiguous bytes;
+//                     SBO = byte distance between 8-row groups, LBO = byte distance between the two 16-byte K chunks
+//   MN-major operand: core matrix = 8 rows (K) x 16 bytes (4 tf32 along MN);
+//                     SBO = byte distance between 4-element MN blocks, LBO = byte distance between 8-row K groups
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16)
+         | ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+
+// ---- MMA issue (ONE thread) ----------------------------------------------------------------------------------------
+// D[tmem_d] (+)= A[tmem_a : 128 lanes x 8 columns] * B[smem desc : N x 8]^T
+__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, bool accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+                 :: "r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
+}
+// D[tmem_d] (+)= A[smem desc] * B[smem desc]
+__device__ __forceinline__ void mma_tf32_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, bool accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
+}
+// all previously issued MMAs of this thread complete -> one arrival on the mbarrier (implies fence::before_thread_sync)
+__device__ __forceinline__ void mma_commit(uint64_t* mbar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(mbar)) : "memory");
+}
+
+// ---- mbarrier ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(mbar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "WAIT_%=:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@p bra DONE_%=;\n\t"
+                 "bra WAIT_%=;\n\t"
+                 "DONE_%=:\n\t}"
+                 :: "r"(smem_u32(mbar)), "r"(parity) : "memory");
+}
+// named barrier over `threads` threads (ids 1..15; 0 is __syncthreads)
+__device__ __forceinline__ void named_barrier(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(threads) : "memory");
+}
+
+// hi / lo split for error-compensated TF32: hi keeps the top 19 bits (exactly representable in TF32), lo = x - hi
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+    hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+    lo = x - hi;
+}
+
+}  // namespace umma
+}  // namespace vsrd
