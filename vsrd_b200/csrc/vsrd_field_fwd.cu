@@ -344,10 +344,12 @@ __global__ void union_bound_kernel(SceneDev scene, RaysDev rays, float* __restri
 static int g_fwd_sms = 0;
 static int g_fwd_mt = 2;      // m-tiles per warp tile (VSRD_FWD_MT=1 selects the 16-row variant)
 
-// 0 = tensor-core kernel (default), 1 = SIMT cross-check (VSRD_FIELD_IMPL=simt, read per call)
+// 2 = tcgen05 kernel (default), 0 = mma.sync kernel (VSRD_FIELD_IMPL=mma), 1 = SIMT cross-check (VSRD_FIELD_IMPL=simt); read per call
 static int forward_impl() {
     const char* impl = getenv("VSRD_FIELD_IMPL");
-    return (impl && strcmp(impl, "simt") == 0) ? 1 : 0;
+    if (impl && strcmp(impl, "simt") == 0) return 1;
+    if (impl && strcmp(impl, "mma") == 0) return 0;
+    return 2;
 }
 
 static int forward_setup() {
@@ -390,7 +392,9 @@ static int launch_field(const SceneDev& s, const RaysDev& r, float* field, void*
     VSRD_CHECK_ARG(total < (size_t)1 << 31, "R*M must be < 2^31");
     if (forward_setup()) return 1;
     cudaStream_t st = (cudaStream_t)stream;
-    if (s.W && forward_impl() == 0) {
+    if (s.W && forward_impl() == 2) {
+        if (launch_field_forward_umma(s, r, field, total, st)) return 1;
+    } else if (s.W && forward_impl() == 0) {
         if (g_fwd_mt == 2) launch_forward_mma<2>(s, r, (float4*)field, total, st);
         else launch_forward_mma<1>(s, r, (float4*)field, total, st);
     } else {

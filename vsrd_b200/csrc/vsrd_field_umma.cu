@@ -1,0 +1,493 @@
+// sm_100a field FORWARD kernel on the 5th-generation tensor cores (tcgen05 + TMEM): per-(sample, instance) box SDF +
+// residual MLP, value and spatial gradient (hyper_distance_field.py:57-73,
+// sinusoidal_encoder.py:14-19, sdfs.py:5-37, main.py:433-458).
+//
+// Layout: ONE THREAD == ONE SAMPLE.  A tile is 128 consecutive samples of one instance, owned by a group of four
+// warps (TMEM lane == sample).  Per tile the group makes seven round trips
+//
+//     registers --tcgen05.st--> A operand in TMEM --tcgen05.mma (3xTF32, weights in shared memory)--> D in TMEM
+//               --tcgen05.ld--> registers of the thread that owns the sample
+//
+//   L0  positional encoding e[48]      -> h0 = W0 e + b0 (16)  AND  g_c = dh0 / da_c (3 x 16, derivative weights W0'_c:
+//                                         the chain through sin / cos is linear in e, so d/dx costs no extra sweep in)
+//   L1..L3  a_l = gelu(LayerNorm(h))   -> h_l = W_l a_l + b_l          (bias = one extra k-step against a ones column)
+//   (layer 4, 16 -> 1, and its adjoint stay on the SIMT pipes)
+//   R3..R1  hbar = LayerNorm/GELU adjoint -> abar = W_l^T hbar         (reverse sweep for d out / d h0)
+//   d out / d a_c = hbar0 . g_c
+//
+// LayerNorm / GELU are purely per-thread (16 channels in 16 registers): no shuffles, no fragment layouts, no MMA issue
+// slots on the SIMT pipes.  Three groups per CTA (one CTA per SM) keep the tensor pipe and the LSU/TMEM paths busy
+// while a group waits for its MMAs.  Measured building blocks: tools/umma_probe.cu (profiles/r02_umma_probe.txt).
+#include "vsrd_common.cuh"
+#include "vsrd_umma.cuh"
+
+namespace vsrd {
+namespace fu {
+
+using namespace umma;
+
+constexpr int kMaxGroups = 4;                // tile groups (4 warps each) per CTA: 4 x 128 TMEM columns = all 512
+constexpr int kGroupThreads = 128;
+constexpr int kTile = 128;                   // samples per tile
+
+// ---- TMEM columns of one group (128) ---------------------------------------------------------------------------
+// L0 streams the three PE coordinates through two operand buffers (hi 16 + lo 16 columns each): coordinates 0 and 1
+// go first, coordinate 2 reuses buffer 0 once their MMAs have completed (its encoding is computed meanwhile).
+constexpr int kColBuf0 = 0, kColBuf1 = 32;   // after L0: A hi [0,16), A lo [16,32), D [32,48)
+constexpr int kColAhi = 0, kColAlo = 16, kColD = 32;
+constexpr int kColH0 = 64;                   // h0 [64,80)
+constexpr int kColG = 80;                    // g_x, g_y, g_z [80,128)
+constexpr int kColsPerGroup = 128;
+
+// ---- shared-memory B operands (K-major, no swizzle; one [16 x 16] block = 256 floats, one [16 x 8] block = 128) ----
+// every block is stored hi then lo
+constexpr int kBlk = 256;
+constexpr int kOffW0 = 0;                                 // [c] value weights of coordinate c:        3 x 2 x 256
+constexpr int kOffW0d = kOffW0 + 3 * 2 * kBlk;            // [c] derivative weights W0'_c:             3 x 2 x 256
+constexpr int kOffWl = kOffW0d + 3 * 2 * kBlk;            // [l-1] hidden weights W_l, l = 1..3:       3 x 2 x 256
+constexpr int kOffWt = kOffWl + 3 * 2 * kBlk;             // [l-1] transposed hidden weights W_l^T:    3 x 2 x 256
+constexpr int kOffBias = kOffWt + 3 * 2 * kBlk;           // biases of layers 0..3 (plain fp32, added on the SIMT side): 4 x 16
+constexpr int kOffTail = kOffBias + 4 * 16;               // w4[16], b4
+constexpr int kWeightFloats = kOffTail + 32;
+constexpr int kStashFloats = 3 * 32;                      // per thread: layers 1..3 x (z[16], gelu'(z) / sigma [16])
+constexpr size_t smem_bytes(int groups) { return 1024 + (size_t)kWeightFloats * 4 + (size_t)groups * kGroupThreads * kStashFloats * 4; }
+
+__host__ __device__ constexpr int b_index(int n, int k) { return (k / 4) * 64 + (n / 8) * 32 + (n % 8) * 4 + (k % 4); }   // N = 16
+constexpr uint32_t kLbo = 256, kSbo = 128;                // bytes: K-chunk stride, 8-row group stride
+
+__device__ __forceinline__ void put_split(float* block, int n, int k, float v) {
+    float hi, lo;
+    split_tf32(v, hi, lo);
+    block[b_index(n, k)] = hi;
+    block[kBlk + b_index(n, k)] = lo;
+}
+
+// Global (reference layout: per layer [out][in + 1], bias last) -> the B operand blocks above.
+__device__ void stage_weights_umma(const float* __restrict__ W, float* sW) {
+    for (int i = threadIdx.x; i < kHid * kEnc; i += blockDim.x) {                         // layer 0
+        const int o = i / kEnc, j = i % kEnc, c = j / 16, jj = j % 16, k = jj >> 1;
+        const float w = __ldg(W + kW0 + o * (kEnc + 1) + j);
+        put_split(sW + kOffW0 + c * 2 * kBlk, o, jj, w);
+        // e = (cos(2^k a), sin(2^k a)):  d/da of  w_cos cos + w_sin sin  =  2^k (w_sin cos - w_cos sin)
+        const float f = (float)(1 << k);
+        if (jj & 1) put_split(sW + kOffW0d + c * 2 * kBlk, o, jj - 1, f * w);             // sin weight multiplies cos
+        else put_split(sW + kOffW0d + c * 2 * kBlk, o, jj + 1, -f * w);                   // cos weight multiplies -sin
+    }
+    for (int i = threadIdx.x; i < 4 * kHid; i += blockDim.x) {                            // biases of layers 0..3
+        const int l = i / kHid, o = i % kHid;
+        sW[kOffBias + i] = l == 0 ? __ldg(W + kW0 + o * (kEnc + 1) + kEnc) : __ldg(W + kW1 + (l - 1) * kWStride + o * (kHid + 1) + kHid);
+    }
+    for (int i = threadIdx.x; i < 3 * kHid * kHid; i += blockDim.x) {                     // hidden layers and transposes
+        const int l = i / (kHid * kHid), o = (i / kHid) % kHid, in = i % kHid;
+        const float w = __ldg(W + kW1 + l * kWStride + o * (kHid + 1) + in);
+        put_split(sW + kOffWl + l * 2 * kBlk, o, in, w);
+        put_split(sW + kOffWt + l * 2 * kBlk, in, o, w);
+    }
+    for (int i = threadIdx.x; i < kHid + 1; i += blockDim.x) sW[kOffTail + i] = __ldg(W + kW4 + i);
+}
+
+// ---- per-thread math ---------------------------------------------------------------------------------------------
+// sin / cos with a three-term Cody-Waite reduction and minimax polynomials on [-pi/4, pi/4] (abs. error ~1e-7)
+__device__ __forceinline__ void sincos_cw(float x, float& s, float& c) {
+    const float kf = rintf(x * 0.63661977236758134308f);
+    float r = fmaf(kf, -1.5707962513e+00f, x);
+    r = fmaf(kf, -7.5497894159e-08f, r);
+    r = fmaf(kf, -5.3903029534e-15f, r);
+    const int q = (int)kf;
+    const float r2 = r * r;
+    float sp = fmaf(r2, -1.9515295891e-4f, 8.3321608736e-3f);
+    sp = fmaf(sp, r2, -1.6666654611e-1f);
+    sp = fmaf(sp * r2, r, r);
+    float cp = fmaf(r2, 2.443315711809948e-5f, -1.388731625493765e-3f);
+    cp = fmaf(cp, r2, 4.166664568298827e-2f);
+    cp = fmaf(cp, r2, -0.5f);
+    cp = fmaf(cp, r2, 1.0f);
+    const float ss = (q & 1) ? cp : sp;
+    const float cc = (q & 1) ? sp : cp;
+    s = (q & 2) ? -ss : ss;
+    c = ((q + 1) & 2) ? -cc : cc;
+}
+
+// e[2k] = cos(2^k a), e[2k+1] = sin(2^k a), k = 0..7: accurate anchors at k = 0 and k = 4 (2^k a is exact, so the
+// argument equals fl(freq_k * u) of sinusoidal_encoder.py:16), three double-angle steps after each anchor
+__device__ __forceinline__ void encode16(float a, float2 (&e)[8]) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        float sn, cs;
+        sincos_cw(half ? 16.0f * a : a, sn, cs);
+        e[4 * half] = make_float2(cs, sn);
+#pragma unroll
+        for (int d = 1; d < 4; ++d) {
+            const float s2 = 2.0f * sn * cs;
+            cs = (cs - sn) * (cs + sn);
+            sn = s2;
+            e[4 * half + d] = make_float2(cs, sn);
+        }
+    }
+}
+
+// Two-wide fp32 arithmetic (fma.rn.f32x2 & co.: one issue slot for two channels)
+using f2 = float2;
+__device__ __forceinline__ f2 bc(float a) { return make_float2(a, a); }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
+
+// Phi, phi of the exact-erf GELU for a channel pair (Abramowitz-Stegun 7.1.26 with ex2 / rcp approximations,
+// |err| < 1.5e-7; the polynomial carries the factor 1/2 of the tail): Phi = 1/2 + copysign(1/2 - tail, z)
+__device__ __forceinline__ void gelu_terms2(f2 z, f2& Phi, f2& phi) {
+    const f2 arg = mul2(mul2(z, z), bc(-0.72134752044448170368f));
+    f2 E, t;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(E.x) : "f"(arg.x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(E.y) : "f"(arg.y));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.x) : "f"(fmaf(0.3275911f * kInvSqrt2, fabsf(z.x), 1.0f)));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.y) : "f"(fmaf(0.3275911f * kInvSqrt2, fabsf(z.y), 1.0f)));
+    f2 poly = fma2(bc(0.5f * 1.061405429f), t, bc(0.5f * -1.453152027f));
+    poly = fma2(poly, t, bc(0.5f * 1.421413741f));
+    poly = fma2(poly, t, bc(0.5f * -0.284496736f));
+    poly = fma2(poly, t, bc(0.5f * 0.254829592f));
+    const f2 tail = mul2(mul2(poly, t), E);
+    f2 q = fma2(tail, bc(-1.0f), bc(0.5f));                    // 1/2 - tail >= 0
+    q.x = __uint_as_float(__float_as_uint(q.x) | (__float_as_uint(z.x) & 0x80000000u));
+    q.y = __uint_as_float(__float_as_uint(q.y) | (__float_as_uint(z.y) & 0x80000000u));
+    Phi = add2(q, bc(0.5f));
+    phi = mul2(E, bc(kInvSqrt2Pi));
+}
+
+// h -> z = LayerNorm(h) (no affine, eps 1e-5), a = gelu(z), g = gelu'(z) / sigma; channel pairs (2i, 2i + 1)
+__device__ __forceinline__ void norm_gelu(const f2 (&h)[8], f2 (&z)[8], f2 (&a)[8], f2 (&g)[8]) {
+    f2 acc = h[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) acc = add2(acc, h[i]);
+    const f2 mean = bc((acc.x + acc.y) * (-1.0f / 16.0f));
+    f2 var = bc(0.0f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { z[i] = add2(h[i], mean); var = fma2(z[i], z[i], var); }
+    const float rs1 = rsqrtf((var.x + var.y) * (1.0f / 16.0f) + kLnEps);
+    const f2 rs = bc(rs1);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        z[i] = mul2(z[i], rs);
+        f2 Phi, phi;
+        gelu_terms2(z[i], Phi, phi);
+        a[i] = mul2(z[i], Phi);
+        g[i] = mul2(fma2(z[i], phi, Phi), rs);
+    }
+}
+
+// adjoint of a = gelu(LayerNorm(h)) w.r.t. h:  zb = abar * gelu'(z) / sigma;  hbar = zb - mean(zb) - z mean(z zb)
+__device__ __forceinline__ void norm_gelu_adjoint(const f2 (&abar)[8], const f2 (&z)[8], const f2 (&g)[8], f2 (&hbar)[8]) {
+    f2 m1 = bc(0.0f), m2 = bc(0.0f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        hbar[i] = mul2(abar[i], g[i]);
+        m1 = add2(m1, hbar[i]);
+        m2 = fma2(z[i], hbar[i], m2);
+    }
+    const f2 s1 = bc((m1.x + m1.y) * (-1.0f / 16.0f)), s2 = bc((m2.x + m2.y) * (-1.0f / 16.0f));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) hbar[i] = fma2(z[i], s2, add2(hbar[i], s1));
+}
+
+// v (8 channel pairs) -> hi / lo columns of the group's A operand
+__device__ __forceinline__ void store_operand(uint32_t lane_base, int col_hi, int col_lo, const f2 (&v)[8]) {
+    float hi[16], lo[16];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const f2 h = make_float2(__uint_as_float(__float_as_uint(v[i].x) & 0xFFFFE000u), __uint_as_float(__float_as_uint(v[i].y) & 0xFFFFE000u));
+        const f2 l = fma2(h, bc(-1.0f), v[i]);                 // exact: v - hi
+        hi[2 * i] = h.x; hi[2 * i + 1] = h.y;
+        lo[2 * i] = l.x; lo[2 * i + 1] = l.y;
+    }
+    tmem_st16(lane_base + col_hi, hi);
+    tmem_st16(lane_base + col_lo, lo);
+}
+__device__ __forceinline__ void load_pairs(uint32_t taddr, f2 (&v)[8]) {
+    float t[16];
+    tmem_ld16(taddr, t);
+    wait_ld();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = make_float2(t[2 * i], t[2 * i + 1]);
+}
+
+// The start address sits in the low 14 bits (in 16-byte units) of a shared-memory descriptor, so the descriptor of
+// "base + byte offset" is one 64-bit add of a compile-time constant to the descriptor of the weight arena's base.
+__device__ __forceinline__ uint64_t desc_at(uint64_t base_desc, int float_offset) { return base_desc + (uint64_t)(float_offset * 4 >> 4); }
+
+// D[tmem_d, 16 columns] (+)= A(hi at a_hi, lo at a_lo; 16 columns = 2 k-steps) * B(block at float offset: hi, lo)^T, 3xTF32
+__device__ __forceinline__ void mma3_16x16(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint64_t base_desc, int block, uint32_t idesc, bool accumulate) {
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+        const uint64_t bhi = desc_at(base_desc, block + ks * 128);                      // k-step = two 64-float K chunks
+        const uint64_t blo = desc_at(base_desc, block + kBlk + ks * 128);
+        mma_tf32_ts(tmem_d, a_hi + ks * 8, bhi, idesc, accumulate || ks > 0);
+        mma_tf32_ts(tmem_d, a_lo + ks * 8, bhi, idesc, true);
+        mma_tf32_ts(tmem_d, a_hi + ks * 8, blo, idesc, true);
+    }
+}
+// accumulator columns + bias -> channel pairs
+__device__ __forceinline__ void load_biased(uint32_t taddr, const float* bias, f2 (&v)[8]) {
+    load_pairs(taddr, v);
+    const float2* b = reinterpret_cast<const float2*>(bias);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = add2(v[i], b[i]);
+}
+
+template <int kGroups>
+__global__ void __launch_bounds__(kGroups * kGroupThreads, 1) field_forward_umma_kernel(
+        SceneDev scene, RaysDev rays, float4* __restrict__ field, int tiles_per_inst) {
+    static_assert(kGroups >= 1 && kGroups <= kMaxGroups, "TMEM columns");
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ uint64_t s_mbar[kMaxGroups];
+    __shared__ uint32_t s_tmem_base;
+    float* sW = reinterpret_cast<float*>(smem_raw);
+    float* sStash = sW + kWeightFloats;
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int group = warp >> 2, wq = warp & 3, gt = tid & (kGroupThreads - 1);
+    // per group: [pair index][thread] of float2 (channel pairs): a warp's 32 lanes touch 256 contiguous bytes
+    float* stash = sStash + (size_t)group * kGroupThreads * kStashFloats + 2 * gt;
+    constexpr int kSS = kGroupThreads;                                                    // stride between pairs, in float2
+
+    if (warp == 0) tmem_alloc<512>(&s_tmem_base);
+    if (tid == 0) {
+#pragma unroll
+        for (int g = 0; g < kGroups; ++g) mbar_init(&s_mbar[g], 1);
+        mbar_fence_init();
+    }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = s_tmem_base + group * kColsPerGroup;
+    const uint32_t lane_base = tmem + ((uint32_t)(32 * wq) << 16);
+    const uint32_t idesc = make_idesc_tf32(128, 16);
+    const uint64_t wdesc = make_smem_desc(smem_u32(sW), kLbo, kSbo);      // descriptor of the weight arena's base
+    uint64_t* mbar = &s_mbar[group];
+    uint32_t parity = 0;
+
+    const int total = rays.R * rays.M;
+    const long long all_tiles = (long long)scene.N * tiles_per_inst;
+    const long long begin = all_tiles * blockIdx.x / gridDim.x;
+    const long long end = all_tiles * (blockIdx.x + 1) / gridDim.x;
+    const float cull_margin = kCullLogEps * scene_temperature(scene);
+    const float pi_scale = kPiF / scene.scale;
+    unsigned tiles_visited = 0, tiles_culled = 0;
+
+    for (long long seg = begin; seg < end;) {
+        const int inst = (int)(seg / tiles_per_inst);
+        const long long seg_end = min(end, (long long)(inst + 1) * tiles_per_inst);
+        fence_before_sync();
+        __syncthreads();                                   // every group is done with the previous instance's weights
+        stage_weights_umma(scene.W + (size_t)inst * kNumW, sW);
+        fence_proxy_async_smem();
+        __syncthreads();
+        fence_after_sync();
+        Instance I;
+        load_instance(scene, inst, I);
+
+#pragma unroll 1
+        for (long long tile = seg + group; tile < seg_end; tile += kGroups) {
+            const int base = (int)(tile - (long long)inst * tiles_per_inst) * kTile;
+            const bool in_range = base + gt < total;
+            const int idx = min(base + gt, total - 1);
+            const int r = idx / rays.M;
+            const int j = idx - r * rays.M;
+            float x[3];
+            sample_position(rays, r, j, x);
+            BoxEval b;
+            box_eval(x, I, b);
+            bool skip = false;                             // warp-uniform: this warp's 32 samples need no residual MLP
+            if (rays.bound != nullptr) {
+                // instance culling (VsrdRays::union_bound): a sample farther from this box than the nearest box + the
+                // residual's range + 30 T has a soft-min weight < 1e-13: the box field suffices.  A WARP whose 32 samples
+                // are all far skips its SIMT work (it still takes part in the group's barriers; its TMEM lanes carry stale
+                // operands, which only reach its own, unread, accumulator rows); a TILE whose four warps are all far is
+                // skipped outright.
+                const bool far = !in_range || b.value - (__ldg(rays.bound + idx) + 1.0f) > cull_margin;
+                skip = __all_sync(kFull, far);
+                int all_far;
+                asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %1, 0;\n\tbar.red.and.pred q, %2, %3, p;\n\tselp.b32 %0, 1, 0, q;\n\t}"
+                             : "=r"(all_far) : "r"((int)skip), "r"(1 + group), "r"(kGroupThreads) : "memory");
+                if ((tid & 31) == 0) { ++tiles_visited; tiles_culled += skip ? 1u : 0u; }
+                if (skip && in_range)
+                    field[(size_t)inst * total + base + gt] = make_float4(
+                        b.value,
+                        I.R[0] * b.gp[0] + I.R[1] * b.gp[1] + I.R[2] * b.gp[2],
+                        I.R[3] * b.gp[0] + I.R[4] * b.gp[1] + I.R[5] * b.gp[2],
+                        I.R[6] * b.gp[0] + I.R[7] * b.gp[1] + I.R[8] * b.gp[2]);
+                if (all_far) continue;
+            }
+            // ------------------------------------------------------------ L0: positional encoding -> h0, g_c
+            f2 h[8];
+            {
+                const float m[3] = {fabsf(b.p[0]), b.p[1], b.p[2]};
+                f2 e[8];
+                if (!skip) {
+                    encode16(kPiF * (m[0] / scene.scale), e);
+                    store_operand(lane_base, kColBuf0, kColBuf0 + 16, e);
+                    encode16(kPiF * (m[1] / scene.scale), e);
+                    store_operand(lane_base, kColBuf1, kColBuf1 + 16, e);
+                    wait_st();
+                }
+                fence_before_sync();
+                named_barrier(1 + group, kGroupThreads);
+                if (gt == 0) {
+                    fence_after_sync();
+                    mma3_16x16(tmem + kColH0, tmem + kColBuf0, tmem + kColBuf0 + 16, wdesc, kOffW0, idesc, false);
+                    mma3_16x16(tmem + kColG, tmem + kColBuf0, tmem + kColBuf0 + 16, wdesc, kOffW0d, idesc, false);
+                    mma3_16x16(tmem + kColH0, tmem + kColBuf1, tmem + kColBuf1 + 16, wdesc, kOffW0 + 2 * kBlk, idesc, true);
+                    mma3_16x16(tmem + kColG + 16, tmem + kColBuf1, tmem + kColBuf1 + 16, wdesc, kOffW0d + 2 * kBlk, idesc, false);
+                    mma_commit(mbar);
+                }
+                if (!skip) encode16(kPiF * (m[2] / scene.scale), e);   // overlaps the MMAs of coordinates 0, 1
+                mbar_wait(mbar, parity); parity ^= 1;                  // ... which must be done before buffer 0 is reused
+                fence_after_sync();
+                if (!skip) {
+                    store_operand(lane_base, kColBuf0, kColBuf0 + 16, e);
+                    wait_st();
+                }
+                fence_before_sync();
+                named_barrier(1 + group, kGroupThreads);
+                if (gt == 0) {
+                    fence_after_sync();
+                    mma3_16x16(tmem + kColH0, tmem + kColBuf0, tmem + kColBuf0 + 16, wdesc, kOffW0 + 4 * kBlk, idesc, true);
+                    mma3_16x16(tmem + kColG + 32, tmem + kColBuf0, tmem + kColBuf0 + 16, wdesc, kOffW0d + 4 * kBlk, idesc, false);
+                    mma_commit(mbar);
+                }
+            }
+            mbar_wait(mbar, parity); parity ^= 1;
+            fence_after_sync();
+            if (!skip) load_biased(lane_base + kColH0, sW + kOffBias, h);
+            // ------------------------------------------------------------ L1..L3 + layer 4 on the SIMT pipes
+            f2 abar[8];                                    // adjoint of h3 after the loop
+            float out = 0.0f;
+#pragma unroll
+            for (int l = 1; l <= 4; ++l) {
+                f2 z[8], a[8], g[8];
+                if (!skip) norm_gelu(h, z, a, g);
+                if (l < 4) {
+                    if (!skip) {
+                        float2* st = reinterpret_cast<float2*>(stash) + (l - 1) * 16 * kSS;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) { st[i * kSS] = z[i]; st[(8 + i) * kSS] = g[i]; }
+                        store_operand(lane_base, kColAhi, kColAlo, a);
+                        wait_st();
+                    }
+                    fence_before_sync();
+                    named_barrier(1 + group, kGroupThreads);
+                    if (gt == 0) {
+                        fence_after_sync();
+                        mma3_16x16(tmem + kColD, tmem + kColAhi, tmem + kColAlo, wdesc, kOffWl + (l - 1) * 2 * kBlk, idesc, false);
+                        mma_commit(mbar);
+                    }
+                    mbar_wait(mbar, parity); parity ^= 1;
+                    fence_after_sync();
+                    if (!skip) load_biased(lane_base + kColD, sW + kOffBias + 16 * l, h);
+                } else if (!skip) {
+                    // out = w4 . a4 + b4;  abar4 = w4;  hbar3 = adjoint through LayerNorm/GELU of layer 4, right here
+                    const float2* w4 = reinterpret_cast<const float2*>(sW + kOffTail);
+                    f2 acc = bc(0.0f), wv[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { wv[i] = w4[i]; acc = fma2(wv[i], a[i], acc); }
+                    out = acc.x + acc.y + sW[kOffTail + 16];
+                    norm_gelu_adjoint(wv, z, g, abar);                                    // = hbar3 (adjoint of h3)
+                }
+            }
+            // ------------------------------------------------------------ R3..R1: abar_l = W_l^T hbar_l, then through layer l's norm/GELU
+#pragma unroll
+            for (int l = 3; l >= 1; --l) {
+                if (!skip) {
+                    store_operand(lane_base, kColAhi, kColAlo, abar);
+                    wait_st();
+                }
+                fence_before_sync();
+                named_barrier(1 + group, kGroupThreads);
+                if (gt == 0) {
+                    fence_after_sync();
+                    mma3_16x16(tmem + kColD, tmem + kColAhi, tmem + kColAlo, wdesc, kOffWt + (l - 1) * 2 * kBlk, idesc, false);
+                    mma_commit(mbar);
+                }
+                mbar_wait(mbar, parity); parity ^= 1;
+                fence_after_sync();
+                if (!skip) {
+                    f2 ab[8], z[8], g[8];
+                    const float2* st = reinterpret_cast<const float2*>(stash) + (l - 1) * 16 * kSS;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { z[i] = st[i * kSS]; g[i] = st[(8 + i) * kSS]; }
+                    load_pairs(lane_base + kColD, ab);
+                    norm_gelu_adjoint(ab, z, g, abar);                                    // abar <- hbar_{l-1}
+                }
+            }
+            if (skip) { fence_before_sync(); continue; }
+            // ------------------------------------------------------------ d out / d a_c = hbar0 . g_c
+            float ga[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                f2 g[8];
+                load_pairs(lane_base + kColG + 16 * c, g);
+                f2 acc = bc(0.0f);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc = fma2(abar[i], g[i], acc);
+                ga[c] = acc.x + acc.y;
+            }
+            const float res = sigmoidf_(out - 1.0f);
+            const float sp = res * (1.0f - res) * pi_scale;
+            const float gp0 = b.gp[0] + sp * b.s[0] * ga[0];
+            const float gp1 = b.gp[1] + sp * ga[1];
+            const float gp2 = b.gp[2] + sp * ga[2];
+            if (in_range)
+                field[(size_t)inst * total + base + gt] = make_float4(
+                    b.value + res,
+                    I.R[0] * gp0 + I.R[1] * gp1 + I.R[2] * gp2,
+                    I.R[3] * gp0 + I.R[4] * gp1 + I.R[5] * gp2,
+                    I.R[6] * gp0 + I.R[7] * gp1 + I.R[8] * gp2);
+            // the next tile's tcgen05.st must not overtake this tile's tcgen05.ld of the same columns
+            fence_before_sync();
+        }
+        seg = seg_end;
+    }
+    if ((tid & 31) == 0 && rays.cull_stats != nullptr && tiles_visited) {
+        atomicAdd(rays.cull_stats, (unsigned long long)tiles_culled);
+        atomicAdd(rays.cull_stats + 1, (unsigned long long)tiles_visited);
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_free<512>(s_tmem_base);
+}
+
+}  // namespace fu
+
+static int g_umma_sms = 0;
+static int g_umma_groups = 4;
+
+template <int kGroups>
+static void launch_umma(const SceneDev& s, const RaysDev& r, float* field, size_t total, cudaStream_t st) {
+    const int tiles_per_inst = (int)((total + fu::kTile - 1) / fu::kTile);
+    const long long all_tiles = (long long)s.N * tiles_per_inst;
+    const long long want = (all_tiles + kGroups - 1) / kGroups;
+    const int grid = (int)(want < g_umma_sms ? want : g_umma_sms);
+    fu::field_forward_umma_kernel<kGroups><<<grid, kGroups * fu::kGroupThreads, fu::smem_bytes(kGroups), st>>>(
+        s, r, (float4*)field, tiles_per_inst);
+}
+
+int launch_field_forward_umma(const SceneDev& s, const RaysDev& r, float* field, size_t total, cudaStream_t st) {
+    if (!g_umma_sms) {
+        int dev = 0;
+        cudaDeviceProp prop;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess)
+            return fail("vsrd_b200: no CUDA device%s");
+        if (cudaFuncSetAttribute(fu::field_forward_umma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)fu::smem_bytes(3)) != cudaSuccess ||
+            cudaFuncSetAttribute(fu::field_forward_umma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)fu::smem_bytes(4)) != cudaSuccess)
+            return fail("vsrd_b200: cannot reserve shared memory for field_forward_umma_kernel (built for sm_100a)%s");
+        const char* g = getenv("VSRD_UMMA_GROUPS");
+        if (g && (g[0] == '3' || g[0] == '4')) g_umma_groups = g[0] - '0';
+        g_umma_sms = prop.multiProcessorCount;
+    }
+    if (g_umma_groups == 3) launch_umma<3>(s, r, field, total, st);
+    else launch_umma<4>(s, r, field, total, st);
+    return 0;
+}
+
+}  // namespace vsrd
