@@ -208,6 +208,16 @@ int vsrd_projection_step(const VsrdViews* views, int num_instances, const float*
                          float* boxes_2d, int64_t* gt_indices, float* losses, float* grad_world_boxes,
                          float* scratch, void* stream);
 
+/* vsrd.operations.project_box_3d (vsrd/operations/geometric_operations.py:343-389; scripts/main.py:346-355 calls it once
+ * per view and instance, 136 times per step) for `num_boxes` CAMERA-frame boxes [B,8,3] sharing one intrinsic matrix
+ * [3,3]: the 12 edges of main.py's LINE_INDICES are clipped to z > 0 and projected; boxes_2d [B,4] = (min u, min v,
+ * max u, max v), zeros when the box is entirely behind the camera.  No host synchronisation (the reference's
+ * `torch.any(masks)` forces one per call).  The backward maps grad_boxes_2d [B,4] to grad_boxes_3d [B,8,3]. */
+int vsrd_project_box_3d(const float* boxes_3d, int num_boxes, const float* intrinsic_matrix, float epsilon,
+                        float* boxes_2d, void* stream);
+int vsrd_project_box_3d_backward(const float* boxes_3d, int num_boxes, const float* intrinsic_matrix, float epsilon,
+                                 const float* grad_boxes_2d, float* grad_boxes_3d, void* stream);
+
 /* ---- a2: ray selection (scripts/main.py:620-627: torch.multinomial(max_n soft_masks, num_rays, no
  * replacement) over all V*H*W pixels, every step).  The weights do not change within a frame, so the
  * max over instances and its inclusive CDF (double) are built once per frame:

@@ -18,7 +18,7 @@ import torch
 from oracle import frame_oracle as fo
 from oracle import vsrd_oracle as oracle
 
-VERSION = 1
+VERSION = 2
 CACHE_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "_cache")
 CASES = {
     # name: (frame kwargs, seed, steps, warm-up, rays, samples)
@@ -107,11 +107,14 @@ def _optimise(c, raw, emb, hyper, opt, sched, inv_proj, cam, ext, intr, gt2d, so
                                      jitter=c["jitter"][step][:, None, :].to(dtype), sorted_uniforms=c["uniforms"][step][:, None, :].to(dtype))
         loss = loss + 0.1 * iou + 1.0 * l1
         if step in (0, warm):
-            marks[step] = float(loss)
+            marks[step] = float(loss.detach())
         opt.zero_grad()
         loss.backward()
         opt.step()
         sched.step()
+        if step + 1 == steps // 2:                         # boxes half way: before the chaotic amplification sets in
+            with torch.no_grad():
+                marks["half"] = oracle.box_corners(*[oracle.decode_box_parameters(*raw)[i] for i in (0, 1, 2)]).double().clone()
     with torch.no_grad():
         loc, dim, rot = oracle.decode_box_parameters(*raw)
         return oracle.box_corners(loc, dim, rot)
@@ -123,9 +126,10 @@ def get_case(name):
         data = dict(np.load(path))
     else:
         b32, m32 = run_oracle(name, torch.float32)
-        b64, _ = run_oracle(name, torch.float64)
+        b64, m64 = run_oracle(name, torch.float64)
         warm = CASES[name][3]
-        data = dict(boxes_f32=b32.numpy(), boxes_f64=b64.numpy(), loss_first=np.float64(m32[0]), loss_warm=np.float64(m32[warm]))
+        data = dict(boxes_f32=b32.numpy(), boxes_f64=b64.numpy(), half_f32=m32["half"].numpy(), half_f64=m64["half"].numpy(),
+                    loss_first=np.float64(m32[0]), loss_warm=np.float64(m32[warm]))
         os.makedirs(CACHE_DIR, exist_ok=True)
         tmp = path + f".{os.getpid()}.tmp.npz"
         np.savez(tmp, **data)
@@ -146,6 +150,7 @@ if __name__ == "__main__":
         t0 = time.time()
         c = get_case(name)
         ious = [float(vsrd.operations.box_3d_iou_exact(a @ rot.T, b @ rot.T)[0]) for a, b in zip(c["boxes_f32"], c["boxes_f64"])]
+        print(f"{name}: half way: fp32 vs fp64 max corner difference {float((c['half_f32'] - c['half_f64']).abs().max()):.5f} m")
         print(f"{name}: {time.time() - t0:.0f} s; fp32 oracle vs fp64 oracle after {c['steps']} steps: max corner difference "
               f"{float((c['boxes_f32'] - c['boxes_f64']).abs().max()):.5f} m, 3D IoU {[round(v, 5) for v in ious]}; boxes moved "
               f"{float((c['boxes_f32'] - c['boxes_init']).abs().max()):.3f} m", flush=True)

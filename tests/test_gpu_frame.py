@@ -251,3 +251,29 @@ def test_vsrd_losses_projection_losses_match_the_frame_oracle():
 def oracle_decode(raw):
     from oracle import vsrd_oracle as vo
     return vo.decode_box_parameters(*raw)
+
+
+def test_fused_project_box_3d_matches_the_pytorch_ops_and_the_reference_golden():
+    """`vsrd.operations.project_box_3d` on CUDA (one launch + one backward launch) against its own PyTorch-op form on
+    the CPU (pinned to the reference's function by tests/golden/units.npz in test_vsrd_api.py): boxes in front of the
+    camera, straddling the image plane and behind it; values and the gradient w.r.t. the corners."""
+    import vsrd
+    u = np.load(os.path.join(GOLDEN_DIR, "units.npz"))
+    boxes = torch.from_numpy(u["pb_boxes_3d"])
+    k = torch.from_numpy(u["pb_intrinsic"])
+    lines = [[0, 1], [1, 2], [2, 3], [3, 0], [4, 5], [5, 6], [6, 7], [7, 4], [0, 4], [1, 5], [2, 6], [3, 7]]
+    got = torch.stack([vsrd.operations.project_box_3d(b.cuda(), lines, k.cuda()) for b in boxes])
+    torch.testing.assert_close(got.cpu(), torch.from_numpy(u["pb_boxes_2d"]), rtol=1e-5, atol=1e-3)
+    assert torch.equal(got[2].cpu(), torch.zeros(2, 2))                      # entirely behind the camera
+    gen = torch.Generator().manual_seed(3)
+    weights = torch.randn(len(boxes), 2, 2, generator=gen)
+    for i, box in enumerate(boxes):
+        a = box.clone().requires_grad_(True)
+        b = box.clone().cuda().requires_grad_(True)
+        ref = vsrd.operations.project_box_3d(a, lines, k)                    # CPU tensors -> the PyTorch-op path
+        out = vsrd.operations.project_box_3d(b, lines, k.cuda())
+        torch.testing.assert_close(out.cpu(), ref, rtol=1e-5, atol=1e-3)
+        if ref.requires_grad:
+            (ref * weights[i]).sum().backward()
+            (out * weights[i].cuda()).sum().backward()
+            torch.testing.assert_close(b.grad.cpu(), a.grad, rtol=1e-4, atol=1e-4)

@@ -1,7 +1,12 @@
 #!/usr/bin/env python
 """Summarise an .ncu-rep (ncu --set full) into the handful of counters DESIGN.md / bench.py cite.
     python tools/ncu_summary.py gpurun_out/prof.ncu-rep > profiles/rNN_xxx_ncu_summary.txt
+    python tools/ncu_summary.py gpurun_out/prof.ncu-rep --roofline R S N profiles/rNN_xxx_ncu_summary.txt
+        additionally writes profiles/roofline_kernel.json (kernel name + DRAM bytes per launch of the first kernel in the
+        report, captured at the shape R rays x S samples x N instances), which bench.py reports as roofline.traffic
 """
+import json
+import os
 import csv
 import io
 import subprocess
@@ -50,5 +55,28 @@ def main(path):
                 print(f"   {w:88s} {r[idx[w]]:>16s} {units[idx[w]]}")
 
 
+def roofline(path, rays, samples, instances, source):
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units, first = rows[0], rows[1], rows[2]
+    idx = {h: i for i, h in enumerate(hdr)}
+
+    def in_bytes(name):
+        value, unit = float(first[idx[name]].replace(",", "")), units[idx[name]].lower()
+        return value * {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}[unit]
+
+    out = dict(kernel=re.sub(r"\(.*", "", first[idx["Kernel Name"]]).replace("void ", ""), shape=[rays, samples, instances],
+               traffic_bytes=in_bytes("dram__bytes_read.sum") + in_bytes("dram__bytes_write.sum"),
+               dram_bytes_read=in_bytes("dram__bytes_read.sum"), dram_bytes_write=in_bytes("dram__bytes_write.sum"),
+               ncu_duration_us=float(first[idx["gpu__time_duration.sum"]].replace(",", "")), source=source)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(root, "profiles", "roofline_kernel.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    print(json.dumps(out), file=sys.stderr)
+
+
 if __name__ == "__main__":
+    import re
     main(sys.argv[1])
+    if len(sys.argv) > 2 and sys.argv[2] == "--roofline":
+        roofline(sys.argv[1], int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]), sys.argv[6])

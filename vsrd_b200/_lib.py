@@ -180,6 +180,8 @@ SIGNATURES = {
                                      _P(VsrdLoss), _V, _V, _V]),
     "vsrd_field_backward": (_I, [_P(VsrdScene), _P(VsrdRays), _V, _V, _V, _V, _V, _V, _V]),
     "vsrd_projection_scratch_floats": (ctypes.c_size_t, [_I, _I]),
+    "vsrd_project_box_3d": (_I, [_V, _I, _V, ctypes.c_float, _V, _V]),
+    "vsrd_project_box_3d_backward": (_I, [_V, _I, _V, ctypes.c_float, _V, _V, _V]),
     "vsrd_projection_step": (_I, [_P(VsrdViews), _I, _V, _V, _V, _V, _V, _V, _V, _V, _V, _V]),
     "vsrd_ray_cdf_scratch_doubles": (ctypes.c_size_t, [ctypes.c_int64]),
     "vsrd_ray_cdf_build": (_I, [_V, ctypes.c_int64, _I, _V, _V, _V]),

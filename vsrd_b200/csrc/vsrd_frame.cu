@@ -410,6 +410,43 @@ __global__ void step_state_kernel(VsrdStepState* st, VsrdSchedule cfg, int64_t s
 
 using namespace vsrd;
 
+// vsrd.operations.project_box_3d (geometric_operations.py:343-389) for a batch of camera-frame boxes: one thread per
+// box; the backward recomputes the projection and applies its adjoint (project_box_backward with E = identity).
+namespace vsrd {
+__constant__ float kIdentity4[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+
+__global__ void project_box_3d_kernel(const float* __restrict__ boxes, const float* __restrict__ K, int num, float eps,
+                                      float* __restrict__ out) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= num) return;
+    float k[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) k[i] = __ldg(K + i);
+    BoxProjection bp;
+    project_box(kIdentity4, k, boxes + 24 * (size_t)b, 0.0f, 0.0f, eps, bp, false);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) out[4 * (size_t)b + i] = bp.box[i];
+}
+
+__global__ void project_box_3d_backward_kernel(const float* __restrict__ boxes, const float* __restrict__ K, int num, float eps,
+                                               const float* __restrict__ grad_out, float* __restrict__ grad_boxes) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= num) return;
+    float k[9], g[4], gw[24];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) k[i] = __ldg(K + i);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) g[i] = grad_out[4 * (size_t)b + i];
+#pragma unroll
+    for (int i = 0; i < 24; ++i) gw[i] = 0.0f;
+    BoxProjection bp;
+    project_box(kIdentity4, k, boxes + 24 * (size_t)b, 0.0f, 0.0f, eps, bp, false);
+    project_box_backward(kIdentity4, k, bp, 0.0f, 0.0f, eps, g, gw, false);
+#pragma unroll
+    for (int i = 0; i < 24; ++i) grad_boxes[24 * (size_t)b + i] = gw[i];
+}
+}  // namespace vsrd
+
 extern "C" {
 
 size_t vsrd_projection_scratch_floats(int num_views, int num_instances) {
@@ -501,6 +538,28 @@ int vsrd_step_state_update(VsrdStepState* step_state, const VsrdSchedule* schedu
     VSRD_CHECK_ARG(step_state && schedule, "step_state / schedule must not be NULL");
     VSRD_CHECK_ARG(schedule->num_steps >= 1, "num_steps must be positive");
     step_state_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_state, *schedule, set_step);
+    VSRD_CHECK_LAUNCH();
+    return 0;
+}
+
+
+int vsrd_project_box_3d(const float* boxes_3d, int num_boxes, const float* intrinsic_matrix, float epsilon,
+                        float* boxes_2d, void* stream) {
+    VSRD_CHECK_ARG(num_boxes >= 0, "num_boxes must be non-negative");
+    if (num_boxes == 0) return 0;
+    VSRD_CHECK_ARG(boxes_3d && intrinsic_matrix && boxes_2d, "NULL pointer");
+    project_box_3d_kernel<<<(num_boxes + 63) / 64, 64, 0, (cudaStream_t)stream>>>(boxes_3d, intrinsic_matrix, num_boxes, epsilon, boxes_2d);
+    VSRD_CHECK_LAUNCH();
+    return 0;
+}
+
+int vsrd_project_box_3d_backward(const float* boxes_3d, int num_boxes, const float* intrinsic_matrix, float epsilon,
+                                 const float* grad_boxes_2d, float* grad_boxes_3d, void* stream) {
+    VSRD_CHECK_ARG(num_boxes >= 0, "num_boxes must be non-negative");
+    if (num_boxes == 0) return 0;
+    VSRD_CHECK_ARG(boxes_3d && intrinsic_matrix && grad_boxes_2d && grad_boxes_3d, "NULL pointer");
+    project_box_3d_backward_kernel<<<(num_boxes + 63) / 64, 64, 0, (cudaStream_t)stream>>>(
+        boxes_3d, intrinsic_matrix, num_boxes, epsilon, grad_boxes_2d, grad_boxes_3d);
     VSRD_CHECK_LAUNCH();
     return 0;
 }

@@ -72,8 +72,10 @@ VSRD_HD void pinhole(const float* K, const float p[3], float eps, float h[3], fl
 }
 
 // One (view, instance) pair: world corners [8,3] -> clipped 2D box.
+// `clip_to_image = false` stops after the min / max over the clipped edge points (geometric_operations.py:343-389 on
+// its own; main.py applies torchvision's clip_boxes_to_image separately): box == raw.
 VSRD_HD void project_box(const float* E, const float* K, const float* world, float height, float width,
-                         float eps, BoxProjection& o) {
+                         float eps, BoxProjection& o, bool clip_to_image = true) {
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
 #pragma unroll
@@ -104,6 +106,10 @@ VSRD_HD void project_box(const float* E, const float* K, const float* world, flo
     } else {
         o.raw[0] = lo[0]; o.raw[1] = lo[1]; o.raw[2] = hi[0]; o.raw[3] = hi[1];
     }
+    if (!clip_to_image) {
+        o.box[0] = o.raw[0]; o.box[1] = o.raw[1]; o.box[2] = o.raw[2]; o.box[3] = o.raw[3];
+        return;
+    }
     o.box[0] = fminf(fmaxf(o.raw[0], 0.0f), width);
     o.box[1] = fminf(fmaxf(o.raw[1], 0.0f), height);
     o.box[2] = fminf(fmaxf(o.raw[2], 0.0f), width);
@@ -114,14 +120,14 @@ VSRD_HD void project_box(const float* E, const float* K, const float* world, flo
 // (accumulated into `gworld`).  Mirrors autograd: clamp passes the gradient inside the closed range,
 // min/max send it to the selected point, torch.clamp(max=1) on the clip weight blocks it when active.
 VSRD_HD void project_box_backward(const float* E, const float* K, const BoxProjection& o, float height, float width,
-                                  float eps, const float gbox[4], float gworld[24]) {
+                                  float eps, const float gbox[4], float gworld[24], bool clip_to_image = true) {
     float gcam[8][3];
 #pragma unroll
     for (int c = 0; c < 8; ++c) gcam[c][0] = gcam[c][1] = gcam[c][2] = 0.0f;
     const float bound[4] = {width, height, width, height};
     for (int s = 0; s < 4; ++s) {
         if (o.ext[s] < 0) continue;
-        const float g = (o.raw[s] >= 0.0f && o.raw[s] <= bound[s]) ? gbox[s] : 0.0f;
+        const float g = (!clip_to_image || (o.raw[s] >= 0.0f && o.raw[s] <= bound[s])) ? gbox[s] : 0.0f;
         if (g == 0.0f) continue;
         const int e = o.ext[s] >> 1, end = o.ext[s] & 1, a = s & 1;
         ClippedEdge ce;

@@ -349,6 +349,25 @@ def projection_step(views: ViewArgs, world_boxes, gt_boxes_2d=None, visible=None
 
 # ---- a2: ray selection ---------------------------------------------------------------------------
 
+def project_box_3d(boxes_3d: torch.Tensor, intrinsic_matrix: torch.Tensor, epsilon: float = 1e-6) -> torch.Tensor:
+    """Camera-frame boxes [B,8,3] + one intrinsic matrix [3,3] -> 2D boxes [B,4] (min u, min v, max u, max v)."""
+    boxes = _f32(boxes_3d, "boxes_3d").reshape(-1, 8, 3)
+    k = _f32(intrinsic_matrix, "intrinsic_matrix").reshape(3, 3)
+    out = torch.empty(boxes.shape[0], 4, device=boxes.device, dtype=torch.float32)
+    _lib.check(_lib.load().vsrd_project_box_3d(_ptr(boxes), boxes.shape[0], _ptr(k), float(epsilon), _ptr(out), _stream()))
+    return out
+
+
+def project_box_3d_backward(boxes_3d, intrinsic_matrix, grad_boxes_2d, epsilon: float = 1e-6) -> torch.Tensor:
+    boxes = _f32(boxes_3d, "boxes_3d").reshape(-1, 8, 3)
+    k = _f32(intrinsic_matrix, "intrinsic_matrix").reshape(3, 3)
+    grad = _f32(grad_boxes_2d, "grad_boxes_2d").reshape(boxes.shape[0], 4)
+    out = torch.empty_like(boxes)
+    _lib.check(_lib.load().vsrd_project_box_3d_backward(_ptr(boxes), boxes.shape[0], _ptr(k), float(epsilon), _ptr(grad),
+                                                        _ptr(out), _stream()))
+    return out
+
+
 def ray_cdf_build(soft_masks: torch.Tensor) -> torch.Tensor:
     """soft_masks [..., N] (flattened to [P,N]) -> inclusive CDF [P] (float64) of max_n soft_masks."""
     m = _f32(soft_masks, "soft_masks")
