@@ -189,35 +189,6 @@ def test_rays_that_miss_everything_follow_the_reference(F):
     assert float((labels - ref[0]).abs().max()) < 1e-4
 
 
-_BWD_SCRIPT = r"""
-import sys, torch
-sys.path.insert(0, {root!r})
-from tests.test_gpu_properties import _scene, _rays, _render
-from vsrd_b200 import functional as F
-frame, leaves = _scene(5, "street", seed=11)
-o, d = _rays(frame, 77, seed=5)
-dev_leaves, (labels, grads, *_r) = _render(F, leaves, o, d, 24, requires_grad=True)
-gen = torch.Generator(device="cuda").manual_seed(1)
-u = torch.randn(labels.shape, device="cuda", generator=gen)
-v = torch.randn(grads.shape, device="cuda", generator=gen) * 0.1
-g = torch.autograd.grad([labels, grads], dev_leaves, [u, v])
-torch.save([t.cpu() for t in g], sys.argv[1])
-"""
-
-
-def test_backward_m_tile_variants_agree(tmp_path):
-    """VSRD_BWD_MT selects the backward field kernel variant (read once per process): 16-sample tiles with (3, default)
-    or without (1) tile pairing, or 32-sample tiles (2)."""
-    outs = []
-    for mt in ("3", "1", "2"):
-        path = str(tmp_path / f"g{mt}.pt")
-        env = dict(os.environ, VSRD_BWD_MT=mt)
-        proc = subprocess.run([sys.executable, "-c", _BWD_SCRIPT.format(root=ROOT), path], env=env, capture_output=True, text=True, timeout=600)
-        assert proc.returncode == 0, proc.stderr[-2000:]
-        outs.append(torch.load(path))
-    for other in outs[1:]:
-        for a, b in zip(outs[0], other):
-            assert float((a - b).norm()) <= 1e-5 * float(b.norm()) + 1e-9, float((a - b).norm() / b.norm())
 
 
 @pytest.mark.parametrize("n,layout,temperature,share", [(8, "street", 0.1, 0.2), (24, "parking", 0.3, 0.2)])

@@ -687,9 +687,9 @@ __global__ void reduce_segment_rows_kernel(const float* __restrict__ partials, i
 }
 
 static int g_sms = 0;
-static int g_bwd_mt = 3;       // VSRD_BWD_MT: 3 (ships) = one m-tile per warp pass, lane phases shared by a PAIR of tiles, 12 warps x
-                               // 168 registers: 0.738 ms; 1 = the same without pairing: 0.770 ms; 2 = two m-tiles, 8 warps x 255
-                               // registers: 0.810 ms (R=1000 S=100 N=8)
+// Shipped configuration: one m-tile per warp pass, lane == sample phases shared by a PAIR of tiles, 12 warps x 168 registers:
+// 0.738 ms at R=1000 S=100 N=8.  Measured and removed (round 1): the same without pairing 0.770 ms; two m-tiles per warp, 8 warps
+// x 255 registers 0.810 ms.
 
 static int setup() {
     if (g_sms) return 0;
@@ -697,15 +697,9 @@ static int setup() {
     if (cudaGetDevice(&dev) != cudaSuccess) return fail("vsrd_b200: no CUDA device%s");
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return fail("vsrd_b200: cudaGetDeviceProperties failed%s");
-    if (cudaFuncSetAttribute(field_backward_mma_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)BwdCfg<2>::kSmemBytes) != cudaSuccess ||
-        cudaFuncSetAttribute(field_backward_mma_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)BwdCfg<1>::kSmemBytes) != cudaSuccess ||
-        cudaFuncSetAttribute(field_backward_mma_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(field_backward_mma_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)BwdCfg<1>::kSmemBytes) != cudaSuccess)
         return fail("vsrd_b200: cannot reserve %s of shared memory for field_backward_mma_kernel (built for sm_100a)", "206 KB");
-    const char* mt = getenv("VSRD_BWD_MT");
-    if (mt && (mt[0] == '1' || mt[0] == '2' || mt[0] == '3')) g_bwd_mt = mt[0] - '0';      // 3 = one m-tile, tile pairs
     g_sms = prop.multiProcessorCount;
     return 0;
 }
@@ -732,7 +726,7 @@ static int launch(const SceneDev& s, const RaysDev& r, const float* adjoint, flo
 
 int backward_mma_tile_rows() {
     if (bwd5::setup()) return -1;
-    return bwd5::g_bwd_mt == 2 ? 32 : 16;
+    return 16;
 }
 
 int backward_mma_partial_rows(int num_instances) {
@@ -743,9 +737,7 @@ int backward_mma_partial_rows(int num_instances) {
 int launch_field_backward_mma(const SceneDev& s, const RaysDev& r, const float* adjoint, float* partials,
                               float* gloc, float* grot, float* gdim, float* gW, cudaStream_t st) {
     if (bwd5::setup()) return 1;
-    if (bwd5::g_bwd_mt == 3) return bwd5::launch<1, 1>(s, r, adjoint, partials, gloc, grot, gdim, gW, st);
-    return bwd5::g_bwd_mt == 1 ? bwd5::launch<1, 0>(s, r, adjoint, partials, gloc, grot, gdim, gW, st)
-                               : bwd5::launch<2, 0>(s, r, adjoint, partials, gloc, grot, gdim, gW, st);
+    return bwd5::launch<1, 1>(s, r, adjoint, partials, gloc, grot, gdim, gW, st);
 }
 
 }  // namespace vsrd

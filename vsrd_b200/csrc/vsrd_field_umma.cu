@@ -458,7 +458,7 @@ __global__ void __launch_bounds__(kGroups * kGroupThreads, 1) field_forward_umma
 }  // namespace fu
 
 static int g_umma_sms = 0;
-static int g_umma_groups = 4;
+constexpr int kUmmaGroups = 4;      // measured (cfg2 fine pass): 4 groups x 128 registers 0.227 ms, 3 groups x 160 registers 0.260 ms
 
 template <int kGroups>
 static void launch_umma(const SceneDev& s, const RaysDev& r, float* field, size_t total, cudaStream_t st) {
@@ -476,17 +476,12 @@ int launch_field_forward_umma(const SceneDev& s, const RaysDev& r, float* field,
         cudaDeviceProp prop;
         if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess)
             return fail("vsrd_b200: no CUDA device%s");
-        if (cudaFuncSetAttribute(fu::field_forward_umma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)fu::smem_bytes(3)) != cudaSuccess ||
-            cudaFuncSetAttribute(fu::field_forward_umma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)fu::smem_bytes(4)) != cudaSuccess)
+        if (cudaFuncSetAttribute(fu::field_forward_umma_kernel<kUmmaGroups>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)fu::smem_bytes(kUmmaGroups)) != cudaSuccess)
             return fail("vsrd_b200: cannot reserve shared memory for field_forward_umma_kernel (built for sm_100a)%s");
-        const char* g = getenv("VSRD_UMMA_GROUPS");
-        if (g && (g[0] == '3' || g[0] == '4')) g_umma_groups = g[0] - '0';
         g_umma_sms = prop.multiProcessorCount;
     }
-    if (g_umma_groups == 3) launch_umma<3>(s, r, field, total, st);
-    else launch_umma<4>(s, r, field, total, st);
+    launch_umma<kUmmaGroups>(s, r, field, total, st);
     return 0;
 }
 
