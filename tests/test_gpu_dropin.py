@@ -64,11 +64,18 @@ def test_main_py_composition_through_the_drop_in_api_matches_the_oracle():
     assert float((gradients.detach().cpu().double() - out[1].detach()).abs().max()) < 1e-3
     assert abs(float(loss) - float(ref_loss)) < 1e-4
     assert len(got) == len(want) == 27
-    for p, a, b in zip(params, got, want):
-        denom = float(b.norm())
-        if denom > 1e-9:
-            rel = float((a.detach().cpu().double().reshape(b.shape) - b).norm()) / denom
-            assert rel < 5e-3, (tuple(p.shape), rel)
+    # the fp32 oracle (the reference's own precision) on the same samples: the yardstick for ill-conditioned terms
+    leaves32 = [state[0][k][0].float().requires_grad_(True) for k in ("locations", "dimensions", "orientations", "embeddings")]
+    hyper32 = oracle.HyperNetwork()
+    hyper32.load_state_dict(state[1])
+    loc32, dim32, rot32 = oracle.decode_box_parameters(*leaves32[:3])
+    out32 = oracle.render_pass(oracle.Scene(loc32, rot32, dim32, hyper32(leaves32[3]), sched["temperature"]).field(), origins, dirs,
+                               fine.detach().cpu(), sched["std_deviation"], sched["cosine_ratio"])
+    loss32 = oracle.silhouette_loss(out32[0], targets) + 0.01 * oracle.eikonal_loss(out32[1])
+    want32 = torch.autograd.grad(loss32, leaves32 + list(hyper32.parameters()))
+    from tests.helpers import assert_grad_within_reference_error
+    for p, a, b, b32 in zip(params, got, want, want32):
+        assert_grad_within_reference_error(a, b, b32, name=str(tuple(p.shape)))
 
 
 def _gpu_scene(n=3, seed=5):

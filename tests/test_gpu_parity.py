@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from oracle import vsrd_oracle as oracle
-from tests.helpers import load_golden, rel_l2, render_kwargs, scene_from_golden
+from tests.helpers import RENDER_CASES, load_golden, rel_l2, render_kwargs, scene_from_golden
 
 pytestmark = pytest.mark.gpu
 
@@ -91,9 +91,17 @@ def test_render_pass_matches_golden(F, case):
                                                std_deviation=kw["sdf_std_deviation"], cosine_ratio=kw["cosine_ratio"])
     assert (labels.cpu() - g["labels"]).abs().max() < 1e-4                      # north_star: 1e-4 abs
     assert (weights.cpu() - _ray_major(g["fine_weights"])).abs().max() < 1e-4
+    # un-normalised union gradient (no tolerance of its own in BASELINE; it only acts through the opacities above):
+    # within 1e-3 of the fp64 reference, or 2x the fp32 reference's own distance from fp64 where that is larger
     near = (g["fine_distances"][1:] < 1e3).expand_as(g["sampled_gradients"])
-    diff = (grads.cpu().permute(1, 0, 2) - g["sampled_gradients"]).abs()
-    assert diff[near].max() < 2e-3
+    got = grads.cpu().permute(1, 0, 2)
+    if case.replace("f32", "f64") in RENDER_CASES:
+        g64 = load_golden(case.replace("f32", "f64"))
+        own = float((g["sampled_gradients"].double() - g64["sampled_gradients"]).abs()[near].max())
+        err = float((got.double() - g64["sampled_gradients"]).abs()[near].max())
+        assert err < max(1e-3, 2.0 * own), (err, own)
+    else:
+        assert (got - g["sampled_gradients"]).abs()[near].max() < 1e-3
 
 
 @pytest.mark.parametrize("case", ["box_f32", "residual_f32", "late_f32"])
@@ -162,7 +170,7 @@ def _cuda_grads(F, g, dist_rm, keep, loss_fn):
     return loss.detach().cpu(), {n: t.cpu() for n, t in zip(names, torch.autograd.grad(loss, leaves))}
 
 
-@pytest.mark.parametrize("case", ["box_f32", "residual_f32"])
+@pytest.mark.parametrize("case", ["box_f32", "residual_f32", "late_f32"])
 def test_linear_upstream_gradients_match_fp64_oracle(F, case):
     """Random linear functional of (labels, gradients, weights): isolates the kernels' adjoint from the
     ill-conditioned BCE-at-the-clamp.  north_star: parameter gradients within 1e-3 rel."""
@@ -181,14 +189,16 @@ def test_linear_upstream_gradients_match_fp64_oracle(F, case):
                 + (weights * cw.to(dev, dtype)).sum())
 
     l64, want = _oracle_grads(g, dist, keep, torch.float64, loss_fn)
+    _, want32 = _oracle_grads(g, dist, keep, torch.float32, loss_fn)
     l32, got = _cuda_grads(F, g, dist, keep, loss_fn)
     assert abs(float(l32) - float(l64)) < 1e-3 * max(1.0, abs(float(l64)))
     for n in want:
         err = rel_l2(got[n].double(), want[n])
-        assert err < 1e-3, f"{n}: rel-L2 {err}"
+        own = rel_l2(want32[n].double(), want[n])          # the fp32 reference's own error (late schedule: > 1e-3)
+        assert err < max(1e-3, 1.5 * own), f"{n}: rel-L2 {err} (fp32 reference's own error {own})"
 
 
-@pytest.mark.parametrize("case", ["box_f32", "residual_f32"])
+@pytest.mark.parametrize("case", ["box_f32", "residual_f32", "late_f32"])
 def test_training_loss_gradients(F, case):
     """BCE + 0.01 eikonal (the loss main.py optimises)."""
     g = load_golden(case)
@@ -211,7 +221,8 @@ def test_training_loss_gradients(F, case):
         e_ref = rel_l2(want32[n].double(), want64[n])
         e_32 = rel_l2(got[n].double(), want32[n].double())
         e_64 = rel_l2(got[n].double(), want64[n])
-        assert e_32 < 1e-3, f"{n}: vs fp32 oracle {e_32}"
+        # two fp32 evaluations of an ill-conditioned loss are each `e_ref` from the truth, i.e. up to 2 e_ref apart
+        assert e_32 < max(1e-3, 2.0 * e_ref), f"{n}: vs fp32 oracle {e_32} (reference's own error vs fp64 {e_ref})"
         assert e_64 < max(1e-3, 1.5 * e_ref), f"{n}: vs fp64 oracle {e_64} (reference's own error {e_ref})"
 
 
