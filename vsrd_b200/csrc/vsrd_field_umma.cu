@@ -233,7 +233,27 @@ __device__ __forceinline__ void load_biased(uint32_t taddr, const float* bias, f
     for (int i = 0; i < 8; ++i) v[i] = add2(v[i], b[i]);
 }
 
-template <int kGroups>
+// The MMAs of the eight round trips of a tile, issued by ONE thread of the group once the operands of the stage are in TMEM:
+//   0: L0, coordinates 0 and 1    1: L0, coordinate 2    2..4: hidden layers 1..3    5..7: reverse sweep through layers 3..1
+__device__ __forceinline__ void issue_stage(int stage, uint32_t tmem, uint64_t wdesc, uint32_t idesc, uint64_t* mbar) {
+    fence_after_sync();
+    if (stage == 0) {
+        mma3_16x16(tmem + kColH0, tmem + kColBuf0, tmem + kColBuf0 + 16, wdesc, kOffW0, idesc, false);
+        mma3_16x16(tmem + kColG, tmem + kColBuf0, tmem + kColBuf0 + 16, wdesc, kOffW0d, idesc, false);
+        mma3_16x16(tmem + kColH0, tmem + kColBuf1, tmem + kColBuf1 + 16, wdesc, kOffW0 + 2 * kBlk, idesc, true);
+        mma3_16x16(tmem + kColG + 16, tmem + kColBuf1, tmem + kColBuf1 + 16, wdesc, kOffW0d + 2 * kBlk, idesc, false);
+    } else if (stage == 1) {
+        mma3_16x16(tmem + kColH0, tmem + kColBuf0, tmem + kColBuf0 + 16, wdesc, kOffW0 + 4 * kBlk, idesc, true);
+        mma3_16x16(tmem + kColG + 32, tmem + kColBuf0, tmem + kColBuf0 + 16, wdesc, kOffW0d + 4 * kBlk, idesc, false);
+    } else if (stage <= 4) {
+        mma3_16x16(tmem + kColD, tmem + kColAhi, tmem + kColAlo, wdesc, kOffWl + (stage - 2) * 2 * kBlk, idesc, false);
+    } else {
+        mma3_16x16(tmem + kColD, tmem + kColAhi, tmem + kColAlo, wdesc, kOffWt + (7 - stage) * 2 * kBlk, idesc, false);
+    }
+    mma_commit(mbar);
+}
+
+template <int kGroups, bool kCull>
 __global__ void __launch_bounds__(kGroups * kGroupThreads, 1) field_forward_umma_kernel(
         SceneDev scene, RaysDev rays, float4* __restrict__ field, int tiles_per_inst) {
     static_assert(kGroups >= 1 && kGroups <= kMaxGroups, "TMEM columns");
@@ -296,94 +316,83 @@ __global__ void __launch_bounds__(kGroups * kGroupThreads, 1) field_forward_umma
             sample_position(rays, r, j, x);
             BoxEval b;
             box_eval(x, I, b);
-            bool skip = false;                             // warp-uniform: this warp's 32 samples need no residual MLP
-            if (rays.bound != nullptr) {
+            if constexpr (kCull) {
                 // instance culling (VsrdRays::union_bound): a sample farther from this box than the nearest box + the
-                // residual's range + 30 T has a soft-min weight < 1e-13: the box field suffices.  A WARP whose 32 samples
-                // are all far skips its SIMT work (it still takes part in the group's barriers; its TMEM lanes carry stale
-                // operands, which only reach its own, unread, accumulator rows); a TILE whose four warps are all far is
-                // skipped outright.
+                // residual's range + 30 T has a soft-min weight < 1e-13: the box field suffices.  A TILE whose four warps
+                // are all far is skipped outright; a WARP whose 32 samples are all far writes the box field and then only
+                // keeps the group's eight round trips company (barriers, the MMA issue if it owns the issuing thread, the
+                // mbarrier waits): its TMEM lanes carry stale operands, which only reach its own, unread, accumulator rows.
                 const bool far = !in_range || b.value - (__ldg(rays.bound + idx) + 1.0f) > cull_margin;
-                skip = __all_sync(kFull, far);
+                const bool skip = __all_sync(kFull, far);
                 int all_far;
                 asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %1, 0;\n\tbar.red.and.pred q, %2, %3, p;\n\tselp.b32 %0, 1, 0, q;\n\t}"
                              : "=r"(all_far) : "r"((int)skip), "r"(1 + group), "r"(kGroupThreads) : "memory");
                 if ((tid & 31) == 0) { ++tiles_visited; tiles_culled += skip ? 1u : 0u; }
-                if (skip && in_range)
-                    field[(size_t)inst * total + base + gt] = make_float4(
-                        b.value,
-                        I.R[0] * b.gp[0] + I.R[1] * b.gp[1] + I.R[2] * b.gp[2],
-                        I.R[3] * b.gp[0] + I.R[4] * b.gp[1] + I.R[5] * b.gp[2],
-                        I.R[6] * b.gp[0] + I.R[7] * b.gp[1] + I.R[8] * b.gp[2]);
-                if (all_far) continue;
+                if (skip) {
+                    if (in_range)
+                        field[(size_t)inst * total + base + gt] = make_float4(
+                            b.value,
+                            I.R[0] * b.gp[0] + I.R[1] * b.gp[1] + I.R[2] * b.gp[2],
+                            I.R[3] * b.gp[0] + I.R[4] * b.gp[1] + I.R[5] * b.gp[2],
+                            I.R[6] * b.gp[0] + I.R[7] * b.gp[1] + I.R[8] * b.gp[2]);
+                    if (all_far) continue;
+#pragma unroll 1
+                    for (int stage = 0; stage < 8; ++stage) {
+                        fence_before_sync();
+                        named_barrier(1 + group, kGroupThreads);
+                        if (gt == 0) issue_stage(stage, tmem, wdesc, idesc, mbar);
+                        mbar_wait(mbar, parity); parity ^= 1;
+                        fence_after_sync();
+                    }
+                    fence_before_sync();
+                    continue;
+                }
             }
             // ------------------------------------------------------------ L0: positional encoding -> h0, g_c
             f2 h[8];
             {
                 const float m[3] = {fabsf(b.p[0]), b.p[1], b.p[2]};
                 f2 e[8];
-                if (!skip) {
-                    encode16(kPiF * (m[0] / scene.scale), e);
-                    store_operand(lane_base, kColBuf0, kColBuf0 + 16, e);
-                    encode16(kPiF * (m[1] / scene.scale), e);
-                    store_operand(lane_base, kColBuf1, kColBuf1 + 16, e);
-                    wait_st();
-                }
+                encode16(kPiF * (m[0] / scene.scale), e);
+                store_operand(lane_base, kColBuf0, kColBuf0 + 16, e);
+                encode16(kPiF * (m[1] / scene.scale), e);
+                store_operand(lane_base, kColBuf1, kColBuf1 + 16, e);
+                wait_st();
                 fence_before_sync();
                 named_barrier(1 + group, kGroupThreads);
-                if (gt == 0) {
-                    fence_after_sync();
-                    mma3_16x16(tmem + kColH0, tmem + kColBuf0, tmem + kColBuf0 + 16, wdesc, kOffW0, idesc, false);
-                    mma3_16x16(tmem + kColG, tmem + kColBuf0, tmem + kColBuf0 + 16, wdesc, kOffW0d, idesc, false);
-                    mma3_16x16(tmem + kColH0, tmem + kColBuf1, tmem + kColBuf1 + 16, wdesc, kOffW0 + 2 * kBlk, idesc, true);
-                    mma3_16x16(tmem + kColG + 16, tmem + kColBuf1, tmem + kColBuf1 + 16, wdesc, kOffW0d + 2 * kBlk, idesc, false);
-                    mma_commit(mbar);
-                }
-                if (!skip) encode16(kPiF * (m[2] / scene.scale), e);   // overlaps the MMAs of coordinates 0, 1
+                if (gt == 0) issue_stage(0, tmem, wdesc, idesc, mbar);
+                encode16(kPiF * (m[2] / scene.scale), e);              // overlaps the MMAs of coordinates 0, 1
                 mbar_wait(mbar, parity); parity ^= 1;                  // ... which must be done before buffer 0 is reused
                 fence_after_sync();
-                if (!skip) {
-                    store_operand(lane_base, kColBuf0, kColBuf0 + 16, e);
-                    wait_st();
-                }
+                store_operand(lane_base, kColBuf0, kColBuf0 + 16, e);
+                wait_st();
                 fence_before_sync();
                 named_barrier(1 + group, kGroupThreads);
-                if (gt == 0) {
-                    fence_after_sync();
-                    mma3_16x16(tmem + kColH0, tmem + kColBuf0, tmem + kColBuf0 + 16, wdesc, kOffW0 + 4 * kBlk, idesc, true);
-                    mma3_16x16(tmem + kColG + 32, tmem + kColBuf0, tmem + kColBuf0 + 16, wdesc, kOffW0d + 4 * kBlk, idesc, false);
-                    mma_commit(mbar);
-                }
+                if (gt == 0) issue_stage(1, tmem, wdesc, idesc, mbar);
             }
             mbar_wait(mbar, parity); parity ^= 1;
             fence_after_sync();
-            if (!skip) load_biased(lane_base + kColH0, sW + kOffBias, h);
+            load_biased(lane_base + kColH0, sW + kOffBias, h);
             // ------------------------------------------------------------ L1..L3 + layer 4 on the SIMT pipes
             f2 abar[8];                                    // adjoint of h3 after the loop
             float out = 0.0f;
 #pragma unroll
             for (int l = 1; l <= 4; ++l) {
                 f2 z[8], a[8], g[8];
-                if (!skip) norm_gelu(h, z, a, g);
+                norm_gelu(h, z, a, g);
                 if (l < 4) {
-                    if (!skip) {
-                        float2* st = reinterpret_cast<float2*>(stash) + (l - 1) * 16 * kSS;
+                    float2* st = reinterpret_cast<float2*>(stash) + (l - 1) * 16 * kSS;
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) { st[i * kSS] = z[i]; st[(8 + i) * kSS] = g[i]; }
-                        store_operand(lane_base, kColAhi, kColAlo, a);
-                        wait_st();
-                    }
+                    for (int i = 0; i < 8; ++i) { st[i * kSS] = z[i]; st[(8 + i) * kSS] = g[i]; }
+                    store_operand(lane_base, kColAhi, kColAlo, a);
+                    wait_st();
                     fence_before_sync();
                     named_barrier(1 + group, kGroupThreads);
-                    if (gt == 0) {
-                        fence_after_sync();
-                        mma3_16x16(tmem + kColD, tmem + kColAhi, tmem + kColAlo, wdesc, kOffWl + (l - 1) * 2 * kBlk, idesc, false);
-                        mma_commit(mbar);
-                    }
+                    if (gt == 0) issue_stage(1 + l, tmem, wdesc, idesc, mbar);
                     mbar_wait(mbar, parity); parity ^= 1;
                     fence_after_sync();
-                    if (!skip) load_biased(lane_base + kColD, sW + kOffBias + 16 * l, h);
-                } else if (!skip) {
+                    load_biased(lane_base + kColD, sW + kOffBias + 16 * l, h);
+                } else {
                     // out = w4 . a4 + b4;  abar4 = w4;  hbar3 = adjoint through LayerNorm/GELU of layer 4, right here
                     const float2* w4 = reinterpret_cast<const float2*>(sW + kOffTail);
                     f2 acc = bc(0.0f), wv[8];
@@ -396,29 +405,20 @@ __global__ void __launch_bounds__(kGroups * kGroupThreads, 1) field_forward_umma
             // ------------------------------------------------------------ R3..R1: abar_l = W_l^T hbar_l, then through layer l's norm/GELU
 #pragma unroll
             for (int l = 3; l >= 1; --l) {
-                if (!skip) {
-                    store_operand(lane_base, kColAhi, kColAlo, abar);
-                    wait_st();
-                }
+                store_operand(lane_base, kColAhi, kColAlo, abar);
+                wait_st();
                 fence_before_sync();
                 named_barrier(1 + group, kGroupThreads);
-                if (gt == 0) {
-                    fence_after_sync();
-                    mma3_16x16(tmem + kColD, tmem + kColAhi, tmem + kColAlo, wdesc, kOffWt + (l - 1) * 2 * kBlk, idesc, false);
-                    mma_commit(mbar);
-                }
+                if (gt == 0) issue_stage(8 - l, tmem, wdesc, idesc, mbar);
                 mbar_wait(mbar, parity); parity ^= 1;
                 fence_after_sync();
-                if (!skip) {
-                    f2 ab[8], z[8], g[8];
-                    const float2* st = reinterpret_cast<const float2*>(stash) + (l - 1) * 16 * kSS;
+                f2 ab[8], z[8], g[8];
+                const float2* st = reinterpret_cast<const float2*>(stash) + (l - 1) * 16 * kSS;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) { z[i] = st[i * kSS]; g[i] = st[(8 + i) * kSS]; }
-                    load_pairs(lane_base + kColD, ab);
-                    norm_gelu_adjoint(ab, z, g, abar);                                    // abar <- hbar_{l-1}
-                }
+                for (int i = 0; i < 8; ++i) { z[i] = st[i * kSS]; g[i] = st[(8 + i) * kSS]; }
+                load_pairs(lane_base + kColD, ab);
+                norm_gelu_adjoint(ab, z, g, abar);                                        // abar <- hbar_{l-1}
             }
-            if (skip) { fence_before_sync(); continue; }
             // ------------------------------------------------------------ d out / d a_c = hbar0 . g_c
             float ga[3];
 #pragma unroll
@@ -466,8 +466,12 @@ static void launch_umma(const SceneDev& s, const RaysDev& r, float* field, size_
     const long long all_tiles = (long long)s.N * tiles_per_inst;
     const long long want = (all_tiles + kGroups - 1) / kGroups;
     const int grid = (int)(want < g_umma_sms ? want : g_umma_sms);
-    fu::field_forward_umma_kernel<kGroups><<<grid, kGroups * fu::kGroupThreads, fu::smem_bytes(kGroups), st>>>(
-        s, r, (float4*)field, tiles_per_inst);
+    if (r.bound != nullptr)        // instance culling on (fine pass): the variant with the per-warp skip logic
+        fu::field_forward_umma_kernel<kGroups, true><<<grid, kGroups * fu::kGroupThreads, fu::smem_bytes(kGroups), st>>>(
+            s, r, (float4*)field, tiles_per_inst);
+    else
+        fu::field_forward_umma_kernel<kGroups, false><<<grid, kGroups * fu::kGroupThreads, fu::smem_bytes(kGroups), st>>>(
+            s, r, (float4*)field, tiles_per_inst);
 }
 
 int launch_field_forward_umma(const SceneDev& s, const RaysDev& r, float* field, size_t total, cudaStream_t st) {
@@ -476,7 +480,9 @@ int launch_field_forward_umma(const SceneDev& s, const RaysDev& r, float* field,
         cudaDeviceProp prop;
         if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess)
             return fail("vsrd_b200: no CUDA device%s");
-        if (cudaFuncSetAttribute(fu::field_forward_umma_kernel<kUmmaGroups>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        if (cudaFuncSetAttribute(fu::field_forward_umma_kernel<kUmmaGroups, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)fu::smem_bytes(kUmmaGroups)) != cudaSuccess ||
+            cudaFuncSetAttribute(fu::field_forward_umma_kernel<kUmmaGroups, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)fu::smem_bytes(kUmmaGroups)) != cudaSuccess)
             return fail("vsrd_b200: cannot reserve shared memory for field_forward_umma_kernel (built for sm_100a)%s");
         g_umma_sms = prop.multiProcessorCount;

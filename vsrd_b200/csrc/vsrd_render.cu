@@ -219,7 +219,7 @@ struct LossDev {
 constexpr int kRegsMaxInstances = 16;
 
 template <int NMAX>
-__global__ void __launch_bounds__(VSRD_MAX_INTERVALS) composite_forward_kernel(
+__global__ void __launch_bounds__(VSRD_MAX_INTERVALS, NMAX <= 8 ? 2 : 1) composite_forward_kernel(
         SceneDev scene, RaysDev rays, float sigma, float rho, float eps, const float4* __restrict__ field,
         float* __restrict__ labels, float* __restrict__ grads, float* __restrict__ weights,
         LossDev loss, float* __restrict__ loss_out) {
@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(VSRD_MAX_INTERVALS) composite_forward_kernel(
 // (transmittance prefix product, suffix sum of a_k omega_k).
 // =============================================================================================
 template <int NMAX>
-__global__ void __launch_bounds__(VSRD_MAX_INTERVALS) composite_backward_kernel(
+__global__ void __launch_bounds__(VSRD_MAX_INTERVALS, NMAX <= 8 ? 2 : 1) composite_backward_kernel(
         SceneDev scene, RaysDev rays, float sigma, float rho, float eps, const float4* __restrict__ field,
         const float* __restrict__ grad_labels, const float* __restrict__ grad_grads, const float* __restrict__ grad_weights,
         LossDev loss, const float* __restrict__ labels, float4* __restrict__ adjoint, int tile_shift, int tiles_per_inst) {

@@ -108,14 +108,16 @@ __device__ __forceinline__ void mbar_init(uint64_t* mbar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(mbar)), "r"(count) : "memory");
 }
 __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// The suspend-time hint lets the hardware park the warp until the phase completes (or ~10 ms pass) instead of polling:
+// without it the spin loop of the waiting warps took 12 % of the issued instructions (profiles/r02_field_forward_umma_*).
 __device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
     asm volatile("{\n\t.reg .pred p;\n\t"
                  "WAIT_%=:\n\t"
-                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
                  "@p bra DONE_%=;\n\t"
                  "bra WAIT_%=;\n\t"
                  "DONE_%=:\n\t}"
-                 :: "r"(smem_u32(mbar)), "r"(parity) : "memory");
+                 :: "r"(smem_u32(mbar)), "r"(parity), "r"(0x989680u) : "memory");
 }
 // named barrier over `threads` threads (ids 1..15; 0 is __syncthreads)
 __device__ __forceinline__ void named_barrier(int id, int threads) {
