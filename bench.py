@@ -21,7 +21,7 @@ Unit of work: ray-samples = R * ((S-1) + (2S-1)) per step.
   frames      whole frames labelled per hour through vsrd_b200.sequence.label_sequence over a cfg5 frame list
               (N ~ Poisson(6) clipped to [1,24], 4 frames per rank, several in flight per GPU) INCLUDING the final NCCL
               all_gather of the boxes; per-rank min / max seconds for the DistributedSampler and the balanced partition.
-  roofline    dominant kernel (field backward) against the FP32-FMA peak.
+  roofline    dominant kernel (field backward, mma.sync 3xTF32) against the FP32-FMA peak; `forward_fine` = the tcgen05 forward.
   cpu_baseline  the reference's own modules (staged under baseline/_ref, oracle/reference_step.py) on the host cores,
               bounded sample; the oracle port when the staged reference is absent.  The same leg checks the device
               leg's labels / loss of one batch against the oracle.
@@ -757,7 +757,7 @@ def run_native(args):
                          "bound_note": "issue-bound FP32 work between 3xTF32 mma.sync contractions: DRAM traffic is one pass over "
                                        "the adjoint buffer (26 MB per launch, 0.5 % of the HBM roofline) and the tensor pipe is "
                                        "~30 % busy, so the kernel is rated against the FP32 FMA peak (DESIGN.md section 3)",
-                         "forward_fine": {"kernel": "field_forward_mma_kernel<2>", "kernel_ms": per_kernel.get("field_forward_fine"),
+                         "forward_fine": {"kernel": "field_forward_umma_kernel<4, cull> (tcgen05 / TMEM, vsrd_field_umma.cu)", "kernel_ms": per_kernel.get("field_forward_fine"),
                                           "achieved": (2 * F_MLP * args.instances * args.rays * m_fine
                                                        / (per_kernel["field_forward_fine"] * 1e-3) / 1e12)
                                           if per_kernel.get("field_forward_fine") else None,
