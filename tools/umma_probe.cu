@@ -13,6 +13,9 @@
 #include <cstdlib>
 #include <vector>
 
+#include <cuda_bf16.h>
+#include <cstring>
+
 #include "../vsrd_b200/csrc/vsrd_umma.cuh"
 
 using namespace vsrd::umma;
@@ -215,6 +218,58 @@ __global__ void __launch_bounds__(128) wgrad_kernel(WgParams p) {
     if (warp == 0) tmem_free<32>(tmem);
 }
 
+// T5: the weight-gradient contraction as shipped: bf16 operands staged K-major SWIZZLE_128B with the SAMPLES along K
+//     (thread s writes element (row f, column s) of both operands), D[f][o] = sum_s act[s][f] * adj[s][o], fp32 accumulate.
+//     A: F <= 24 rows (3 atoms of 8 rows per 64-sample k-block; the MMA reads 16 atoms = garbage rows beyond), B: 16 rows.
+__device__ __forceinline__ uint32_t sw128_offset(int row, int sample) {      // bytes inside one k-block region of `atoms` atoms
+    const int sp = sample & 63, chunk = sp >> 3, e = sp & 7;
+    return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + (((chunk ^ (row & 7)) << 4)) + e * 2);
+}
+__global__ void __launch_bounds__(128) wgrad_bf16_kernel(WgParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_b[];
+    __shared__ uint64_t mbar;
+    __shared__ uint32_t tmem_base_slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    // layout: A [2 k-blocks][3 atoms][1024], then B [2][2][1024], then 32 KB of slack for the A window
+    unsigned char* sA = smem_b;
+    unsigned char* sB = smem_b + 2 * 3 * 1024;
+    if (warp == 0) tmem_alloc<32>(&tmem_base_slot);
+    if (tid == 0) { mbar_init(&mbar, 1); mbar_fence_init(); }
+    for (int i = tid; i < (2 * 3 * 1024 + 2 * 2 * 1024 + 32768) / 4; i += 128) reinterpret_cast<uint32_t*>(smem_b)[i] = 0x7fc07fc0u;  // bf16 NaNs
+    __syncthreads();
+    {
+        const int s = tid, kb = s >> 6;
+        for (int f = 0; f < p.F; ++f)
+            *reinterpret_cast<__nv_bfloat16*>(sA + kb * 3 * 1024 + sw128_offset(f, s)) = __float2bfloat16_rn(p.act[s * p.F + f]);
+        for (int o = 0; o < 16; ++o)
+            *reinterpret_cast<__nv_bfloat16*>(sB + kb * 2 * 1024 + sw128_offset(o, s)) = __float2bfloat16_rn(p.adj[s * 16 + o]);
+    }
+    fence_proxy_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    const uint32_t tmem = tmem_base_slot;
+    if (tid == 0) {
+        fence_after_sync();
+        const uint32_t idesc = make_idesc_bf16(128, 16);
+        for (int ks = 0; ks < 8; ++ks) {
+            const uint64_t da = make_smem_desc_sw128(smem_u32(sA) + (ks >> 2) * 3 * 1024 + (ks & 3) * 32, 1024);
+            const uint64_t db = make_smem_desc_sw128(smem_u32(sB) + (ks >> 2) * 2 * 1024 + (ks & 3) * 32, 1024);
+            mma_bf16_ss(tmem, da, db, idesc, ks > 0);
+        }
+        mma_commit(&mbar);
+    }
+    mbar_wait(&mbar, 0);
+    fence_after_sync();
+    float d[16];
+    tmem_ld16(tmem + ((uint32_t)(32 * warp) << 16), d);
+    wait_ld();
+    if (tid < p.F)
+        for (int o = 0; o < 16; ++o) p.D[tid * 16 + o] = d[o];
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_free<32>(tmem);
+}
+
 // T4: G groups of 128 threads, each looping `iters` round trips of a 16 -> 16 layer (6 MMAs per round trip)
 template <int G>
 __global__ void __launch_bounds__(128 * G) latency_kernel(int iters, float* out, long long* cycles) {
@@ -374,6 +429,30 @@ int main() {
                 }
             printf("T3 weight gradient F=%d, %dxTF32 (SS, MN-major): max abs error %.3e (max |ref| %.2f)\n", F, passes, e, scale);
         }
+    }
+    // ---- T5: bf16 SWIZZLE_128B K-major weight gradient
+    for (int F : {16, 17, 24}) {
+        std::vector<float> act(128 * F), adj(128 * 16), W(F * 16);
+        for (auto& v : act) v = (float)rand() / RAND_MAX * 2 - 1;
+        for (auto& v : adj) v = (float)rand() / RAND_MAX * 2 - 1;
+        CK(cudaMemcpy(dA, act.data(), act.size() * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(dB, adj.data(), adj.size() * 4, cudaMemcpyHostToDevice));
+        const size_t smem = 2 * 3 * 1024 + 2 * 2 * 1024 + 32768 + 1024;
+        CK(cudaFuncSetAttribute(wgrad_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        wgrad_bf16_kernel<<<1, 128, smem>>>(WgParams{dA, dB, dD, F, 1});
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(W.data(), dD, W.size() * 4, cudaMemcpyDeviceToHost));
+        auto bf = [](float x) { uint32_t u; memcpy(&u, &x, 4); u = (u + 0x7fffu + ((u >> 16) & 1u)) & 0xffff0000u; memcpy(&x, &u, 4); return x; };
+        double e = 0.0, eb = 0.0, scale = 0.0;
+        for (int f = 0; f < F; ++f)
+            for (int o = 0; o < 16; ++o) {
+                double ref = 0.0, refb = 0.0;
+                for (int s = 0; s < 128; ++s) { ref += (double)act[s * F + f] * adj[s * 16 + o]; refb += (double)bf(act[s * F + f]) * bf(adj[s * 16 + o]); }
+                e = fmax(e, fabs(ref - W[f * 16 + o]));
+                eb = fmax(eb, fabs(refb - W[f * 16 + o]));
+                scale = fmax(scale, fabs(ref));
+            }
+        printf("T5 weight gradient F=%d, bf16 SW128 K-major SS: max abs error vs fp64 %.3e, vs bf16-rounded operands %.3e (max |ref| %.2f)\n", F, e, eb, scale);
     }
     // ---- T4: latency / throughput
     float* dout; long long* dcyc;

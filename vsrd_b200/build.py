@@ -18,8 +18,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ_DIR = os.path.join(HERE, "_obj")
 LIB_PATH = os.path.join(HERE, "libvsrd_b200.so")
-SOURCES = ["vsrd_render.cu", "vsrd_field_fwd.cu", "vsrd_field_umma.cu", "vsrd_field_bwd.cu", "vsrd_field_bwd_mma.cu", "vsrd_frame.cu", "vsrd_surface.cu", "vsrd_model.cu"]
-HEADERS = ["vsrd_common.cuh", "vsrd_math.cuh", "vsrd_frag.cuh", "vsrd_umma.cuh", "vsrd_frame_math.cuh", os.path.join("..", "..", "include", "vsrd_b200.h")]
+SOURCES = ["vsrd_render.cu", "vsrd_field_fwd.cu", "vsrd_field_umma.cu", "vsrd_field_bwd_umma.cu", "vsrd_field_bwd.cu", "vsrd_field_bwd_mma.cu", "vsrd_frame.cu", "vsrd_surface.cu", "vsrd_model.cu"]
+HEADERS = ["vsrd_common.cuh", "vsrd_math.cuh", "vsrd_frag.cuh", "vsrd_umma.cuh", "vsrd_umma_field.cuh", "vsrd_frame_math.cuh", os.path.join("..", "..", "include", "vsrd_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",

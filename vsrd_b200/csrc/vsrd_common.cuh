@@ -118,6 +118,10 @@ int backward_mma_tile_rows();         // samples per warp tile (16 or 32); -1 on
 int launch_field_backward_mma(const SceneDev& s, const RaysDev& r, const float* adjoint, float* partials,
                               float* gloc, float* grot, float* gdim, float* gW, cudaStream_t st);
 
+// vsrd_field_bwd_umma.cu: tcgen05 / TMEM field backward for residual instances (same partial-row protocol)
+int launch_field_backward_umma(const SceneDev& s, const RaysDev& r, const float* adjoint, float* partials,
+                               float* gloc, float* grot, float* gdim, float* gW, cudaStream_t st);
+
 // vsrd_field_umma.cu: tcgen05 / TMEM field forward for residual instances (one thread == one sample).
 int launch_field_forward_umma(const SceneDev& s, const RaysDev& r, float* field, size_t total, cudaStream_t st);
 

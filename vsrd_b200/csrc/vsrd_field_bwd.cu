@@ -207,6 +207,12 @@ int vsrd_field_backward(const VsrdScene* scene, const VsrdRays* rays, const floa
     cudaStream_t st = (cudaStream_t)stream;
     const size_t total = (size_t)r.R * r.M;
     VSRD_CHECK_ARG(total < (size_t)1 << 31, "R*M must be < 2^31");
+    if (total > 0 && s.W) {
+        const char* impl = getenv("VSRD_BWD_IMPL");           // A/B switch while the tcgen05 backward is being validated
+        if (impl && strcmp(impl, "umma") == 0)
+            return launch_field_backward_umma(s, r, adjoint, partials, grad_locations, grad_rotations, grad_half_extents,
+                                              grad_mlp_weights, st);
+    }
     if (total > 0 && s.W)
         return launch_field_backward_mma(s, r, adjoint, partials, grad_locations, grad_rotations, grad_half_extents,
                                          grad_mlp_weights, st);

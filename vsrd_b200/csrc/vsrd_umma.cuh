@@ -85,6 +85,23 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
          | ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
 }
 
+// bf16 x bf16 -> fp32 (kind::f16): a_format = b_format = 1 (BF16), K = 16 per instruction
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+// K-major SWIZZLE_128B operand (layout type 2): rows of 128 bytes, 8-row atoms of 1024 bytes (1024-byte aligned), the
+// 16-byte chunk c of row r stored at chunk position c ^ (r % 8); SBO = byte distance between 8-row atoms, LBO unused (1).
+// A k-step inside the 128-byte row advances the start address by 32 bytes.
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uint32_t sbo_bytes) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32)
+         | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void mma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, bool accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
+}
+
 // ---- MMA issue (ONE thread) ----------------------------------------------------------------------------------------
 // D[tmem_d] (+)= A[tmem_a : 128 lanes x 8 columns] * B[smem desc : N x 8]^T
 __device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, bool accumulate) {
