@@ -189,6 +189,14 @@ int vsrd_field_backward(const VsrdScene* scene, const VsrdRays* rays, const floa
                         float* grad_locations, float* grad_rotations, float* grad_half_extents,
                         float* grad_mlp_weights, void* stream);
 
+/* EXPERIMENT, not called by anything the package ships: vsrd_field_backward's contract served by a
+ * tcgen05 / TMEM kernel (residual instances only, R*M > 0).  Measured slower than the shipped kernel, and its MLP weight
+ * gradients carry the rounding of bf16 operand staging (2e-3 relative); kept so that the measurement can be repeated
+ * (tools/compare_backward.py). */
+int vsrd_experimental_field_backward_tcgen05(const VsrdScene* scene, const VsrdRays* rays, const float* adjoint,
+                                             float* partials, float* grad_locations, float* grad_rotations,
+                                             float* grad_half_extents, float* grad_mlp_weights, void* stream);
+
 /* ---- a14 + a15: multi-view box projection, matching and projection losses, forward and adjoint in
  * ONE launch (scripts/main.py:339-415; operations/geometric_operations.py:343-389 project_box_3d and
  * clip_lines_to_front; torchvision clip_boxes_to_image / distance_box_iou / distance_box_iou_loss;

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""A/B of the two field-backward kernels on one scene (VSRD_BWD_IMPL is read per call): relative differences of the
-four gradients and CUDA-event timings.   python tools/compare_backward.py [--cfg cfg2] [--rays 1000] [--reps 10]"""
+"""A/B of the shipped field-backward kernel ("mma": mma.sync, fragments in registers) and the experimental tcgen05 /
+TMEM one ("umma", ops.experimental_field_backward_tcgen05) on one scene: relative differences of the four gradients
+and CUDA-event timings.   python tools/compare_backward.py [--cfg cfg2] [--rays 1000] [--reps 10]"""
 import argparse
 import os
 import sys
@@ -31,16 +32,15 @@ if a.sparse > 0:
     keep = (torch.rand(r, generator=gen) >= a.sparse).to(dev)
     adj = (adj.reshape(adj.shape[0], r, -1, 4) * keep[None, :, None, None]).reshape(adj.shape)
 out, times = {}, {}
-for impl in ("mma", "umma"):
-    os.environ["VSRD_BWD_IMPL"] = impl
-    g = ops.field_backward(scene, rays, adj)
+for impl, backward in (("mma", ops.field_backward), ("umma", ops.experimental_field_backward_tcgen05)):
+    g = backward(scene, rays, adj)
     torch.cuda.synchronize()
     out[impl] = [t.clone() for t in g]
     ts = []
     for _ in range(a.reps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        ops.field_backward(scene, rays, adj)
+        backward(scene, rays, adj)
         e1.record()
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))

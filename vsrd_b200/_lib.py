@@ -179,6 +179,7 @@ SIGNATURES = {
     "vsrd_composite_backward": (_I, [_P(VsrdScene), _P(VsrdRays), _P(VsrdRenderParams), _V, _V, _V, _V,
                                      _P(VsrdLoss), _V, _V, _V]),
     "vsrd_field_backward": (_I, [_P(VsrdScene), _P(VsrdRays), _V, _V, _V, _V, _V, _V, _V]),
+    "vsrd_experimental_field_backward_tcgen05": (_I, [_P(VsrdScene), _P(VsrdRays), _V, _V, _V, _V, _V, _V, _V]),
     "vsrd_projection_scratch_floats": (ctypes.c_size_t, [_I, _I]),
     "vsrd_project_box_3d": (_I, [_V, _I, _V, ctypes.c_float, _V, _V]),
     "vsrd_project_box_3d_backward": (_I, [_V, _I, _V, ctypes.c_float, _V, _V, _V]),

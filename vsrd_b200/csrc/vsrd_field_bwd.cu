@@ -207,12 +207,6 @@ int vsrd_field_backward(const VsrdScene* scene, const VsrdRays* rays, const floa
     cudaStream_t st = (cudaStream_t)stream;
     const size_t total = (size_t)r.R * r.M;
     VSRD_CHECK_ARG(total < (size_t)1 << 31, "R*M must be < 2^31");
-    if (total > 0 && s.W) {
-        const char* impl = getenv("VSRD_BWD_IMPL");           // A/B switch while the tcgen05 backward is being validated
-        if (impl && strcmp(impl, "umma") == 0)
-            return launch_field_backward_umma(s, r, adjoint, partials, grad_locations, grad_rotations, grad_half_extents,
-                                              grad_mlp_weights, st);
-    }
     if (total > 0 && s.W)
         return launch_field_backward_mma(s, r, adjoint, partials, grad_locations, grad_rotations, grad_half_extents,
                                          grad_mlp_weights, st);
@@ -230,6 +224,22 @@ int vsrd_field_backward(const VsrdScene* scene, const VsrdRays* rays, const floa
                                                  s.W ? grad_mlp_weights : nullptr);
     VSRD_CHECK_LAUNCH();
     return 0;
+}
+
+// EXPERIMENT, not on the product path: the same contract served by the tcgen05 / TMEM kernel of
+// vsrd_field_bwd_umma.cu.  Slower than the shipped kernel and its weight gradients carry bf16 staging error (2e-3).
+int vsrd_experimental_field_backward_tcgen05(const VsrdScene* scene, const VsrdRays* rays, const float* adjoint, float* partials,
+                                             float* grad_locations, float* grad_rotations, float* grad_half_extents,
+                                             float* grad_mlp_weights, void* stream) {
+    SceneDev s; RaysDev r;
+    if (check_scene(scene, s) || check_rays(rays, r)) return 1;
+    VSRD_CHECK_ARG(adjoint && partials && grad_locations && grad_rotations && grad_half_extents && grad_mlp_weights, "NULL pointer");
+    VSRD_CHECK_ARG(s.W != nullptr, "the tcgen05 backward serves residual instances only");
+    if (device_setup()) return 1;
+    const size_t total = (size_t)r.R * r.M;
+    VSRD_CHECK_ARG(total > 0 && total < (size_t)1 << 31, "R*M must be in [1, 2^31)");
+    return launch_field_backward_umma(s, r, adjoint, partials, grad_locations, grad_rotations, grad_half_extents,
+                                      grad_mlp_weights, (cudaStream_t)stream);
 }
 
 }  // extern "C"

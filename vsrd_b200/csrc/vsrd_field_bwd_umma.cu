@@ -37,6 +37,7 @@ constexpr int kColBuf0 = 0, kColBuf1 = 32;     // L0 / RL0 operand buffers (hi 1
 constexpr int kColA = 0, kColAd = 32;          // hidden / reverse operands: value hi|lo [0,32), tangent hi|lo [32,64)
 constexpr int kColD = 64, kColDd = 80;         // accumulators: h | gbar | g_c [64,80), hd | gdbar | k_c [80,96)
 constexpr int kColG1 = 96;                     // second g_c of the forward L0 [96,112)
+constexpr int kColPark = 96;                   // after L0: layer 3's (z, zd) parked across layer 4 [96,128)
 constexpr int kColsPerGroup = 128;
 constexpr int kColDw = kGroups * kColsPerGroup;          // 384: dW0_c at +16 c (c = 0..2), dW_l at +48 + 16 (l - 1) (l = 1..3)
 static_assert(kColDw + 96 <= 512, "TMEM columns");
@@ -61,8 +62,10 @@ constexpr int kOffTail = kOffBias + 4 * 16;                // w4[16], b4
 constexpr int kWeightFloats = kOffTail + 32;
 constexpr int kStashPairs = 2 * 16;                        // per thread: layers 1, 2 x (z 8 pairs, zd 8 pairs)
 constexpr int kRedFloats = 32;                             // layer-4 weight gradient (17) + pose (15)
-constexpr size_t kSmemBytes = 1024 + (size_t)kGroups * kStageBytes + (size_t)(kWeightFloats + kRedFloats) * 4
-                            + (size_t)kThreadsB * kStashPairs * 8;
+constexpr int kInstFloats = 16;                            // the segment's instance: t, half extents, R
+constexpr int kParkFloats = 15;                            // per thread, across the MLP: dG, x - t, and the box part of dimbar, pbar, vbar
+constexpr size_t kSmemBytes = 1024 + (size_t)kGroups * kStageBytes + (size_t)(kWeightFloats + kRedFloats + kInstFloats) * 4
+                            + (size_t)kThreadsB * kStashPairs * 8 + (size_t)kThreadsB * kParkFloats * 4;
 
 __device__ void stage_weights_bwd(const float* __restrict__ W, float* sW) {
     for (int i = threadIdx.x; i < kHid * kEnc; i += blockDim.x) {                         // layer 0 and its a-derivatives
@@ -115,19 +118,6 @@ __device__ __forceinline__ void norm_gelu_dual(const f2 (&h)[8], const f2 (&hd)[
         const f2 d1 = fma2(z[i], phi, Phi);
         ad[i] = mul2(d1, zd[i]);
         if (kTerms) { g1[i] = d1; g2[i] = mul2(phi, fma2(z[i], mul2(z[i], bc(-1.0f)), bc(2.0f))); }
-    }
-}
-
-// the GELU terms of a stashed layer again: a = z Phi, g1 = gelu'(z), g2 = gelu''(z) = phi (2 - z^2), ad = g1 zd
-__device__ __forceinline__ void gelu_again(const f2 (&z)[8], const f2 (&zd)[8], f2 (&a)[8], f2 (&ad)[8], f2 (&g1)[8], f2 (&g2)[8]) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        f2 Phi, phi;
-        gelu_terms2(z[i], Phi, phi);
-        a[i] = mul2(z[i], Phi);
-        g1[i] = fma2(z[i], phi, Phi);
-        ad[i] = mul2(g1[i], zd[i]);
-        g2[i] = mul2(phi, fma2(z[i], mul2(z[i], bc(-1.0f)), bc(2.0f)));
     }
 }
 
@@ -197,8 +187,10 @@ __device__ __forceinline__ void mma_wgrad(uint32_t tmem_d, uint32_t stage_addr, 
 }
 
 // stages: 0 L0 (c = 0, 1)   1 L0 (c = 2)   2..4 hidden l = 1..3   5..7 reverse l = 3..1   8..10 reverse L0 c = 0..2
+// The weight-gradient chain of a stage is issued AFTER the commit the group waits on, so it runs on the tensor pipe under
+// the group's next SIMT phase; its own commit (mbar_w) guards the staging buffers and the final readout.
 __device__ __forceinline__ void issue_stage(int stage, uint32_t tmem, uint32_t tmem_dw, uint64_t wdesc, uint32_t stage_addr,
-                                            uint32_t idesc, uint32_t idesc_bf16, uint64_t* mbar) {
+                                            uint32_t idesc, uint32_t idesc_bf16, uint64_t* mbar, uint64_t* mbar_w) {
     fence_after_sync();
     if (stage == 0) {
         mma3_16x16(tmem + kColD, tmem + kColBuf0, tmem + kColBuf0 + 16, wdesc, kOffW0, idesc, false);
@@ -216,12 +208,18 @@ __device__ __forceinline__ void issue_stage(int stage, uint32_t tmem, uint32_t t
         const int l = 8 - stage;
         mma3_16x16(tmem + kColD, tmem + kColA, tmem + kColA + 16, wdesc, kOffWt + (l - 1) * 2 * kBlk, idesc, false);
         mma3_16x16(tmem + kColDd, tmem + kColAd, tmem + kColAd + 16, wdesc, kOffWt + (l - 1) * 2 * kBlk, idesc, false);
+        mma_commit(mbar);
         mma_wgrad(tmem_dw + 48 + 16 * (l - 1), stage_addr, idesc_bf16);
+        mma_commit(mbar_w);
+        return;
     } else {
         const int c = stage - 8;
         mma3_16x16(tmem + kColD, tmem + kColBuf0, tmem + kColBuf0 + 16, wdesc, kOffW0d + c * 2 * kBlk, idesc, false);
         mma3_16x16(tmem + kColDd, tmem + kColBuf0, tmem + kColBuf0 + 16, wdesc, kOffW0dd + c * 2 * kBlk, idesc, false);
+        mma_commit(mbar);
         mma_wgrad(tmem_dw + 16 * c, stage_addr, idesc_bf16);
+        mma_commit(mbar_w);
+        return;
     }
     mma_commit(mbar);
 }
@@ -233,15 +231,33 @@ __device__ __forceinline__ float dot16(const f2 (&a)[8], const f2 (&b)[8]) {
     return acc.x + acc.y;
 }
 
+// Sum 16 per-lane values over the warp with a transposing butterfly (16 shuffles): afterwards lane L holds the warp total
+// of value (L >> 1); the even lanes add theirs to red[0..15].  Keeps no accumulator alive across tiles.
+__device__ __forceinline__ void warp_sum16_to_smem(float (&v)[16], int lane, float* red) {
+#pragma unroll
+    for (int half = 8, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
+        const bool up = (lane & bit) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const float send = up ? v[i] : v[i + half];
+            const float keep = up ? v[i + half] : v[i];
+            v[i] = keep + __shfl_xor_sync(kFull, send, bit);
+        }
+    }
+    v[0] += __shfl_xor_sync(kFull, v[0], 1);
+    if ((lane & 1) == 0) atomicAdd(red + (lane >> 1), v[0]);
+}
+
 __global__ void __launch_bounds__(kThreadsB, 1) field_backward_umma_kernel(
         SceneDev scene, RaysDev rays, const float4* __restrict__ adjoint, float* __restrict__ partials, int tiles_per_inst) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    __shared__ uint64_t s_mbar[kGroups];
+    __shared__ uint64_t s_mbar[kGroups], s_mbar_w[kGroups];
     __shared__ uint32_t s_tmem_base;
     unsigned char* sStage = smem_raw;                                                    // 1024-byte aligned atoms
     float* sW = reinterpret_cast<float*>(smem_raw + kGroups * kStageBytes);
     float* sRed = sW + kWeightFloats;
-    float2* sStash = reinterpret_cast<float2*>(sRed + kRedFloats);
+    float* sInst = sRed + kRedFloats;
+    float2* sStash = reinterpret_cast<float2*>(sInst + kInstFloats);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int group = warp >> 2, wq = warp & 3, gt = tid & (kGroupThreads - 1);
@@ -249,11 +265,12 @@ __global__ void __launch_bounds__(kThreadsB, 1) field_backward_umma_kernel(
     constexpr int kSS = kGroupThreads;
     unsigned char* stage = sStage + group * kStageBytes;
     const StageOffsets so = stage_offsets(gt);
+    float* park = reinterpret_cast<float*>(sStash + (size_t)kThreadsB * kStashPairs) + tid;   // [value][thread]
 
     if (warp == 0) tmem_alloc<512>(&s_tmem_base);
     if (tid == 0) {
 #pragma unroll
-        for (int g = 0; g < kGroups; ++g) mbar_init(&s_mbar[g], 1);
+        for (int g = 0; g < kGroups; ++g) { mbar_init(&s_mbar[g], 1); mbar_init(&s_mbar_w[g], 1); }
         mbar_fence_init();
     }
     for (int i = tid; i < kGroups * 2 * kAtom / 4; i += kThreadsB) {                   // the zero atoms of the tangent-pass act operand
@@ -270,7 +287,9 @@ __global__ void __launch_bounds__(kThreadsB, 1) field_backward_umma_kernel(
     const uint64_t wdesc = make_smem_desc(smem_u32(sW), kLbo, kSbo);
     const uint32_t stage_addr = smem_u32(stage);
     uint64_t* mbar = &s_mbar[group];
-    uint32_t parity = 0;
+    uint64_t* mbar_w = &s_mbar_w[group];
+    uint32_t parity = 0, parity_w = 0;
+    bool wgrad_pending = false;                            // group-uniform: a weight-gradient chain may still read the staging buffers
 
     const int total = rays.R * rays.M;
     const long long all_tiles = (long long)scene.N * tiles_per_inst;
@@ -286,6 +305,10 @@ __global__ void __launch_bounds__(kThreadsB, 1) field_backward_umma_kernel(
         __syncthreads();                                   // every group is done with the previous instance
         stage_weights_bwd(scene.W + (size_t)inst * kNumW, sW);
         if (tid < kRedFloats) sRed[tid] = 0.0f;
+        if (tid >= 32 && tid < 47) {
+            const int k = tid - 32;
+            sInst[k] = k < 3 ? __ldg(scene.loc + 3 * inst + k) : k < 6 ? __ldg(scene.dim + 3 * inst + k - 3) : __ldg(scene.rot + 9 * inst + k - 6);
+        }
         if (warp == 0) {                                   // zero the weight-gradient accumulators (lanes 0..31 are all that is read)
             float zero[16];
 #pragma unroll
@@ -298,15 +321,6 @@ __global__ void __launch_bounds__(kThreadsB, 1) field_backward_umma_kernel(
         fence_before_sync();
         __syncthreads();
         fence_after_sync();
-        Instance I;
-        load_instance(scene, inst, I);
-        float pose[15];
-#pragma unroll
-        for (int k = 0; k < 15; ++k) pose[k] = 0.0f;
-        f2 dw4[8];                                         // layer-4 weight gradient, this thread's share
-#pragma unroll
-        for (int i = 0; i < 8; ++i) dw4[i] = bc(0.0f);
-        float db4 = 0.0f;
 
 #pragma unroll 1
         for (long long tile = seg + group; tile < seg_end; tile += kGroups) {
@@ -326,11 +340,18 @@ __global__ void __launch_bounds__(kThreadsB, 1) field_backward_umma_kernel(
             }
             const int r = idx / rays.M;
             const int j = idx - r * rays.M;
+            const float dd = adj.x;
+            float m[3], coef[3], adot[3];
+            {
             float x[3];
             sample_position(rays, r, j, x);
+            Instance I;                                    // read from shared memory where it is used, not held across the tile
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { I.t[k] = sInst[k]; I.dim[k] = sInst[3 + k]; }
+#pragma unroll
+            for (int k = 0; k < 9; ++k) I.R[k] = sInst[6 + k];
             BoxEval b;
             box_eval(x, I, b);
-            const float dd = adj.x;
             const float dG[3] = {adj.y, adj.z, adj.w};
             float v[3], pbar[3], vbar[3], dimbar[3];
 #pragma unroll
@@ -349,9 +370,18 @@ __global__ void __launch_bounds__(kThreadsB, 1) field_backward_umma_kernel(
                     vbar[k] = b.gp[k];
                 }
             }
-            const float m[3] = {fabsf(b.p[0]), b.p[1], b.p[2]};
-            const float coef[3] = {b.s[0] * pi_scale, pi_scale, pi_scale};
-            const float adot[3] = {coef[0] * v[0], coef[1] * v[1], coef[2] * v[2]};
+            m[0] = fabsf(b.p[0]); m[1] = b.p[1]; m[2] = b.p[2];
+            coef[0] = b.s[0] * pi_scale; coef[1] = pi_scale; coef[2] = pi_scale;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                adot[k] = coef[k] * v[k];
+                park[(0 + k) * kThreadsB] = dG[k];
+                park[(3 + k) * kThreadsB] = b.y[k];
+                park[(6 + k) * kThreadsB] = dimbar[k];
+                park[(9 + k) * kThreadsB] = pbar[k];
+                park[(12 + k) * kThreadsB] = vbar[k];
+            }
+            }
             // ------------------------------------------------------------ L0 (dual): h0, hd0 = sum_c adot_c g_c
             f2 h[8], hd[8];
             {
@@ -363,7 +393,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) field_backward_umma_kernel(
                 wait_st();
                 fence_before_sync();
                 named_barrier(1 + group, kGroupThreads);
-                if (gt == 0) issue_stage(0, tmem, tmem_dw, wdesc, stage_addr, idesc, idesc_bf16, mbar);
+                if (gt == 0) issue_stage(0, tmem, tmem_dw, wdesc, stage_addr, idesc, idesc_bf16, mbar, mbar_w);
                 encode16(kPiF * (m[2] / scene.scale), e);
                 mbar_wait(mbar, parity); parity ^= 1;
                 fence_after_sync();
@@ -378,7 +408,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) field_backward_umma_kernel(
                 wait_st();
                 fence_before_sync();
                 named_barrier(1 + group, kGroupThreads);
-                if (gt == 0) issue_stage(1, tmem, tmem_dw, wdesc, stage_addr, idesc, idesc_bf16, mbar);
+                if (gt == 0) issue_stage(1, tmem, tmem_dw, wdesc, stage_addr, idesc, idesc_bf16, mbar, mbar_w);
                 mbar_wait(mbar, parity); parity ^= 1;
                 fence_after_sync();
                 load_biased(lane_base + kColD, sW + kOffBias, h);
@@ -387,7 +417,6 @@ __global__ void __launch_bounds__(kThreadsB, 1) field_backward_umma_kernel(
                 for (int i = 0; i < 8; ++i) hd[i] = fma2(g[i], bc(adot[2]), hd[i]);
             }
             // ------------------------------------------------------------ L1..L3 (dual)
-            f2 z3[8], zd3[8];                              // layer 3's stash stays in registers
             float rs_l[3], mz_l[3];
 #pragma unroll
             for (int l = 1; l <= 3; ++l) {
@@ -397,16 +426,21 @@ __global__ void __launch_bounds__(kThreadsB, 1) field_backward_umma_kernel(
                     float2* st = stash + (l - 1) * 16 * kSS;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) { st[i * kSS] = z[i]; st[(8 + i) * kSS] = zd[i]; }
-                } else {
+                } else {                                   // layer 3's pair is parked in this group's spare TMEM columns
+                    float t[16];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) { z3[i] = z[i]; zd3[i] = zd[i]; }
+                    for (int i = 0; i < 8; ++i) { t[2 * i] = z[i].x; t[2 * i + 1] = z[i].y; }
+                    tmem_st16(lane_base + kColPark, t);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { t[2 * i] = zd[i].x; t[2 * i + 1] = zd[i].y; }
+                    tmem_st16(lane_base + kColPark + 16, t);
                 }
                 store_operand(lane_base, kColA, kColA + 16, a);
                 store_operand(lane_base, kColAd, kColAd + 16, ad);
                 wait_st();
                 fence_before_sync();
                 named_barrier(1 + group, kGroupThreads);
-                if (gt == 0) issue_stage(1 + l, tmem, tmem_dw, wdesc, stage_addr, idesc, idesc_bf16, mbar);
+                if (gt == 0) issue_stage(1 + l, tmem, tmem_dw, wdesc, stage_addr, idesc, idesc_bf16, mbar, mbar_w);
                 mbar_wait(mbar, parity); parity ^= 1;
                 fence_after_sync();
                 load_biased(lane_base + kColD, sW + kOffBias + 16 * l, h);
@@ -414,6 +448,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) field_backward_umma_kernel(
             }
             // ------------------------------------------------------------ layer 4 and its adjoint, on the SIMT pipes
             f2 hbar[8], hdbar[8];
+            float db4;
             {
                 f2 z[8], zd[8], a[8], ad[8], g1[8], g2[8];
                 float rs4, mz4;
@@ -429,11 +464,19 @@ __global__ void __launch_bounds__(kThreadsB, 1) field_backward_umma_kernel(
                 const float spp = sp * (1.0f - 2.0f * res);
                 const float obar = dd * sp + spp * outd;
                 const float odbar = sp;
-                db4 += obar;
+                db4 = obar;
                 f2 gbar[8], gdbar[8];
+                {
+                    float dw4[16];                         // layer-4 weight gradient of this sample -> warp sum -> sRed[0..15]
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const f2 t = fma2(a[i], bc(obar), mul2(ad[i], bc(odbar)));
+                        dw4[2 * i] = t.x; dw4[2 * i + 1] = t.y;
+                    }
+                    warp_sum16_to_smem(dw4, lane, sRed);
+                }
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    dw4[i] = fma2(a[i], bc(obar), fma2(ad[i], bc(odbar), dw4[i]));
                     gbar[i] = mul2(wv[i], bc(obar));
                     gdbar[i] = mul2(wv[i], bc(odbar));
                 }
@@ -442,32 +485,40 @@ __global__ void __launch_bounds__(kThreadsB, 1) field_backward_umma_kernel(
             // ------------------------------------------------------------ R3..R1
 #pragma unroll
             for (int l = 3; l >= 1; --l) {
-                f2 z[8], zd[8], g1[8], g2[8];
-                {
-                    f2 a[8], ad[8];
-                    if (l == 3) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) { z[i] = z3[i]; zd[i] = zd3[i]; }
-                    } else {
-                        const float2* st = stash + (l - 1) * 16 * kSS;
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) { z[i] = st[i * kSS]; zd[i] = st[(8 + i) * kSS]; }
-                    }
-                    gelu_again(z, zd, a, ad, g1, g2);
-                    // dW_l operands: act = (a | 1), (ad);  adj = hbar, hdbar   (h_l = W_l a_l + b_l)
-                    stage_pairs(stage + kStageAv, 3, so, a);
-                    stage_put(stage + kStageAv, 3, so, 16, 1.0f);
-                    stage_pairs(stage + kStageAt, 3, so, ad);
-                    stage_pairs(stage + kStageBv, 2, so, hbar);
-                    stage_pairs(stage + kStageBt, 2, so, hdbar);
-                }
-                fence_proxy_async_smem();
+                // dW_l operands: act = (a | 1), (ad);  adj = hbar, hdbar   (h_l = W_l a_l + b_l).  The adjoints go out first
+                // (staging + MMA operands) so that they are dead while the layer's GELU terms are rebuilt.
+                if (wgrad_pending) { mbar_wait(mbar_w, parity_w); parity_w ^= 1; }
+                wgrad_pending = true;
+                stage_pairs(stage + kStageBv, 2, so, hbar);
+                stage_pairs(stage + kStageBt, 2, so, hdbar);
                 store_operand(lane_base, kColA, kColA + 16, hbar);
                 store_operand(lane_base, kColAd, kColAd + 16, hdbar);
+                f2 z[8], zd[8], g1[8], g2[8];
+                if (l == 3) {
+                    load_pairs(lane_base + kColPark, z);
+                    load_pairs(lane_base + kColPark + 16, zd);
+                } else {
+                    const float2* st = stash + (l - 1) * 16 * kSS;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { z[i] = st[i * kSS]; zd[i] = st[(8 + i) * kSS]; }
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {              // a = z Phi, g1 = gelu'(z), g2 = gelu''(z) = phi (2 - z^2), ad = g1 zd
+                    f2 Phi, phi;
+                    gelu_terms2(z[i], Phi, phi);
+                    const f2 a = mul2(z[i], Phi);
+                    g1[i] = fma2(z[i], phi, Phi);
+                    const f2 ad = mul2(g1[i], zd[i]);
+                    g2[i] = mul2(phi, fma2(z[i], mul2(z[i], bc(-1.0f)), bc(2.0f)));
+                    stage_put(stage + kStageAv, 3, so, 2 * i, a.x); stage_put(stage + kStageAv, 3, so, 2 * i + 1, a.y);
+                    stage_put(stage + kStageAt, 3, so, 2 * i, ad.x); stage_put(stage + kStageAt, 3, so, 2 * i + 1, ad.y);
+                }
+                stage_put(stage + kStageAv, 3, so, 16, 1.0f);
+                fence_proxy_async_smem();
                 wait_st();
                 fence_before_sync();
                 named_barrier(1 + group, kGroupThreads);
-                if (gt == 0) issue_stage(8 - l, tmem, tmem_dw, wdesc, stage_addr, idesc, idesc_bf16, mbar);
+                if (gt == 0) issue_stage(8 - l, tmem, tmem_dw, wdesc, stage_addr, idesc, idesc_bf16, mbar, mbar_w);
                 mbar_wait(mbar, parity); parity ^= 1;
                 fence_after_sync();
                 f2 gbar[8], gdbar[8];
@@ -476,7 +527,10 @@ __global__ void __launch_bounds__(kThreadsB, 1) field_backward_umma_kernel(
                 ln_gelu_reverse2(z, zd, rs_l[l - 1], mz_l[l - 1], gbar, gdbar, g1, g2, hbar, hdbar);   // adjoints of (h_{l-1}, hd_{l-1})
             }
             // ------------------------------------------------------------ RL0: per coordinate
+            mbar_wait(mbar_w, parity_w); parity_w ^= 1;                                   // R1's chain is done with the staging buffers
+            wgrad_pending = false;
             stage_pairs(stage + kStageBv, 2, so, hbar);                                   // value-pass adjoint: the same for c = 0..2
+            float pbar[3], vbar[3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 f2 e[8];
@@ -489,6 +543,8 @@ __global__ void __launch_bounds__(kThreadsB, 1) field_backward_umma_kernel(
                         et[k] = make_float2(-f * e[k].y, f * e[k].x);
                         q[k] = mul2(hdbar[k], bc(adot[c]));
                     }
+                    if (wgrad_pending) { mbar_wait(mbar_w, parity_w); parity_w ^= 1; }
+                    wgrad_pending = true;
                     stage_pairs(stage + kStageAv, 3, so, e);
                     stage_put(stage + kStageAv, 3, so, 16, c == 0 ? 1.0f : 0.0f);         // the bias row counts once
                     stage_pairs(stage + kStageAt, 3, so, et);
@@ -499,7 +555,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) field_backward_umma_kernel(
                 wait_st();
                 fence_before_sync();
                 named_barrier(1 + group, kGroupThreads);
-                if (gt == 0) issue_stage(8 + c, tmem, tmem_dw, wdesc, stage_addr, idesc, idesc_bf16, mbar);
+                if (gt == 0) issue_stage(8 + c, tmem, tmem_dw, wdesc, stage_addr, idesc, idesc_bf16, mbar, mbar_w);
                 mbar_wait(mbar, parity); parity ^= 1;
                 fence_after_sync();
                 f2 g[8], kk[8];
@@ -507,37 +563,29 @@ __global__ void __launch_bounds__(kThreadsB, 1) field_backward_umma_kernel(
                 load_pairs(lane_base + kColDd, kk);
                 const float gh = dot16(hbar, g), gd = dot16(hdbar, g), kd = dot16(hdbar, kk);
                 const float abar = gh + adot[c] * kd;                                    // d phi / d a_c
-                pbar[c] += abar * coef[c];
-                vbar[c] += gd * coef[c];                                                 // d phi / d adot_c = hdbar . g_c
+                pbar[c] = abar * coef[c];
+                vbar[c] = gd * coef[c];                                                 // d phi / d adot_c = hdbar . g_c
             }
             // ------------------------------------------------------------ pose: p = R^T (x - t), v = R^T dG
+            {
+                float pose[16];                            // sRed[16] = layer-4 bias, sRed[17..31] = pose
+                pose[0] = db4;
 #pragma unroll
-            for (int mm = 0; mm < 3; ++mm) {
-                pose[mm] -= I.R[3 * mm] * pbar[0] + I.R[3 * mm + 1] * pbar[1] + I.R[3 * mm + 2] * pbar[2];
-                pose[3 + mm] += dimbar[mm];
+                for (int k = 0; k < 3; ++k) { pbar[k] += park[(9 + k) * kThreadsB]; vbar[k] += park[(12 + k) * kThreadsB]; }
 #pragma unroll
-                for (int k = 0; k < 3; ++k) pose[6 + 3 * mm + k] += b.y[mm] * pbar[k] + dG[mm] * vbar[k];
+                for (int mm = 0; mm < 3; ++mm) {
+                    pose[1 + mm] = -(sInst[6 + 3 * mm] * pbar[0] + sInst[6 + 3 * mm + 1] * pbar[1] + sInst[6 + 3 * mm + 2] * pbar[2]);
+                    pose[4 + mm] = park[(6 + mm) * kThreadsB];
+                    const float y = park[(3 + mm) * kThreadsB], dg = park[mm * kThreadsB];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) pose[7 + 3 * mm + k] = y * pbar[k] + dg * vbar[k];
+                }
+                warp_sum16_to_smem(pose, lane, sRed + 16);
             }
             fence_before_sync();
         }
+        if (wgrad_pending) { mbar_wait(mbar_w, parity_w); parity_w ^= 1; wgrad_pending = false; }
         // ---------------------------------------------------------------- segment epilogue: one partial row per (CTA, instance)
-        {
-            float vals[32];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { vals[2 * i] = dw4[i].x; vals[2 * i + 1] = dw4[i].y; }
-            vals[16] = db4;
-#pragma unroll
-            for (int k = 0; k < 15; ++k) vals[17 + k] = pose[k];
-#pragma unroll
-            for (int sh = 16; sh >= 1; sh >>= 1)
-#pragma unroll
-                for (int k = 0; k < 32; ++k) vals[k] += __shfl_xor_sync(kFull, vals[k], sh);
-            // lane k publishes value k (a select chain keeps vals[] in registers)
-            float mine = 0.0f;
-#pragma unroll
-            for (int k = 0; k < 32; ++k) mine = lane == k ? vals[k] : mine;
-            atomicAdd(&sRed[lane], mine);
-        }
         fence_before_sync();
         __syncthreads();                                   // all groups passed their last commit wait: the accumulators are final
         fence_after_sync();

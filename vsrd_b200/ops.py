@@ -255,7 +255,7 @@ def composite_backward(scene: SceneArgs, rays: RayArgs, field, std_deviation, co
 _partials_cache = {}
 
 
-def field_backward(scene: SceneArgs, rays: RayArgs, adjoint: torch.Tensor):
+def field_backward(scene: SceneArgs, rays: RayArgs, adjoint: torch.Tensor, *, _entry: str = "vsrd_field_backward"):
     dev = rays.directions.device
     n = scene.num_instances
     blocks = _lib.load().vsrd_backward_blocks_per_instance(n, rays.num_rays, rays.num_intervals)
@@ -266,10 +266,16 @@ def field_backward(scene: SceneArgs, rays: RayArgs, adjoint: torch.Tensor):
     g_rot = torch.empty(n, 3, 3, device=dev, dtype=torch.float32)
     g_dim = torch.empty(n, 3, device=dev, dtype=torch.float32)
     g_w = torch.empty(n, MLP_WEIGHTS, device=dev, dtype=torch.float32) if scene.mlp_weights is not None else None
-    _lib.check(_lib.load().vsrd_field_backward(
+    _lib.check(getattr(_lib.load(), _entry)(
         ctypes.byref(scene.struct), ctypes.byref(rays.struct), _ptr(adjoint), _ptr(partials),
         _ptr(g_loc), _ptr(g_rot), _ptr(g_dim), _ptr(g_w), _stream()))
     return g_loc, g_rot, g_dim, g_w
+
+
+def experimental_field_backward_tcgen05(scene: SceneArgs, rays: RayArgs, adjoint: torch.Tensor):
+    """The tcgen05 / TMEM field backward (DESIGN.md 3.2: a measured dead end, NOT used by anything in the package;
+    tools/compare_backward.py and tests/test_gpu_experimental.py call it)."""
+    return field_backward(scene, rays, adjoint, _entry="vsrd_experimental_field_backward_tcgen05")
 
 
 # ---- device-resident schedule -------------------------------------------------------------------
