@@ -146,19 +146,35 @@ __global__ void __launch_bounds__(kThreadsM) hyper_layer_backward_kernel(LayerBa
 
     stage_activations(a.x_in, a.ln_in_w, a.ln_in_b, N, sA);
     if (a.dy == nullptr) {
-        // sDY <- sum of the partials of the layer above: 128-bit loads, all partials of a chunk in flight at once
+        // sDY <- sum of the partials of the layer above, in partial order (deterministic).  Latency-bound on L2: every
+        // thread keeps 2 chunks x 16 partials = 32 independent 128-bit loads in flight (8 in flight cost 11 of the
+        // kernel's 20 us at 64 partials).
         {
             const float4* src = reinterpret_cast<const float4*>(a.partials_in);
             float4* dst = reinterpret_cast<float4*>(sDY);
-            const int chunks = N * (kHW / 4);
-            for (int e = threadIdx.x; e < chunks; e += kThreadsM) {
-                float4 s = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-#pragma unroll 8
-                for (int p = 0; p < a.num_partials; ++p) {
-                    const float4 v = __ldg(src + (size_t)p * chunks + e);
-                    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+            const int chunks = N * (kHW / 4), P = a.num_partials;
+            for (int e0 = threadIdx.x; e0 < chunks; e0 += 2 * kThreadsM) {
+                const int e1 = e0 + kThreadsM;
+                const bool two = e1 < chunks;
+                float4 s0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), s1 = s0;
+                for (int p0 = 0; p0 < P; p0 += 16) {
+                    float4 v0[16], v1[16];
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) {
+                        const bool in = p0 + u < P;
+                        v0[u] = in ? __ldg(src + (size_t)(p0 + u) * chunks + e0) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                        v1[u] = in && two ? __ldg(src + (size_t)(p0 + u) * chunks + e1) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) {
+                        if (p0 + u < P) {
+                            s0.x += v0[u].x; s0.y += v0[u].y; s0.z += v0[u].z; s0.w += v0[u].w;
+                            s1.x += v1[u].x; s1.y += v1[u].y; s1.z += v1[u].z; s1.w += v1[u].w;
+                        }
+                    }
                 }
-                dst[e] = s;
+                dst[e0] = s0;
+                if (two) dst[e1] = s1;
             }
         }
         __syncthreads();
