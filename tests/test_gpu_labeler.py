@@ -162,21 +162,44 @@ def test_two_gpu_sequence_labeling_gathers_every_frame():
     assert line["n_gpus"] == 2 and line["gathered_frames"] == 5 and line["all_frames_gathered_and_finite"]
 
 
+def _torch_optimizer_like_main_py(detector, hyper, lrs=(1e-2, 1e-2, 1e-2, 1e-3, 1e-4), num_steps=20):
+    """The optimizer / scheduler pair the config builds (config.json `optimizer`, `scheduler`; main.py:182-190)."""
+    groups = [[detector.locations], [detector.dimensions], [detector.orientations], [detector.embeddings], list(hyper.parameters())]
+    opt = torch.optim.Adam([dict(params=g, lr=lr) for g, lr in zip(groups, lrs)], lr=lrs[0])
+    return opt, torch.optim.lr_scheduler.ExponentialLR(opt, gamma=0.01 ** (1.0 / num_steps))
+
+
 def test_checkpoint_round_trip_and_reference_format():
-    """checkpoint() follows scripts/main.py:1109-1121 (`models` -> state dicts under the config's names, loadable into a
-    fresh BoxParameters3D as tools/kitti_360/make_predictions.py:50-58 does); load_checkpoint() resumes bit-for-bit."""
+    """checkpoint() follows scripts/main.py:1109-1121 key for key: `models` -> state dicts under the config's names
+    (loadable into a fresh BoxParameters3D as tools/kitti_360/make_predictions.py:50-58 does), `optimizer` / `scheduler`
+    loadable by the torch classes the config names, per-parameter update counts as torch counts them;
+    load_checkpoint() resumes bit-for-bit."""
     import vsrd
     frame, init = _frame(seed=5)
     kw = dict(num_steps=20, warmup_steps=6, num_rays=128, num_samples=16, seed=2, use_graph=False)
     a, _ = _labeler(frame, init, **kw)
     for _ in range(10):
         a.step()
-    ckpt = a.checkpoint()
+    ckpt = a.checkpoint(metrics=dict(iou_3d=torch.tensor(0.5)))
+    assert set(ckpt) == {"step", "models", "optimizer", "scheduler", "metrics", "losses"}
     assert ckpt["step"] == 9 and set(ckpt["models"]) == {"detector", "hyper_distance_field", "positional_encoder"}
+    assert set(ckpt["metrics"]) == {"iou_3d"}
     det = vsrd.models.BoxParameters3D(*ckpt["models"]["detector"]["embeddings"].shape)
     det.load_state_dict(ckpt["models"]["detector"])
     with torch.no_grad():
         assert torch.allclose(det()["boxes_3d"][0], a.boxes()["boxes_3d"].cpu(), atol=1e-6)
+    # the torch classes of the config accept the optimizer / scheduler entries
+    hyp = vsrd.models.HyperDistanceField(in_channels=48, out_channels_list=[16] * 4, hyper_in_channels=256,
+                                         hyper_out_channels_list=[256] * 4)
+    opt, sched = _torch_optimizer_like_main_py(det, hyp)
+    opt.load_state_dict(ckpt["optimizer"])
+    sched.load_state_dict(ckpt["scheduler"])
+    assert sched.last_epoch == 10 and sched._step_count == 11
+    gamma = 0.01 ** (1.0 / 20)
+    assert [g["lr"] for g in opt.param_groups] == pytest.approx([lr * gamma ** 10 for lr in (1e-2, 1e-2, 1e-2, 1e-3, 1e-4)], rel=1e-6)
+    steps = [int(opt.state[g["params"][0]]["step"]) for g in opt.param_groups]
+    assert steps == [10, 10, 10, 4, 4]                        # embeddings / hypernetwork first get a gradient at step 6
+    assert all(opt.state[p]["exp_avg"].shape == p.shape for g in opt.param_groups for p in g["params"])
     b, _ = _labeler(frame, init, **kw)
     b.load_checkpoint(ckpt)
     assert b.step_index == 10
@@ -185,6 +208,40 @@ def test_checkpoint_round_trip_and_reference_format():
         b.step()
     assert torch.equal(a.boxes()["boxes_3d"], b.boxes()["boxes_3d"])
     assert torch.equal(a.arena.params, b.arena.params)
+    # a checkpoint whose update counts contradict the schedule is refused, not resumed with a wrong bias correction
+    c, _ = _labeler(frame, init, **dict(kw, warmup_steps=3))
+    with pytest.raises(ValueError, match="Adam updates"):
+        c.load_checkpoint(ckpt)
+
+
+def test_checkpoint_from_torch_adam_resumes_in_the_fused_labeler():
+    """A checkpoint whose `optimizer` is torch.optim.Adam's OWN state_dict (the autograd + torch.optim labeler, i.e. what
+    the reference's main.py writes) resumes in the fused labeler: same moments, same update counts, and the continued
+    optimisation tracks the torch one."""
+    frame, init = _frame(seed=6)
+    kw = dict(num_steps=20, warmup_steps=4, num_rays=128, num_samples=16, seed=3, use_graph=False)
+    t, _ = _labeler(frame, init, models="torch", **kw)
+    f, _ = _labeler(frame, init, **kw)
+    for _ in range(9):
+        t.step()
+        f.step()
+    ck_t, ck_f = t.checkpoint(), f.checkpoint()
+    assert set(ck_t["optimizer"]["state"]) == set(ck_f["optimizer"]["state"])
+    for i, entry in ck_t["optimizer"]["state"].items():
+        mine = ck_f["optimizer"]["state"][i]
+        assert float(entry["step"]) == float(mine["step"])
+        for key in ("exp_avg", "exp_avg_sq"):
+            ref = entry[key].cpu().double()
+            # two fp32 trajectories (autograd vs fused kernels) nine resampled steps apart: percent-level agreement pins
+            # WHICH moment sits where (a misplaced slice is an O(1) difference), not the rounding
+            assert float((mine[key].double() - ref).norm()) <= 2e-2 * float(ref.norm()) + 1e-12, (i, key)
+    g, _ = _labeler(frame, init, **kw)
+    g.load_checkpoint(ck_t)
+    assert g.step_index == 9
+    for _ in range(6):
+        t.step()
+        g.step()
+    assert torch.allclose(g.boxes()["boxes_3d"], t.boxes()["boxes_3d"], atol=2e-3)
 
 
 def test_culling_does_not_change_the_optimised_boxes():

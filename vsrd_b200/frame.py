@@ -344,10 +344,18 @@ class FrameLabeler:
                     dimensions=world["dimensions"][0], orientations=world["orientations"][0])
 
     # ---- checkpoints (scripts/main.py:1109-1121, 134-136) ----------------------------------------------
-    def checkpoint(self) -> Dict:
-        """What the reference saves as `step_{step}.pt` for a frame: `step`, `models` = state dicts under the config's
-        model names (`detector` is what tools/kitti_360/make_predictions.py:50-58 loads to produce the pseudo labels),
-        plus the Adam moments so `load_checkpoint` resumes bit-for-bit.  Host tensors; waits for the labeler's stream."""
+    def checkpoint(self, metrics: Optional[Dict] = None) -> Dict:
+        """What the reference saves as `step_{step}.pt` for a frame (scripts/main.py:1109-1121), key for key:
+          step       index of the last completed optimisation step
+          models     state dicts under the config's model names (`detector` is what
+                     tools/kitti_360/make_predictions.py:50-58 loads to produce the pseudo labels)
+          optimizer  torch.optim.Adam.state_dict() over the config's five parameter groups (per-parameter `step`,
+                     `exp_avg`, `exp_avg_sq`; `lr` = the decayed rate) -- loadable by torch.optim.Adam.load_state_dict
+          scheduler  torch.optim.lr_scheduler.ExponentialLR.state_dict() (`last_epoch` = completed steps)
+          metrics    the caller's metric dict (main.py:888-924 fills it with IoU metrics when the frame has 3D ground
+                     truth, else leaves it empty)
+        plus one extra key, `losses` = (total, silhouette, eikonal, iou, l1) of the last step.  Host tensors; waits for
+        the labeler's stream."""
         import vsrd
         self.stream.synchronize()
         cpu = lambda sd: {k: v.detach().cpu().clone() for k, v in sd.items()}
@@ -355,16 +363,25 @@ class FrameLabeler:
                     models=dict(detector=cpu(self.detector.state_dict()),
                                 hyper_distance_field=cpu(self.hyper.state_dict()),
                                 positional_encoder=cpu(vsrd.models.SinusoidalEncoder(num_frequencies=8).state_dict())),
-                    metrics=dict(losses=self.losses.detach().cpu().clone()))
+                    metrics=dict(metrics or {}),
+                    losses=self.losses.detach().cpu().clone())
         if self.arena is not None:
-            ckpt["optimizer"] = dict(kind="vsrd_b200.arena", exp_avg=self.arena.exp_avg.cpu(), exp_avg_sq=self.arena.exp_avg_sq.cpu())
+            ckpt["optimizer"], ckpt["scheduler"] = self.arena.torch_optimizer_state(self.step_index)
         else:
             ckpt["optimizer"] = self.optimizer.state_dict()
+            gamma = math.exp(self._log_gamma)
+            lrs = [base * gamma ** self.step_index for base in self._base_lrs]
+            ckpt["scheduler"] = dict(gamma=gamma, base_lrs=list(self._base_lrs), last_epoch=self.step_index,
+                                     _step_count=self.step_index + 1, _get_lr_called_within_step=False, _last_lr=lrs)
         return ckpt
 
     def load_checkpoint(self, ckpt: Dict) -> None:
-        """Restore parameters, optimiser moments and the schedule position from `checkpoint()` (or, parameters only,
-        from a checkpoint written by the reference's main.py)."""
+        """Restore parameters, Adam moments and the schedule position from `checkpoint()` or from a checkpoint written by
+        the reference's main.py with the same config (same key set).  The schedule position comes from `step`; the
+        optimizer's per-group update counts must agree with it (`step + 1 - first step of the group`), which is how
+        torch counts them for this schedule -- anything else is refused rather than resumed with a wrong bias correction."""
+        opt = ckpt.get("optimizer")
+        completed = int(ckpt["step"]) + 1
         with torch.cuda.stream(self.stream), torch.no_grad():
             for module, key in ((self.detector, "detector"), (self.hyper, "hyper_distance_field")):
                 state = ckpt["models"].get(key)
@@ -373,13 +390,20 @@ class FrameLabeler:
                 own = module.state_dict()
                 for name, value in state.items():
                     own[name].copy_(torch.as_tensor(value).reshape(own[name].shape))     # in place: parameters stay in the arena
-            opt = ckpt.get("optimizer")
-            if self.arena is not None and isinstance(opt, dict) and opt.get("kind") == "vsrd_b200.arena":
-                self.arena.exp_avg.copy_(opt["exp_avg"])
-                self.arena.exp_avg_sq.copy_(opt["exp_avg_sq"])
-            elif self.arena is None and isinstance(opt, dict) and "state" in opt:
-                self.optimizer.load_state_dict(opt)
-        self.seek(int(ckpt["step"]) + 1)
+            if isinstance(opt, dict) and "state" in opt:
+                if self.arena is not None:
+                    counts = self.arena.torch_update_counts(opt)
+                    for k, count in enumerate(counts):
+                        expected = completed - int(self.arena.adam_groups.first_step[k])
+                        if (count or 0) != max(expected, 0):
+                            raise ValueError(f"vsrd_b200: optimizer group {k} made {count} Adam updates, the schedule says "
+                                             f"{max(expected, 0)} after step {completed - 1} (different warmup_steps?)")
+                    self.arena.load_torch_optimizer_state(opt)
+                else:
+                    self.optimizer.load_state_dict(opt)
+            elif opt is not None:
+                raise ValueError("vsrd_b200: `optimizer` is not a torch.optim.Adam state_dict")
+        self.seek(completed)
 
     def run(self) -> Dict[str, torch.Tensor]:
         if self.rays != "draw" or self.inject_samples:

@@ -47,6 +47,8 @@ class ParameterArena:
             ends.append(offset)
         self.detector, self.hyper = detector, hyper
         self.num_instances = int(detector.locations.shape[-2])
+        self._groups = groups
+        self._num_steps = int(num_steps)
 
         g = _lib.VsrdAdamGroups()
         g.num_groups = len(groups)
@@ -126,3 +128,70 @@ class ParameterArena:
 
     def adam_step(self, step_state=None, step: int = 0) -> None:
         ops.adam_step(self.params, self.grads, self.exp_avg, self.exp_avg_sq, self.adam_groups, step_state, step)
+
+    # ---- interchange with torch.optim.Adam / ExponentialLR (scripts/main.py:182-190, 1118-1119) -------------------
+    def _slices(self):
+        """(group index, parameter, arena offset) in torch's parameter order: groups in order, parameters within."""
+        offset = 0
+        for k, group in enumerate(self._groups):
+            for p in group:
+                yield k, p, offset
+                offset += p.numel()
+
+    def torch_optimizer_state(self, completed_steps: int):
+        """`optimizer.state_dict()` and `scheduler.state_dict()` as the reference's torch.optim.Adam over the config's five
+        parameter groups and its ExponentialLR would hold them after `completed_steps` optimisation steps.  Built with
+        real torch objects on host copies, so the key set is the installed torch's own.  A group that has not received
+        a gradient yet (embeddings / hypernetwork before `warmup_steps`) has no `state` entry, as in torch."""
+        g = self.adam_groups
+        host = [[torch.nn.Parameter(p.detach().cpu().clone()) for p in group] for group in self._groups]
+        opt = torch.optim.Adam([dict(params=ps, lr=float(g.base_lr[k])) for k, ps in enumerate(host)],
+                               lr=float(g.base_lr[0]), betas=(float(g.beta1), float(g.beta2)), eps=float(g.eps))
+        gamma = math.exp(float(g.log_gamma))
+        sched = torch.optim.lr_scheduler.ExponentialLR(opt, gamma=gamma)
+        exp_avg, exp_avg_sq = self.exp_avg.cpu(), self.exp_avg_sq.cpu()
+        flat = [p for ps in host for p in ps]
+        for (k, p, offset), hp in zip(self._slices(), flat):
+            updates = completed_steps - int(g.first_step[k])
+            if updates > 0:
+                n = p.numel()
+                opt.state[hp] = dict(step=torch.tensor(float(updates)),
+                                     exp_avg=exp_avg[offset:offset + n].view(p.shape).clone(),
+                                     exp_avg_sq=exp_avg_sq[offset:offset + n].view(p.shape).clone())
+        lrs = [float(g.base_lr[k]) * gamma ** completed_steps for k in range(len(host))]
+        for group, lr in zip(opt.param_groups, lrs):
+            group["lr"] = lr
+        sched.last_epoch = int(completed_steps)
+        sched._step_count = int(completed_steps) + 1
+        sched._last_lr = lrs
+        return opt.state_dict(), sched.state_dict()
+
+    def load_torch_optimizer_state(self, state_dict: Dict) -> None:
+        """Adam moments from a torch.optim.Adam `state_dict()` over the same five groups (a checkpoint written by the
+        reference's main.py, or by `torch_optimizer_state`).  Parameters without a state entry get zero moments.  The
+        bias-correction count is not stored here: the kernel derives it from the schedule step and `warmup_steps`, which
+        is what torch's per-parameter `step` equals for this schedule (checked)."""
+        groups = state_dict["param_groups"]
+        if [len(gr["params"]) for gr in groups] != [len(gr) for gr in self._groups]:
+            raise ValueError("vsrd_b200: optimizer state_dict does not have the config's parameter groups "
+                             "(locations, dimensions, orientations, embeddings, hypernetwork)")
+        state = state_dict["state"]
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        index = 0
+        for k, p, offset in self._slices():
+            entry = state.get(index, state.get(str(index)))
+            index += 1
+            if entry is None:
+                continue
+            n = p.numel()
+            self.exp_avg[offset:offset + n].copy_(torch.as_tensor(entry["exp_avg"]).reshape(-1))
+            self.exp_avg_sq[offset:offset + n].copy_(torch.as_tensor(entry["exp_avg_sq"]).reshape(-1))
+
+    def torch_update_counts(self, state_dict: Dict):
+        """Per-group Adam update counts of a torch state_dict (None for a group without state)."""
+        out, index = [], 0
+        for gr in state_dict["param_groups"]:
+            entry = state_dict["state"].get(gr["params"][0], state_dict["state"].get(str(gr["params"][0])))
+            out.append(None if entry is None else int(float(entry["step"])))
+        return out
