@@ -79,13 +79,18 @@ typedef struct VsrdRays {
     const float* origins;         /* [R,3]   ray_positions                                    */
     const float* directions;      /* [R,3]   ray_directions                                   */
     const float* distances;       /* [R,M+1] sampled_distances, ascending                     */
-    /* Optional instance culling.  union_bound[R*M] = min over instances of the BOX SDF at every sample
-     * (vsrd_union_bound).  The residual lies in (0,1), so an instance whose box SDF exceeds union_bound + 1 by more than
-     * VSRD_CULL_LOG_EPS * temperature has a soft-min weight below exp(-VSRD_CULL_LOG_EPS) ~ 1e-13 of the dominant one:
-     * warp tiles made of such samples skip the residual MLP (forward: box value and gradient are written; backward:
-     * nothing is accumulated).  NULL disables it.  cull_stats (DEVICE uint64[2], may be NULL) accumulates
-     * {tiles skipped, tiles visited} over all field launches. */
-    const float* union_bound;
+    /* Optional instance culling.  The residual lies in (0,1), so an instance whose BOX SDF exceeds the lowest
+     * box SDF + 1 by more than VSRD_CULL_LOG_EPS * temperature has a soft-min weight w below exp(-VSRD_CULL_LOG_EPS) = 2e-9
+     * of the dominant one, and its union-gradient coefficient |w (1 - (d_i - d) / T)| stays below 20 exp(-20) = 4e-8 < 2^-24:
+     * neither term can change the fp32 sums of the union it is added to.  vsrd_cull_samples() tests
+     * that per (instance, sample), writes the box value and gradient of the pairs that pass into `field`, and lists the
+     * others in forward_samples: a header of VSRD_CULL_HEADER_INTS int32 (the live-sample count of instance i at
+     * [i * VSRD_CULL_COUNT_STRIDE], one cache line apart), then [N][R*M] flat sample indices (in no particular order;
+     * every sample's result is independent of its neighbours in the list).  vsrd_field_forward then
+     * evaluates the residual MLP on the listed samples only, an equal share of them per thread block.  NULL disables it.
+     * cull_stats (DEVICE uint64[4], may be NULL) accumulates over all field launches {backward tiles skipped, backward
+     * tiles visited (vsrd_backward_tile_rows() samples each), forward (sample, instance) pairs skipped, visited}. */
+    int32_t* forward_samples;
     unsigned long long* cull_stats;
     /* Backward side of the culling: live_tiles [N][ceil(R*M / vsrd_backward_tile_rows())] bytes, ZEROED by the caller
      * before vsrd_composite_backward, which (a) writes exact zeros for the adjoints of instances whose soft-min weight
@@ -94,7 +99,9 @@ typedef struct VsrdRays {
      * work is balanced and the accumulation order stays deterministic).  NULL disables it. */
     uint8_t* live_tiles;
 } VsrdRays;
-#define VSRD_CULL_LOG_EPS 30.0f
+#define VSRD_CULL_COUNT_STRIDE 32
+#define VSRD_CULL_HEADER_INTS (VSRD_MAX_INSTANCES * VSRD_CULL_COUNT_STRIDE)
+#define VSRD_CULL_LOG_EPS 20.0f      /* x exp(-x) < 2^-24 = 5.96e-8 for x >= 20: value AND gradient terms of the soft-min */
 /* Samples per warp tile of the backward field kernel (16 or 32), for sizing VsrdRays::live_tiles. */
 int vsrd_backward_tile_rows(void);
 
@@ -155,9 +162,10 @@ int vsrd_place_fine(const float* coarse_distances, const float* coarse_weights, 
                     uint64_t seed, const VsrdStepState* step_state, int num_rays, int num_samples,
                     float* distances, void* stream);
 
-/* union_bound[R*M] = min_i box_sdf_i(sample) for the culling test described at VsrdRays (reads origins / directions /
- * distances and the box parameters of `scene`; rays->union_bound itself is ignored). */
-int vsrd_union_bound(const VsrdScene* scene, const VsrdRays* rays, float* union_bound, void* stream);
+/* The culling pre-pass described at VsrdRays::forward_samples, to be enqueued before vsrd_field_forward on the same
+ * `field` buffer (reads origins / directions / distances and the box parameters of `scene`; rays->forward_samples itself
+ * is ignored, the list goes to `forward_samples`: VSRD_CULL_HEADER_INTS + N * R * M int32). */
+int vsrd_cull_samples(const VsrdScene* scene, const VsrdRays* rays, float* field, int32_t* forward_samples, void* stream);
 
 /* ---- a5-a8: per-(sample, instance) field: box SDF + residual MLP, value and spatial gradient.
  * out field[N][R*M] as float4 (d_i, dd_i/dx, dd_i/dy, dd_i/dz). */

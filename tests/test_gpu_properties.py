@@ -195,30 +195,60 @@ def test_rays_that_miss_everything_follow_the_reference(F):
 
 @pytest.mark.parametrize("n,layout,temperature,share", [(8, "street", 0.1, 0.2), (24, "parking", 0.3, 0.2)])
 def test_instance_culling_is_invisible_at_the_parity_bar(F, n, layout, temperature, share):
-    """Late-schedule temperatures (weights below exp(-30) are dropped): the culled and the un-culled kernels
-    must agree far inside the parity tolerances, and the kernels must actually have skipped tiles."""
+    """Late-schedule temperatures.  Culling drops soft-min weights below exp(-20) (value and gradient terms below 2^-24 of
+    the sums they are added to; include/vsrd_b200.h).  (a) At IDENTICAL sample positions the culled and the un-culled
+    kernels agree to rounding.  (b) Through the two-pass renderer the culled coarse pass moves the importance samples
+    by rounding-level amounts, which the quadrature turns into label changes of a few 1e-6: still far inside the parity
+    tolerances (1e-4 labels, 1e-3 gradients).  The kernels must actually have skipped work, in the forward pre-pass
+    ((sample, instance) pairs) as well as in the backward (16-sample tiles)."""
     from vsrd_b200 import ops
     frame, leaves = _scene(n, layout, seed=0)
     o, d = _rays(frame, 500, seed=2)
     sched = dict(temperature=temperature, std_deviation=temperature, cosine_ratio=0.9)
-    results = []
+
+    def upstream(labels, grads):
+        gen = torch.Generator(device=DEV).manual_seed(3)
+        return [torch.randn(labels.shape, device=DEV, generator=gen), torch.randn(grads.shape, device=DEV, generator=gen) * 0.01]
+
+    two_pass, fixed = [], []
     try:
         for enabled in (True, False):
             ops.set_culling(enabled)
             ops.culling_counters(DEV, reset=True)
             dev_leaves, (labels, grads, cd, cw, fd, fw) = _render(F, leaves, o, d, 64, requires_grad=True, **sched)
-            gen = torch.Generator(device=DEV).manual_seed(3)
-            u = torch.randn(labels.shape, device=DEV, generator=gen)
-            v = torch.randn(grads.shape, device=DEV, generator=gen) * 0.01
-            g = torch.autograd.grad([labels, grads], dev_leaves, [u, v])
-            results.append((labels.detach(), grads.detach(), fd, fw.detach(), g, ops.culling_counters(DEV)))
+            g = torch.autograd.grad([labels, grads], dev_leaves, upstream(labels, grads))
+            two_pass.append((labels.detach(), grads.detach(), fd, fw.detach(), g, ops.culling_counters(DEV),
+                             ops.culling_counters(DEV, forward=True)))
+        fine_distances = two_pass[1][2]                        # the un-culled run's sample positions, for both
+        for enabled in (True, False):
+            ops.set_culling(enabled)
+            dev_leaves = [t.to(DEV).requires_grad_(True) for t in leaves]
+            labels, grads, fw = F.render_pass(*dev_leaves, o.to(DEV), d.to(DEV), fine_distances, **sched)
+            g = torch.autograd.grad([labels, grads], dev_leaves, upstream(labels, grads))
+            fixed.append((labels.detach(), grads.detach(), fw.detach(), g))
     finally:
         ops.set_culling(True)
-    (la, ga, fda, fwa, gra, (culled, visited)), (lb, gb, fdb, fwb, grb, (culled_off, visited_off)) = results
-    assert visited > 0 and culled > share * visited, (culled, visited)    # a large share of the tiles is far
-    assert culled_off == 0 and visited_off == 0
-    assert torch.equal(fda, fdb)                                          # identical sample placement
-    assert float((la - lb).abs().max()) < 1e-9 and float((fwa - fwb).abs().max()) < 1e-9
-    assert float((ga - gb).abs().max()) < 1e-6
-    for a, b in zip(gra, grb):       # the live-tile list changes which warp sums which tile: fp32 summation-order noise
-        assert float((a - b).norm()) <= 5e-6 * float(b.norm()) + 1e-12, float((a - b).norm() / b.norm())
+
+    def rel(a, b):
+        return float((a - b).norm()) / (float(b.norm()) + 1e-30)
+
+    (la, ga, fwa, gra), (lb, gb, fwb, grb) = fixed
+    print(f"identical samples: labels {float((la - lb).abs().max()):.2e}, weights {float((fwa - fwb).abs().max()):.2e}, "
+          f"gradients {float((ga - gb).abs().max()):.2e}, parameter gradients " + " ".join(f"{rel(a, b):.1e}" for a, b in zip(gra, grb)))
+    assert float((la - lb).abs().max()) < 5e-7 and float((fwa - fwb).abs().max()) < 5e-7
+    # union gradient: each culled instance may contribute up to 20 exp(-20) |grad d_i| = 4e-8 |grad d_i|, N - 1 of them
+    assert float((ga - gb).abs().max()) < 1e-5
+    for a, b in zip(gra, grb):       # + the live-tile list changes which warp sums which tile: fp32 summation-order noise
+        assert rel(a, b) <= 2e-5, rel(a, b)
+
+    (la, ga, fda, fwa, gra, (culled, visited), (fwd_culled, fwd_visited)), (lb, gb, fdb, fwb, grb, (culled_off, visited_off), fwd_off) = two_pass
+    print(f"two-pass: culled backward tiles {culled / visited:.3f}, forward pairs {fwd_culled / fwd_visited:.3f}; "
+          f"labels {float((la - lb).abs().max()):.2e}, weights {float((fwa - fwb).abs().max()):.2e}, "
+          f"gradients {float((ga - gb).abs().max()):.2e}, parameter gradients " + " ".join(f"{rel(a, b):.1e}" for a, b in zip(gra, grb)))
+    assert visited > 0 and culled > share * visited, (culled, visited)    # a large share of the backward tiles is far
+    assert fwd_visited > 0 and fwd_culled > share * fwd_visited, (fwd_culled, fwd_visited)   # coarse + fine forward pairs
+    assert culled_off == 0 and visited_off == 0 and fwd_off == (0, 0)
+    assert torch.allclose(fda, fdb, rtol=1e-5, atol=1e-4)
+    assert float((la - lb).abs().max()) < 2e-5 and float((fwa - fwb).abs().max()) < 2e-5
+    for a, b in zip(gra, grb):
+        assert rel(a, b) <= 2e-4, rel(a, b)

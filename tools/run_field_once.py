@@ -31,8 +31,6 @@ o, d = inp["origins"][:r].to(dev), inp["directions"][:r].to(dev)
 gen = torch.Generator().manual_seed(0)
 dist = torch.sort(torch.rand(r, 2 * fc.NUM_SAMPLES, generator=gen) * 60.0, dim=-1).values.to(dev)
 rays = ops.RayArgs(o, d, dist)
-if a.cull:
-    rays.enable_culling(scene)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 times = {"forward": [], "backward": []}
 for it in range(a.reps):

@@ -14,6 +14,8 @@ LIB_PATH = os.path.join(HERE, "libvsrd_b200.so")
 MLP_WEIGHTS = 1617
 GRAD_STRIDE = 1632
 MAX_INSTANCES = 32
+CULL_COUNT_STRIDE = 32                 # VSRD_CULL_COUNT_STRIDE
+CULL_HEADER_INTS = MAX_INSTANCES * CULL_COUNT_STRIDE
 MAX_INTERVALS = 512
 
 c_float_p = ctypes.c_void_p  # device pointers travel as opaque addresses
@@ -77,7 +79,7 @@ class VsrdRays(ctypes.Structure):
         ("origins", ctypes.c_void_p),
         ("directions", ctypes.c_void_p),
         ("distances", ctypes.c_void_p),
-        ("union_bound", ctypes.c_void_p),
+        ("forward_samples", ctypes.c_void_p),
         ("cull_stats", ctypes.c_void_p),
         ("live_tiles", ctypes.c_void_p),
     ]
@@ -172,7 +174,7 @@ SIGNATURES = {
     "vsrd_gather_rays": (_I, [_V, _V, _V, _I, _I, _I, _I, _V, _V, _V]),
     "vsrd_place_coarse": (_I, [_V, _V, ctypes.c_uint64, _V, _I, _I, _V, _V]),
     "vsrd_place_fine": (_I, [_V, _V, _V, ctypes.c_uint64, _V, _I, _I, _V, _V]),
-    "vsrd_union_bound": (_I, [_P(VsrdScene), _P(VsrdRays), _V, _V]),
+    "vsrd_cull_samples": (_I, [_P(VsrdScene), _P(VsrdRays), _V, _V, _V]),
     "vsrd_field_forward": (_I, [_P(VsrdScene), _P(VsrdRays), _V, _V]),
     "vsrd_composite_forward": (_I, [_P(VsrdScene), _P(VsrdRays), _P(VsrdRenderParams), _V, _V, _V, _V,
                                     _P(VsrdLoss), _V, _V]),

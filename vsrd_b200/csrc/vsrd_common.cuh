@@ -46,8 +46,8 @@ struct RaysDev {
     const float* origins;
     const float* dirs;
     const float* dist;
-    const float* bound;               // min over instances of the box SDF per sample, or NULL (no culling)
-    unsigned long long* cull_stats;   // {tiles skipped, tiles visited} or NULL
+    const int* fwd_samples;           // live samples of the forward field kernel per instance (vsrd_cull_samples), or NULL (no culling)
+    unsigned long long* cull_stats;   // {backward tiles skipped, visited, forward pairs skipped, visited} or NULL
     unsigned char* live;              // [N][tiles] marks of backward tiles with a non-zero adjoint, or NULL
 };
 
@@ -107,7 +107,7 @@ inline int check_rays(const VsrdRays* r, RaysDev& d) {
     VSRD_CHECK_ARG(r->num_rays >= 0, "num_rays must be non-negative");
     VSRD_CHECK_ARG(r->num_intervals >= 1 && r->num_intervals <= VSRD_MAX_INTERVALS, "num_intervals must be in [1, 512]");
     VSRD_CHECK_ARG(r->num_rays == 0 || (r->origins && r->directions && r->distances), "ray pointers must not be NULL");
-    d = RaysDev{r->num_rays, r->num_intervals, r->origins, r->directions, r->distances, r->union_bound, r->cull_stats, r->live_tiles};
+    d = RaysDev{r->num_rays, r->num_intervals, r->origins, r->directions, r->distances, r->forward_samples, r->cull_stats, r->live_tiles};
     return 0;
 }
 

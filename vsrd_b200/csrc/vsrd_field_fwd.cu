@@ -2,7 +2,7 @@
 //
 //   residual instances  -> field_forward_umma_kernel (vsrd_field_umma.cu: tcgen05 / TMEM, one thread == one sample)
 //   box-only instances  -> field_forward_box_kernel below (warm-up steps, main.py:582-618: ~200 flop per sample)
-//   union_bound_kernel     the culling bound (min box SDF over the instances)
+//   cull_samples_kernel    instance culling: box field of the culled (sample, instance) pairs + per-instance lists of the live samples
 #include "vsrd_common.cuh"
 
 namespace vsrd {
@@ -28,25 +28,77 @@ __global__ void __launch_bounds__(kThreads) field_forward_box_kernel(SceneDev sc
         I.R[6] * b.gp[0] + I.R[7] * b.gp[1] + I.R[8] * b.gp[2]);
 }
 
-// min over the instances of the BOX SDF at every sample (the culling bound, see VsrdRays::union_bound)
-__global__ void union_bound_kernel(SceneDev scene, RaysDev rays, float* __restrict__ bound) {
-    __shared__ Instance s_inst[VSRD_MAX_INSTANCES];       // 15 floats per instance, staged once per CTA
+// Instance culling, forward side (VsrdRays::forward_samples): one thread per sample.  It evaluates the BOX SDF of every
+// instance there; an instance whose box SDF exceeds the lowest one + 1 (the residual's range) by more than
+// VSRD_CULL_LOG_EPS * temperature has a soft-min weight < exp(-20) (include/vsrd_b200.h, VsrdRays).  For such a pair the field is the box field,
+// written here, and the residual kernel never sees it; the other pairs are appended to the instance's list of live
+// samples (one atomic per (CTA, instance) reserves a range, the order inside the range is the sample order; the
+// counters sit one cache line apart: 6 k atomics on ONE line cost 10 us, measured).
+constexpr int kCullThreads = 256;
+__global__ void __launch_bounds__(kCullThreads) cull_samples_kernel(SceneDev scene, RaysDev rays, float4* __restrict__ field,
+                                                                  int* __restrict__ lists) {
+    __shared__ Instance s_inst[VSRD_MAX_INSTANCES];
+    __shared__ float s_val[VSRD_MAX_INSTANCES][kCullThreads];
+    __shared__ unsigned s_ballot[VSRD_MAX_INSTANCES][kCullThreads / 32];
+    __shared__ int s_base[VSRD_MAX_INSTANCES];
     for (int i = threadIdx.x; i < scene.N; i += blockDim.x) load_instance(scene, i, s_inst[i]);
     __syncthreads();
-    const size_t total = (size_t)rays.R * rays.M;
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const int r = (int)(idx / rays.M);
-    const int j = (int)(idx - (size_t)r * rays.M);
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int total = rays.R * rays.M;
+    const bool in_range = blockIdx.x * kCullThreads + t < total;
+    const int idx = min(blockIdx.x * kCullThreads + t, total - 1);
+    const int r = idx / rays.M;
+    const int j = idx - r * rays.M;
     float x[3];
     sample_position(rays, r, j, x);
     float lowest = INFINITY;
     for (int i = 0; i < scene.N; ++i) {
         BoxEval b;
         box_eval(x, s_inst[i], b);
+        s_val[i][t] = b.value;
         lowest = fminf(lowest, b.value);
     }
-    bound[idx] = lowest;
+    const float threshold = lowest + 1.0f + kCullLogEps * scene_temperature(scene);
+    unsigned live = 0;                                     // bit i: instance i needs its residual MLP at this sample
+    for (int i = 0; i < scene.N; ++i) {
+        const bool far = s_val[i][t] > threshold;
+        if (in_range && far) {                             // rare early in the schedule, most pairs late: the box field
+            const Instance& I = s_inst[i];
+            BoxEval b;
+            box_eval(x, I, b);
+            field[(size_t)i * total + idx] = make_float4(
+                b.value,
+                I.R[0] * b.gp[0] + I.R[1] * b.gp[1] + I.R[2] * b.gp[2],
+                I.R[3] * b.gp[0] + I.R[4] * b.gp[1] + I.R[5] * b.gp[2],
+                I.R[6] * b.gp[0] + I.R[7] * b.gp[1] + I.R[8] * b.gp[2]);
+        }
+        const unsigned votes = __ballot_sync(kFull, in_range && !far);
+        if (lane == 0) s_ballot[i][warp] = votes;
+        live |= (in_range && !far) ? 1u << i : 0u;
+    }
+    __syncthreads();
+    if (t < scene.N) {
+        int count = 0;
+#pragma unroll
+        for (int w = 0; w < kCullThreads / 32; ++w) count += __popc(s_ballot[t][w]);
+        s_base[t] = count ? atomicAdd(lists + t * VSRD_CULL_COUNT_STRIDE, count) : 0;
+    }
+    if (t == VSRD_MAX_INSTANCES && rays.cull_stats != nullptr) {
+        int kept = 0;
+        for (int i = 0; i < scene.N; ++i)
+#pragma unroll
+            for (int w = 0; w < kCullThreads / 32; ++w) kept += __popc(s_ballot[i][w]);
+        const int visited = scene.N * min(kCullThreads, total - (int)blockIdx.x * kCullThreads);
+        atomicAdd(rays.cull_stats + 2, (unsigned long long)(visited - kept));
+        atomicAdd(rays.cull_stats + 3, (unsigned long long)visited);
+    }
+    __syncthreads();
+    for (int i = 0; i < scene.N; ++i) {
+        if (!((live >> i) & 1u)) continue;
+        int pos = s_base[i] + __popc(s_ballot[i][warp] & ((1u << lane) - 1u));
+        for (int w = 0; w < warp; ++w) pos += __popc(s_ballot[i][w]);
+        lists[VSRD_CULL_HEADER_INTS + (size_t)i * total + pos] = idx;
+    }
 }
 
 }  // namespace vsrd
@@ -77,14 +129,18 @@ int vsrd_field_forward(const VsrdScene* scene, const VsrdRays* rays, float* fiel
     return launch_field(s, r, field, stream);
 }
 
-int vsrd_union_bound(const VsrdScene* scene, const VsrdRays* rays, float* union_bound, void* stream) {
+int vsrd_cull_samples(const VsrdScene* scene, const VsrdRays* rays, float* field, int32_t* forward_samples, void* stream) {
     SceneDev s; RaysDev r;
     if (check_scene(scene, s) || check_rays(rays, r)) return 1;
     const size_t total = (size_t)r.R * r.M;
     if (total == 0) return 0;
-    VSRD_CHECK_ARG(union_bound != nullptr, "union_bound is NULL");
+    VSRD_CHECK_ARG(field != nullptr && forward_samples != nullptr, "NULL pointer");
     VSRD_CHECK_ARG(total < (size_t)1 << 31, "R*M must be < 2^31");
-    union_bound_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(s, r, union_bound);
+    static_assert(VSRD_MAX_INSTANCES < kCullThreads, "cull_samples_kernel: one thread per instance plus one for the statistics");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (cudaMemsetAsync(forward_samples, 0, VSRD_CULL_HEADER_INTS * sizeof(int32_t), st) != cudaSuccess)
+        return fail("vsrd_b200: cudaMemsetAsync failed%s");
+    cull_samples_kernel<<<(unsigned)((total + kCullThreads - 1) / kCullThreads), kCullThreads, 0, st>>>(s, r, (float4*)field, forward_samples);
     VSRD_CHECK_LAUNCH();
     return 0;
 }

@@ -123,16 +123,36 @@ __global__ void __launch_bounds__(kGroups * kGroupThreads, 1) field_forward_umma
     uint32_t parity = 0;
 
     const int total = rays.R * rays.M;
-    const long long all_tiles = (long long)scene.N * tiles_per_inst;
+    // Tile source.  Dense: all N x tiles_per_inst tiles of 128 consecutive samples in (instance, tile) order.  Culled
+    // (kCull): cull_samples_kernel has listed the live samples of every instance (and has already written the box field
+    // of the others); a tile is then 128 consecutive ENTRIES of an instance's list -- a thread computes its sample from
+    // (ray, interval) alone, so gathering costs nothing -- and every CTA gets the same number of live tiles.
+    const int* counts = rays.fwd_samples;                  // [i * VSRD_CULL_COUNT_STRIDE] live samples of instance i
+    const int* lists = kCull ? rays.fwd_samples + VSRD_CULL_HEADER_INTS : nullptr;   // [N][R * M] their flat indices
+    auto live_tiles = [&](int i) { return (long long)((__ldg(counts + i * VSRD_CULL_COUNT_STRIDE) + kTile - 1) / kTile); };
+    long long all_tiles = 0;
+    if constexpr (kCull) {
+        for (int i = 0; i < scene.N; ++i) all_tiles += live_tiles(i);
+    } else {
+        all_tiles = (long long)scene.N * tiles_per_inst;
+    }
     const long long begin = all_tiles * blockIdx.x / gridDim.x;
     const long long end = all_tiles * (blockIdx.x + 1) / gridDim.x;
-    const float cull_margin = kCullLogEps * scene_temperature(scene);
     const float pi_scale = kPiF / scene.scale;
-    unsigned tiles_visited = 0, tiles_culled = 0;
+    int inst = 0;
+    long long inst_first = 0;                              // index of the instance's first tile in the tile order
 
     for (long long seg = begin; seg < end;) {
-        const int inst = (int)(seg / tiles_per_inst);
-        const long long seg_end = min(end, (long long)(inst + 1) * tiles_per_inst);
+        long long inst_tiles;
+        if constexpr (kCull) {
+            while (seg >= inst_first + live_tiles(inst)) { inst_first += live_tiles(inst); ++inst; }
+            inst_tiles = live_tiles(inst);
+        } else {
+            inst = (int)(seg / tiles_per_inst);
+            inst_first = (long long)inst * tiles_per_inst;
+            inst_tiles = tiles_per_inst;
+        }
+        const long long seg_end = min(end, inst_first + inst_tiles);
         fence_before_sync();
         __syncthreads();                                   // every group is done with the previous instance's weights
         stage_weights_umma(scene.W + (size_t)inst * kNumW, sW);
@@ -144,47 +164,23 @@ __global__ void __launch_bounds__(kGroups * kGroupThreads, 1) field_forward_umma
 
 #pragma unroll 1
         for (long long tile = seg + group; tile < seg_end; tile += kGroups) {
-            const int base = (int)(tile - (long long)inst * tiles_per_inst) * kTile;
-            const bool in_range = base + gt < total;
-            const int idx = min(base + gt, total - 1);
+            const int base = (int)(tile - inst_first) * kTile;
+            bool in_range;
+            int idx;
+            if constexpr (kCull) {
+                const int count = __ldg(counts + inst * VSRD_CULL_COUNT_STRIDE);
+                in_range = base + gt < count;
+                idx = __ldg(lists + (size_t)inst * total + min(base + gt, count - 1));
+            } else {
+                in_range = base + gt < total;
+                idx = min(base + gt, total - 1);
+            }
             const int r = idx / rays.M;
             const int j = idx - r * rays.M;
             float x[3];
             sample_position(rays, r, j, x);
             BoxEval b;
             box_eval(x, I, b);
-            if constexpr (kCull) {
-                // instance culling (VsrdRays::union_bound): a sample farther from this box than the nearest box + the
-                // residual's range + 30 T has a soft-min weight < 1e-13: the box field suffices.  A TILE whose four warps
-                // are all far is skipped outright; a WARP whose 32 samples are all far writes the box field and then only
-                // keeps the group's eight round trips company (barriers, the MMA issue if it owns the issuing thread, the
-                // mbarrier waits): its TMEM lanes carry stale operands, which only reach its own, unread, accumulator rows.
-                const bool far = !in_range || b.value - (__ldg(rays.bound + idx) + 1.0f) > cull_margin;
-                const bool skip = __all_sync(kFull, far);
-                int all_far;
-                asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %1, 0;\n\tbar.red.and.pred q, %2, %3, p;\n\tselp.b32 %0, 1, 0, q;\n\t}"
-                             : "=r"(all_far) : "r"((int)skip), "r"(1 + group), "r"(kGroupThreads) : "memory");
-                if ((tid & 31) == 0) { ++tiles_visited; tiles_culled += skip ? 1u : 0u; }
-                if (skip) {
-                    if (in_range)
-                        field[(size_t)inst * total + base + gt] = make_float4(
-                            b.value,
-                            I.R[0] * b.gp[0] + I.R[1] * b.gp[1] + I.R[2] * b.gp[2],
-                            I.R[3] * b.gp[0] + I.R[4] * b.gp[1] + I.R[5] * b.gp[2],
-                            I.R[6] * b.gp[0] + I.R[7] * b.gp[1] + I.R[8] * b.gp[2]);
-                    if (all_far) continue;
-#pragma unroll 1
-                    for (int stage = 0; stage < 8; ++stage) {
-                        fence_before_sync();
-                        named_barrier(1 + group, kGroupThreads);
-                        if (gt == 0) issue_stage(stage, tmem, wdesc, idesc, mbar);
-                        mbar_wait(mbar, parity); parity ^= 1;
-                        fence_after_sync();
-                    }
-                    fence_before_sync();
-                    continue;
-                }
-            }
             // ------------------------------------------------------------ L0: positional encoding -> h0, g_c
             f2 h[8];
             {
@@ -273,7 +269,7 @@ __global__ void __launch_bounds__(kGroups * kGroupThreads, 1) field_forward_umma
             const float gp1 = b.gp[1] + sp * ga[1];
             const float gp2 = b.gp[2] + sp * ga[2];
             if (in_range)
-                field[(size_t)inst * total + base + gt] = make_float4(
+                field[(size_t)inst * total + idx] = make_float4(
                     b.value + res,
                     I.R[0] * gp0 + I.R[1] * gp1 + I.R[2] * gp2,
                     I.R[3] * gp0 + I.R[4] * gp1 + I.R[5] * gp2,
@@ -282,10 +278,6 @@ __global__ void __launch_bounds__(kGroups * kGroupThreads, 1) field_forward_umma
             fence_before_sync();
         }
         seg = seg_end;
-    }
-    if ((tid & 31) == 0 && rays.cull_stats != nullptr && tiles_visited) {
-        atomicAdd(rays.cull_stats, (unsigned long long)tiles_culled);
-        atomicAdd(rays.cull_stats + 1, (unsigned long long)tiles_visited);
     }
     fence_before_sync();
     __syncthreads();
@@ -303,7 +295,7 @@ static void launch_umma(const SceneDev& s, const RaysDev& r, float* field, size_
     const long long all_tiles = (long long)s.N * tiles_per_inst;
     const long long want = (all_tiles + kGroups - 1) / kGroups;
     const int grid = (int)(want < g_umma_sms ? want : g_umma_sms);
-    if (r.bound != nullptr)        // instance culling on (fine pass): the variant with the per-warp skip logic
+    if (r.fwd_samples != nullptr)  // instance culling on: the variant that walks the lists of live samples
         fu::field_forward_umma_kernel<kGroups, true><<<grid, kGroups * fu::kGroupThreads, fu::smem_bytes(kGroups), st>>>(
             s, r, (float4*)field, tiles_per_inst);
     else

@@ -358,7 +358,8 @@ __global__ void __launch_bounds__(VSRD_MAX_INTERVALS, NMAX <= 8 ? 2 : 1) composi
     OpacityEval o;
     float alpha = 0.0f, a = 0.0f, delta = 0.0f;
     unsigned live_mask = 0;                             // instances with a non-zero adjoint at this sample
-    constexpr float kCullWeight = 9.3576e-14f;          // exp(-VSRD_CULL_LOG_EPS)
+    constexpr float kCullWeight = 2.0611537e-9f;        // exp(-VSRD_CULL_LOG_EPS)
+    static_assert(VSRD_CULL_LOG_EPS == 20.0f, "kCullWeight = exp(-VSRD_CULL_LOG_EPS)");
     constexpr bool kRegs = NMAX <= kRegsMaxInstances;   // all instances' field values live in registers
     UnionRegs<kRegs ? NMAX : 1> ur;
     if (valid) {
@@ -409,7 +410,7 @@ __global__ void __launch_bounds__(VSRD_MAX_INTERVALS, NMAX <= 8 ? 2 : 1) composi
         auto store = [&](int i, const Vec4& q) {
             Vec4 v = q;
             if (rays.live != nullptr) {
-                // culling: an instance whose soft-min weight is below exp(-30) gets an exactly zero adjoint
+                // culling: an instance whose soft-min weight is below exp(-VSRD_CULL_LOG_EPS) gets an exactly zero adjoint
                 float wi;
                 if constexpr (kRegs) wi = ur.e[i] * ur.invZ;
                 else wi = expf(-(load(i).x / T) - u.mneg) / u.Z;

@@ -19,8 +19,8 @@ from .functional import distance_bins
 
 
 class SilhouetteStep:
-    # gather, place_coarse, field, composite, place_fine, cull bound, field, composite, composite_bwd, field_bwd, reduce
-    KERNELS_PER_STEP = 11
+    # gather, place_coarse, cull, field, composite, place_fine, cull, field, composite, composite_bwd, field_bwd, reduce
+    KERNELS_PER_STEP = 12
 
     def __init__(self, *, inv_projection, camera_positions, image_size, num_rays: int, num_samples: int,
                  distance_range=(0.0, 100.0), scale: float = 100.0, epsilon: float = 1e-6,
@@ -89,7 +89,7 @@ class SilhouetteStep:
         coarse = ops.place_coarse(self.bins, self.num_rays, None, self.seed)
         self._mark("place_coarse")
         rays_c = ops.RayArgs(origins, dirs, coarse)
-        field_c = ops.field_forward(scene, rays_c, cull=False)
+        field_c = ops.field_forward(scene, rays_c, backward=False)
         self._mark("field_forward_coarse")
         _, _, coarse_w, _ = ops.composite_forward(scene, rays_c, field_c, s["std_deviation"], s["cosine_ratio"], self.epsilon)
         self._mark("composite_forward_coarse")
@@ -103,6 +103,7 @@ class SilhouetteStep:
             targets=self.targets, silhouette_weight=self.silhouette_weight, eikonal_weight=eik_w)
         self._mark("composite_forward_fine")
         self.out = dict(labels=labels, loss_parts=loss_parts, fine_distances=fine, coarse_weights=coarse_w)
+        self.rays = dict(coarse=rays_c, fine=rays_f)     # culling lists of the last step (RayArgs.live_pairs)
         if backward:
             adjoint = ops.composite_backward(
                 scene, rays_f, field_f, s["std_deviation"], s["cosine_ratio"], self.epsilon,

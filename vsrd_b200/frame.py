@@ -185,8 +185,9 @@ class FrameLabeler:
             with torch.cuda.stream(self.stream):
                 self._draw_ahead(self.state)          # batch of step 0
                 self.state_ahead.set_step(1)
-        self._graphs: Dict[bool, torch.cuda.CUDAGraph] = {}
-        self._eager_done: Dict[bool, int] = {False: 0, True: 0}
+        # phases: 0 = warm-up (box only), 1 = residual field, 2 = residual field + forward culling pre-pass (late schedule)
+        self._graphs: Dict[int, torch.cuda.CUDAGraph] = {}
+        self._eager_done: Dict[int, int] = {0: 0, 1: 0, 2: 0}
 
     # ---- one optimisation step (main.py:328-865), enqueued on the current stream (= self.stream) ----
     def _step_body(self, residual: bool) -> None:
@@ -252,7 +253,7 @@ class FrameLabeler:
         scene = ops.SceneArgs(loc, rot, dim, mlp_weights, 1.0, self.scale, st)
         coarse = ops.place_coarse(self.bins, self.num_rays, self.jitter, 0, st)
         rays = ops.RayArgs(origins, directions, coarse)
-        field = ops.field_forward(scene, rays, cull=False)
+        field = ops.field_forward(scene, rays, backward=False)
         _, _, coarse_w, _ = ops.composite_forward(scene, rays, field, 1.0, 0.0, 1e-6)
         fine = ops.place_fine(coarse, coarse_w, self.sorted_uniforms, 0, st)
         rays = ops.RayArgs(origins, directions, fine)
@@ -294,11 +295,23 @@ class FrameLabeler:
                 self.state_ahead.set_step(step + 1)
         self.step_index = int(step)
 
-    def _capture(self, residual: bool) -> None:
+    def phase_of(self, step: int) -> int:
+        """0 = warm-up (box only, main.py:582-618), 1 = residual field, 2 = residual field with the forward culling
+        pre-pass: worth its launch once the temperature has dropped to ops.FORWARD_CULL_MAX_TEMPERATURE."""
+        if step < self.warmup_steps:
+            return 0
+        late = self.state.temperature_at(step) <= ops.FORWARD_CULL_MAX_TEMPERATURE
+        return 2 if late and ops.culling_enabled() and self.inputs.num_instances > 1 else 1
+
+    def _run_phase(self, phase: int) -> None:
+        self.state.forward_cull = phase == 2
+        self._step_body(phase >= 1)
+
+    def _capture(self, phase: int) -> None:
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph, stream=self.stream):
-            self._step_body(residual)
-        self._graphs[residual] = graph
+            self._run_phase(phase)
+        self._graphs[phase] = graph
 
     def step(self, pixel_indices: Optional[torch.Tensor] = None, targets: Optional[torch.Tensor] = None,
              jitter: Optional[torch.Tensor] = None, sorted_uniforms: Optional[torch.Tensor] = None) -> None:
@@ -312,7 +325,7 @@ class FrameLabeler:
             raise RuntimeError(f"vsrd_b200: rays={self.rays!r} needs the ray batch of every step")
         if self.inject_samples and (jitter is None or sorted_uniforms is None):
             raise RuntimeError("vsrd_b200: inject_samples=True needs jitter and sorted_uniforms for every step")
-        residual = self.step_index >= self.warmup_steps
+        phase = self.phase_of(self.step_index)
         with torch.cuda.stream(self.stream):
             if self.rays != "draw":
                 self.pixel_indices.copy_(pixel_indices.reshape(-1), non_blocking=True)
@@ -321,14 +334,14 @@ class FrameLabeler:
             if self.inject_samples:
                 self.jitter.copy_(jitter.reshape(self.jitter.shape), non_blocking=True)
                 self.sorted_uniforms.copy_(sorted_uniforms.reshape(self.sorted_uniforms.shape), non_blocking=True)
-            if self.use_graph and residual not in self._graphs and self._eager_done[residual] >= 3:
-                self._capture(residual)
-            if self.use_graph and residual in self._graphs:
-                self._graphs[residual].replay()
+            if self.use_graph and phase not in self._graphs and self._eager_done[phase] >= 3:
+                self._capture(phase)
+            if self.use_graph and phase in self._graphs:
+                self._graphs[phase].replay()
             else:
                 # without graphs, or for the first steps of each phase (allocator / cuBLAS warm-up before capture)
-                self._step_body(residual)
-                self._eager_done[residual] += 1
+                self._run_phase(phase)
+                self._eager_done[phase] += 1
         self.step_index += 1
 
     def synchronize(self) -> None:

@@ -22,11 +22,11 @@ class _RenderPass(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, locations, rotations, half_extents, mlp_weights, origins, directions, distances,
-                temperature, scale, std_deviation, cosine_ratio, epsilon, step_state=None, cull=None):
+                temperature, scale, std_deviation, cosine_ratio, epsilon, step_state=None, differentiable=True):
         scene = SceneArgs(locations.detach(), rotations.detach(), half_extents.detach(),
                           None if mlp_weights is None else mlp_weights.detach(), temperature, scale, step_state)
         rays = RayArgs(origins.detach(), directions.detach(), distances.detach())
-        field = ops.field_forward(scene, rays, cull=cull)
+        field = ops.field_forward(scene, rays, backward=differentiable)
         labels, grads, weights, _ = ops.composite_forward(scene, rays, field, std_deviation, cosine_ratio, epsilon)
         ctx.scene, ctx.rays, ctx.field = scene, rays, field
         ctx.render = (std_deviation, cosine_ratio, epsilon)
@@ -54,12 +54,12 @@ def render_pass(locations, rotations, half_extents, mlp_weights, ray_positions, 
     differentiable w.r.t. the first four arguments.  `step_state` (ops.StepState) makes the kernels read
     temperature / std_deviation / cosine_ratio from device memory instead (CUDA-graph replay across steps).
     """
-    # no-grad calls are the coarse placement passes of the two-pass wrapper (main.py:515-516): culling off there
-    # (ops.field_forward); decided here because grad mode is always off inside Function.forward
-    cull = None if torch.is_grad_enabled() else False
+    # no-grad calls are the coarse placement passes of the two-pass wrapper (main.py:515-516): no backward tile marks
+    # there (ops.field_forward); decided here because grad mode is always off inside Function.forward
+    differentiable = torch.is_grad_enabled()
     return _RenderPass.apply(locations, rotations, half_extents, mlp_weights, ray_positions, ray_directions,
                              distances, float(temperature), float(scale), float(std_deviation),
-                             float(cosine_ratio), float(epsilon), step_state, cull)
+                             float(cosine_ratio), float(epsilon), step_state, differentiable)
 
 
 def distance_bins(distance_range: Sequence[float], num_samples: int, device) -> torch.Tensor:

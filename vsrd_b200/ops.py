@@ -7,6 +7,7 @@ enqueued on torch's current stream, so the calls compose with CUDA graphs and st
 from __future__ import annotations
 
 import ctypes
+import math
 import os
 from typing import Optional, Tuple
 
@@ -78,33 +79,57 @@ class RayArgs:
         self.num_intervals = self.distances.shape[1] - 1
         if self.num_intervals > _lib.MAX_INTERVALS:
             raise RuntimeError(f"vsrd_b200: at most {_lib.MAX_INTERVALS} intervals per ray, got {self.num_intervals}")
-        self.union_bound = None       # culling bound and backward tile marks (enable_culling)
+        self.forward_samples = None   # live-sample lists of the forward kernel and backward tile marks (enable_culling)
         self.live_tiles = None
         self.struct = VsrdRays(r, self.num_intervals, _ptr(self.origins), _ptr(self.directions), _ptr(self.distances), None, None, None)
 
-    def enable_culling(self, scene: "SceneArgs") -> None:
-        """Computes the per-sample culling bound (min box SDF over the instances, one small launch) and attaches it:
-        the field kernels then skip the residual MLP on warp tiles whose soft-min weight is provably < 1e-13
-        (include/vsrd_b200.h, VsrdRays::union_bound)."""
-        if self.union_bound is not None or self.num_rays == 0:
+    def enable_backward_culling(self, scene: "SceneArgs") -> None:
+        """Attaches the tile marks of the backward kernels (include/vsrd_b200.h, VsrdRays::live_tiles): vsrd_composite_backward
+        zeroes the adjoints of instances whose soft-min weight is below exp(-VSRD_CULL_LOG_EPS) and marks the tiles that
+        still carry one; vsrd_field_backward visits the marked tiles only.  No extra launch."""
+        if self.num_rays == 0 or self.live_tiles is not None:
+            return
+        bwd_rows = _lib.load().vsrd_backward_tile_rows()
+        if bwd_rows < 1:
+            _lib.check(1)
+        samples = self.num_rays * self.num_intervals
+        self.live_tiles = torch.zeros(scene.num_instances, (samples + bwd_rows - 1) // bwd_rows,
+                                      device=self.directions.device, dtype=torch.uint8)
+        self.struct.live_tiles = _ptr(self.live_tiles)
+        self.struct.cull_stats = _ptr(_cull_stats(self.directions.device))
+
+    def cull_forward(self, scene: "SceneArgs", field: torch.Tensor) -> None:
+        """Runs the culling pre-pass for `field` (one launch of ~15-25 us at R = 1000: the box field of the (sample,
+        instance) pairs whose soft-min weight is provably < exp(-20) is written here, the other samples are listed per
+        instance) and attaches the lists: the residual field kernel then evaluates the listed samples only
+        (include/vsrd_b200.h, VsrdRays::forward_samples)."""
+        if self.num_rays == 0:
             return
         dev = self.directions.device
-        self.union_bound = torch.empty(self.num_rays * self.num_intervals, device=dev, dtype=torch.float32)
-        _lib.check(_lib.load().vsrd_union_bound(ctypes.byref(scene.struct), ctypes.byref(self.struct),
-                                                _ptr(self.union_bound), _stream()))
-        rows = _lib.load().vsrd_backward_tile_rows()
-        if rows < 1:
-            _lib.check(1)
-        tiles = (self.num_rays * self.num_intervals + rows - 1) // rows
-        self.live_tiles = torch.zeros(scene.num_instances, tiles, device=dev, dtype=torch.uint8)
-        self.struct.union_bound = _ptr(self.union_bound)
-        self.struct.cull_stats = _ptr(_cull_stats(dev))
-        self.struct.live_tiles = _ptr(self.live_tiles)
+        samples = self.num_rays * self.num_intervals
+        if self.forward_samples is None:
+            self.forward_samples = torch.empty(_lib.CULL_HEADER_INTS + scene.num_instances * samples, device=dev, dtype=torch.int32)
+            self.struct.cull_stats = _ptr(_cull_stats(dev))
+        _lib.check(_lib.load().vsrd_cull_samples(ctypes.byref(scene.struct), ctypes.byref(self.struct), _ptr(field),
+                                                 _ptr(self.forward_samples), _stream()))
+        self.struct.forward_samples = _ptr(self.forward_samples)
+        self.num_instances = scene.num_instances
+
+    def live_pairs(self):
+        """(live, total) (sample, instance) pairs of the last culling pre-pass on these rays (synchronises); None
+        without culling."""
+        if self.forward_samples is None:
+            return None
+        live = int(self.forward_samples[:_lib.CULL_HEADER_INTS:_lib.CULL_COUNT_STRIDE][:self.num_instances].sum())
+        return live, self.num_instances * self.num_rays * self.num_intervals
 
 
 # ---- instance culling (SURVEY.md 8d) -----------------------------------------------------------------
 _culling = os.environ.get("VSRD_CULL", "1") != "0"
 _cull_counters = {}
+# The forward pre-pass costs ~35 us per two-pass step at R = 1000 (profiles/r02_forward_culling.txt) and culls nothing
+# while 1 + 20 T exceeds the distances between the boxes of a street scene: it runs once the temperature is at most
+FORWARD_CULL_MAX_TEMPERATURE = 0.5
 
 
 def set_culling(enabled: bool) -> None:
@@ -113,20 +138,25 @@ def set_culling(enabled: bool) -> None:
     _culling = bool(enabled)
 
 
+def culling_enabled() -> bool:
+    return _culling
+
+
 def _cull_stats(device) -> torch.Tensor:
     key = torch.device(device).index or 0
     if key not in _cull_counters:
-        _cull_counters[key] = torch.zeros(2, dtype=torch.int64, device=device)
+        _cull_counters[key] = torch.zeros(4, dtype=torch.int64, device=device)
     return _cull_counters[key]
 
 
-def culling_counters(device="cuda", reset: bool = False):
-    """(warp tiles skipped, warp tiles visited) accumulated by the field kernels on `device` (synchronises)."""
+def culling_counters(device="cuda", reset: bool = False, forward: bool = False):
+    """(skipped, visited) accumulated on `device` (synchronises): tiles of the backward field kernel
+    (vsrd_backward_tile_rows() samples each), or with `forward` the (sample, instance) pairs of the culling pre-pass."""
     t = _cull_stats(torch.device(device))
-    culled, visited = (int(v) for v in t.cpu())
+    v = [int(x) for x in t.cpu()]
     if reset:
         t.zero_()
-    return culled, visited
+    return (v[2], v[3]) if forward else (v[0], v[1])
 
 
 def _state_ptr(step_state) -> Optional[int]:
@@ -200,14 +230,21 @@ def place_fine(coarse_distances, coarse_weights, sorted_uniforms: Optional[torch
 
 # ---- field + compositing ----------------------------------------------------------------------
 
-def field_forward(scene: SceneArgs, rays: RayArgs, cull: Optional[bool] = None) -> torch.Tensor:
-    """`cull`: instance culling for this pass (None = the module default, see set_culling).  Callers switch it off for
-    the coarse pass: its 32-sample tiles span ~32 m of ray and are almost never skippable, so the bound launch is not
-    worth it there."""
-    if (_culling if cull is None else cull) and scene.mlp_weights is not None:
-        rays.enable_culling(scene)
+def field_forward(scene: SceneArgs, rays: RayArgs, cull: Optional[bool] = None, backward: bool = True,
+                  forward_cull: Optional[bool] = None) -> torch.Tensor:
+    """`cull`: instance culling for this pass (None = the module default, see set_culling); `backward`: the pass will
+    be differentiated (attach the backward kernels' tile marks); `forward_cull`: run the forward culling pre-pass
+    (None = by temperature: the scene's own, or the decision its StepState carries, see FORWARD_CULL_MAX_TEMPERATURE)."""
     field = torch.empty(scene.num_instances, rays.num_rays * rays.num_intervals, 4,
                         device=rays.directions.device, dtype=torch.float32)
+    if (_culling if cull is None else cull) and scene.mlp_weights is not None and scene.num_instances > 1:
+        if backward:
+            rays.enable_backward_culling(scene)
+        if forward_cull is None:
+            forward_cull = (scene.temperature <= FORWARD_CULL_MAX_TEMPERATURE if scene.step_state is None
+                            else scene.step_state.forward_cull)
+        if forward_cull:
+            rays.cull_forward(scene, field)
     _lib.check(_lib.load().vsrd_field_forward(ctypes.byref(scene.struct), ctypes.byref(rays.struct), _ptr(field), _stream()))
     return field
 
@@ -293,7 +330,14 @@ class StepState:
                                      float(std_deviation[0]), float(std_deviation[1]), float(eikonal_weight), 0.0,
                                      int(seed) & (2 ** 64 - 1))
         self.buffer = torch.zeros(ctypes.sizeof(VsrdStepState), dtype=torch.uint8, device=device)
+        self.forward_cull = False     # host-side: whether field_forward runs the culling pre-pass (the owner decides per phase)
         self.set_step(0)
+
+    def temperature_at(self, step: int) -> float:
+        """Host copy of the annealed temperature of `step` (scripts/main.py:420-431)."""
+        s = self.schedule
+        x = (math.cos(math.pi * step / max(s.num_steps, 1)) + 1.0) / 2.0
+        return x * (s.max_temperature - s.min_temperature) + s.min_temperature
 
     @property
     def ptr(self) -> int:
