@@ -92,14 +92,18 @@ typedef struct VsrdRays {
      * tiles visited (vsrd_backward_tile_rows() samples each), forward (sample, instance) pairs skipped, visited}. */
     int32_t* forward_samples;
     unsigned long long* cull_stats;
-    /* Backward side of the culling: live_tiles [N][ceil(R*M / vsrd_backward_tile_rows())] bytes, ZEROED by the caller
+    /* Backward side of the culling: live_tiles, vsrd_live_tiles_bytes() bytes ([N][ceil(R*M / vsrd_backward_tile_rows())] marks,
+     * then int32 counts of live samples per block of VSRD_CENSUS_BLOCK_TILES tiles), ZEROED by the caller
      * before vsrd_composite_backward, which (a) writes exact zeros for the adjoints of instances whose soft-min weight
      * is below exp(-VSRD_CULL_LOG_EPS) and (b) marks every warp tile of vsrd_field_backward that received a non-zero
      * adjoint.  vsrd_field_backward then visits only the marked tiles (compacted in order per thread block, so the
      * work is balanced and the accumulation order stays deterministic).  NULL disables it. */
     uint8_t* live_tiles;
 } VsrdRays;
+/* Bytes of VsrdRays::live_tiles for (N, R, M): the marks plus the per-block census behind them. */
+size_t vsrd_live_tiles_bytes(int num_instances, int num_rays, int num_intervals);
 #define VSRD_CULL_COUNT_STRIDE 32
+#define VSRD_CENSUS_BLOCK_TILES 128
 #define VSRD_CULL_HEADER_INTS (VSRD_MAX_INSTANCES * VSRD_CULL_COUNT_STRIDE)
 #define VSRD_CULL_LOG_EPS 20.0f      /* x exp(-x) < 2^-24 = 5.96e-8 for x >= 20: value AND gradient terms of the soft-min */
 /* Samples per warp tile of the backward field kernel (16 or 32), for sizing VsrdRays::live_tiles. */

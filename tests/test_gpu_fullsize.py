@@ -31,9 +31,10 @@ def ops():
 
 @pytest.fixture(params=[True, False], ids=["cull", "nocull"])
 def culling(request, ops):
-    ops.set_culling(request.param)
+    default = ops.CULL_MAX_TEMPERATURE
+    ops.set_culling(request.param, max_temperature=float("inf"))      # cull at every temperature of the schedule
     yield request.param
-    ops.set_culling(True)
+    ops.set_culling(True, max_temperature=default)
 
 
 def _leaves(case, requires_grad):

@@ -42,7 +42,7 @@ def test_graph_replay_equals_eager_steps():
     a, _ = _labeler(frame, init, use_graph=True, **kw)
     b, _ = _labeler(frame, init, use_graph=False, **kw)
     ra, rb = a.run(), b.run()
-    # warm-up (0) and late residual phase with the forward culling pre-pass (2) were captured and replayed; the early
+    # warm-up (0) and late residual phase with instance culling (2) were captured and replayed; the early
     # residual phase (1) lasts three steps at this length, which run eagerly
     assert a._graphs.keys() >= {0, 2}, a._graphs.keys()
     assert torch.isfinite(ra["boxes_3d"]).all()

@@ -236,8 +236,9 @@ def test_instance_culling_is_invisible_at_the_parity_bar(F, n, layout, temperatu
     print(f"identical samples: labels {float((la - lb).abs().max()):.2e}, weights {float((fwa - fwb).abs().max()):.2e}, "
           f"gradients {float((ga - gb).abs().max()):.2e}, parameter gradients " + " ".join(f"{rel(a, b):.1e}" for a, b in zip(gra, grb)))
     assert float((la - lb).abs().max()) < 5e-7 and float((fwa - fwb).abs().max()) < 5e-7
-    # union gradient: each culled instance may contribute up to 20 exp(-20) |grad d_i| = 4e-8 |grad d_i|, N - 1 of them
-    assert float((ga - gb).abs().max()) < 1e-5
+    # union gradient: each culled instance may contribute up to 20 exp(-20) = 4e-8 times the gradient of its residual
+    # (O(10) for a random-init field with frequencies up to 2^7 pi / 100 m), N - 1 of them: measured 6e-8 (N = 8), 1.5e-5 (N = 24)
+    assert float((ga - gb).abs().max()) < 5e-5
     for a, b in zip(gra, grb):       # + the live-tile list changes which warp sums which tile: fp32 summation-order noise
         assert rel(a, b) <= 2e-5, rel(a, b)
 

@@ -175,6 +175,7 @@ SIGNATURES = {
     "vsrd_place_coarse": (_I, [_V, _V, ctypes.c_uint64, _V, _I, _I, _V, _V]),
     "vsrd_place_fine": (_I, [_V, _V, _V, ctypes.c_uint64, _V, _I, _I, _V, _V]),
     "vsrd_cull_samples": (_I, [_P(VsrdScene), _P(VsrdRays), _V, _V, _V]),
+    "vsrd_live_tiles_bytes": (ctypes.c_size_t, [_I, _I, _I]),
     "vsrd_field_forward": (_I, [_P(VsrdScene), _P(VsrdRays), _V, _V]),
     "vsrd_composite_forward": (_I, [_P(VsrdScene), _P(VsrdRays), _P(VsrdRenderParams), _V, _V, _V, _V,
                                     _P(VsrdLoss), _V, _V]),

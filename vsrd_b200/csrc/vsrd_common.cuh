@@ -115,6 +115,12 @@ inline int check_rays(const VsrdRays* r, RaysDev& d) {
 // Rows of VSRD_GRAD_STRIDE floats the caller must provide in `partials` (-1 on error).
 int backward_mma_partial_rows(int num_instances);
 int backward_mma_tile_rows();         // samples per warp tile (16 or 32); -1 on error
+
+// VsrdRays::live_tiles: [N][tiles_per_inst] marks (bytes), then -- at the next multiple of 16 bytes -- the census:
+// int32 [N][census_blocks(tiles_per_inst)] = live samples per block of VSRD_CENSUS_BLOCK_TILES tiles, accumulated by
+// composite_backward_kernel next to the marks, read by backward_ranges_kernel to balance the backward field kernel's CTAs.
+__host__ __device__ inline int census_blocks(int tiles_per_inst) { return (tiles_per_inst + VSRD_CENSUS_BLOCK_TILES - 1) / VSRD_CENSUS_BLOCK_TILES; }
+__host__ __device__ inline size_t census_offset(int N, int tiles_per_inst) { return ((size_t)N * tiles_per_inst + 15) / 16 * 16; }
 int launch_field_backward_mma(const SceneDev& s, const RaysDev& r, const float* adjoint, float* partials,
                               float* gloc, float* grot, float* gdim, float* gW, cudaStream_t st);
 

@@ -184,6 +184,13 @@ extern "C" {
 
 int vsrd_backward_tile_rows(void) { return backward_mma_tile_rows(); }
 
+size_t vsrd_live_tiles_bytes(int num_instances, int num_rays, int num_intervals) {
+    const int rows = backward_mma_tile_rows();
+    if (rows < 1 || num_instances < 1 || num_rays < 0 || num_intervals < 0) return 0;
+    const int tiles_per_inst = (int)(((size_t)num_rays * num_intervals + rows - 1) / rows);
+    return census_offset(num_instances, tiles_per_inst) + sizeof(int32_t) * (size_t)num_instances * census_blocks(tiles_per_inst);
+}
+
 int vsrd_backward_blocks_per_instance(int num_instances, int num_rays, int num_intervals) {
     if (device_setup()) return -1;
     // box-only kernel: one row per CTA of its (G, N) grid; residual kernel: one row per (CTA, instance) segment, at most

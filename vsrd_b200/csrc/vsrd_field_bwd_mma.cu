@@ -138,13 +138,74 @@ __device__ __forceinline__ void pose_terms(const float x[3], const Instance& I, 
     p.coef[2] = pi_scale;
 }
 
+// range_starts[b], b = 0..grid: the first tile of CTA b when `grid` CTAs split the N * tiles_per_inst tiles (instance-
+// major order) into contiguous ranges.  Without culling marks the kernels split the tiles evenly themselves.  With them a block of tiles
+// weighs its live samples (the census vsrd_composite_backward keeps next to the marks, common.cuh::census_offset) plus
+// one per tile (a dead tile still has to be scanned), so that the CTAs get equal shares of LIVE work: late in the
+// schedule 3/4 of the tiles are dead, unevenly over the instances, and an even split of all tiles leaves the CTAs of the
+// nearest instances with several times the work of the others (measured: 75 % of the tiles skipped, kernel only 1.9x
+// faster).  One CTA: scans the block weights, places every range start by bisection + interpolation.  (Kept out of
+// the big kernel: computing the ranges there cost it 100 B of extra register spills.  Counting the marks here instead
+// of in the compositing kernel took 18 - 25 us on one SM.)
+constexpr int kRangeThreads = 1024;
+constexpr int kRangeMaxEntries = 4096;
+__global__ void __launch_bounds__(kRangeThreads) backward_ranges_kernel(const unsigned char* __restrict__ live, int N, int tiles_per_inst,
+                                                                       int group, int grid, long long* __restrict__ range_starts) {
+    const long long all_tiles = (long long)N * tiles_per_inst;
+    // entry k = `group` consecutive census blocks of one instance (group = 1 unless R is huge)
+    __shared__ long long s_prefix[kRangeMaxEntries];       // entry weights, then their inclusive prefix sums
+    __shared__ long long s_warp[kRangeThreads / 32];
+    const int* census = reinterpret_cast<const int*>(live + census_offset(N, tiles_per_inst));
+    const int nb = census_blocks(tiles_per_inst);
+    const int entries_per_inst = (nb + group - 1) / group, entry_tiles = group * VSRD_CENSUS_BLOCK_TILES;
+    const int num_entries = N * entries_per_inst;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int per = (num_entries + kRangeThreads - 1) / kRangeThreads;
+    const int k0 = min(threadIdx.x * per, num_entries), k1 = min(k0 + per, num_entries);
+    long long mine = 0;
+    for (int k = k0; k < k1; ++k) {
+        const int inst = k / entries_per_inst, j = k - inst * entries_per_inst;
+        const int len = min(entry_tiles, tiles_per_inst - j * entry_tiles);
+        long long alive = 0;
+        for (int q = j * group; q < min((j + 1) * group, nb); ++q) alive += __ldg(census + inst * nb + q);
+        mine += alive + len;
+        s_prefix[k] = mine;                                 // running sum inside the thread's run
+    }
+    long long incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const long long up = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += up; }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        long long v = s_warp[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const long long up = __shfl_up_sync(kFull, v, o); if (lane >= o) v += up; }
+        s_warp[lane] = v;
+    }
+    __syncthreads();
+    const long long before = incl - mine + (warp ? s_warp[warp - 1] : 0);
+    for (int k = k0; k < k1; ++k) s_prefix[k] += before;
+    __syncthreads();
+    const long long total_weight = s_prefix[num_entries - 1];
+    for (int b = threadIdx.x; b <= grid; b += blockDim.x) {
+        if (b == grid) { range_starts[b] = all_tiles; continue; }
+        const long long target = total_weight * b / grid;   // first entry whose inclusive prefix exceeds the target
+        int lo = 0, hi = num_entries - 1;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_prefix[mid] > target) hi = mid; else lo = mid + 1; }
+        const int inst = lo / entries_per_inst, j = lo - inst * entries_per_inst;
+        const int len = min(entry_tiles, tiles_per_inst - j * entry_tiles);
+        const long long base = lo ? s_prefix[lo - 1] : 0, weight = s_prefix[lo] - base;
+        range_starts[b] = (long long)inst * tiles_per_inst + (long long)j * entry_tiles + (target - base) * len / weight;
+    }
+}
+
 // PAIR (MT = 1 only): the lane == sample phases (1 and 4) serve TWO 16-sample tiles at once, lanes 0-15 the first and
 // lanes 16-31 the second tile of a pair taken from the live list; the fragment phases (2, 3) run once per half with the
 // one-m-tile register footprint.  Without it half the lanes idle through phases 1 and 4 (~10 % of the instructions).
 template <int MT, int PAIR>
 __global__ void __launch_bounds__(BwdCfg<MT>::kThreads, 1) field_backward_mma_kernel(
         SceneDev scene, RaysDev rays, const float4* __restrict__ adjoint, float* __restrict__ partials,
-        int tiles_per_inst) {
+        const long long* __restrict__ range_starts, int tiles_per_inst) {
     static_assert(PAIR == 0 || MT == 1, "tile pairs are a variant of the one-m-tile kernel");
     using Cfg = BwdCfg<MT>;
     constexpr int kWarpsB = Cfg::kWarps, kThreadsB = Cfg::kThreads, kRows = Cfg::kRows, kSlots = 2 * MT;
@@ -165,9 +226,10 @@ __global__ void __launch_bounds__(BwdCfg<MT>::kThreads, 1) field_backward_mma_ke
     const float4* fragL = sF + lane;
 
     const int total = rays.R * rays.M;
+    // CTA ranges: balanced by live work (backward_ranges_kernel) with culling, an even split of all tiles without
     const long long all_tiles = (long long)scene.N * tiles_per_inst;
-    const long long begin = all_tiles * blockIdx.x / gridDim.x;
-    const long long end = all_tiles * (blockIdx.x + 1) / gridDim.x;
+    const long long begin = range_starts ? range_starts[blockIdx.x] : all_tiles * blockIdx.x / gridDim.x;
+    const long long end = range_starts ? range_starts[blockIdx.x + 1] : all_tiles * (blockIdx.x + 1) / gridDim.x;
     const float pi_scale = kPiF / scene.scale;
     unsigned tiles_visited = 0, tiles_culled = 0;          // per warp; two atomics per warp at the end
     constexpr int kChunkTiles = 2048;
@@ -205,14 +267,16 @@ __global__ void __launch_bounds__(BwdCfg<MT>::kThreads, 1) field_backward_mma_ke
             if (warp == 0) {
                 const unsigned char* flags = live + (chunk - (long long)inst * tiles_per_inst);
                 const int per = (chunk_tiles + 31) / 32, first = lane * per, last = min(first + per, chunk_tiles);
-                int mine = 0;
-                for (int q = first; q < last; ++q) mine += __ldg(flags + q) ? 1 : 0;
+                static_assert(kChunkTiles <= 64 * 32, "one 64-bit mask of marks per lane");
+                unsigned long long marks = 0;               // one pass over the lane's (at most 64) marks
+#pragma unroll 8
+                for (int q = first; q < last; ++q) marks |= (unsigned long long)(__ldg(flags + q) ? 1 : 0) << (q - first);
+                const int mine = __popcll(marks);
                 int incl = mine;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { const int up = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += up; }
                 int pos = incl - mine;
-                for (int q = first; q < last; ++q)
-                    if (__ldg(flags + q)) s_list[pos++] = (unsigned short)q;
+                for (; marks; marks &= marks - 1) s_list[pos++] = (unsigned short)(first + __ffsll((long long)marks) - 1);
                 if (lane == 31) s_live = incl;
             }
             __syncthreads();
@@ -667,19 +731,27 @@ __global__ void __launch_bounds__(BwdCfg<MT>::kThreads, 1) field_backward_mma_ke
     }
 }
 
-// Sum the partial rows of every instance: the CTAs whose tile range intersects the instance's tiles are
-// b0..b1 (cta(T) = ((T + 1) * grid - 1) / all_tiles for tile T), their rows b + inst.
-__global__ void reduce_segment_rows_kernel(const float* __restrict__ partials, int grid, int tiles_per_inst,
-                                           long long all_tiles, float* __restrict__ gloc, float* __restrict__ grot,
+// Sum the partial rows of every instance: CTA b wrote row b + inst for every instance whose tiles intersect its range
+// [range_starts[b], range_starts[b + 1]).
+__global__ void reduce_segment_rows_kernel(const float* __restrict__ partials, const long long* __restrict__ range_starts,
+                                           int grid, int tiles_per_inst, float* __restrict__ gloc, float* __restrict__ grot,
                                            float* __restrict__ gdim, float* __restrict__ gW) {
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ int s_first, s_last;
     const int inst = blockIdx.y;
+    const long long first = (long long)inst * tiles_per_inst, last = first + tiles_per_inst;     // [first, last)
+    if (threadIdx.x == 0) { s_first = grid; s_last = -1; }
+    __syncthreads();
+    const long long all_tiles = (long long)gridDim.y * tiles_per_inst;
+    for (int b = threadIdx.x; b < grid; b += blockDim.x) {
+        const long long lo = range_starts ? range_starts[b] : all_tiles * b / grid;
+        const long long hi = range_starts ? range_starts[b + 1] : all_tiles * (b + 1) / grid;
+        if (lo < hi && lo < last && hi > first) { atomicMin(&s_first, b); atomicMax(&s_last, b); }
+    }
+    __syncthreads();
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= kNumW + kNumPose) return;
-    const long long first = (long long)inst * tiles_per_inst, last = first + tiles_per_inst - 1;
-    const int b0 = (int)(((first + 1) * grid - 1) / all_tiles);
-    const int b1 = (int)(((last + 1) * grid - 1) / all_tiles);
     float s = 0.0f;
-    for (int b = b0; b <= b1; ++b) s += partials[((size_t)b + inst) * kGradStride + f];
+    for (int b = s_first; b <= s_last; ++b) s += partials[((size_t)b + inst) * kGradStride + f];
     if (f < kNumW) gW[(size_t)inst * kNumW + f] = s;
     else if (f < kNumW + 3) gloc[3 * inst + (f - kNumW)] = s;
     else if (f < kNumW + 6) gdim[3 * inst + (f - kNumW - 3)] = s;
@@ -713,11 +785,22 @@ static int launch(const SceneDev& s, const RaysDev& r, const float* adjoint, flo
     const long long all_tiles = (long long)s.N * tiles_per_inst;
     const long long want = (all_tiles + Cfg::kWarps - 1) / Cfg::kWarps;
     const int grid = (int)(want < g_sms ? want : g_sms);
+    // the CTA ranges live in one extra row behind the g_sms + N partial rows (backward_mma_partial_rows)
+    long long* range_starts = reinterpret_cast<long long*>(partials + (size_t)(g_sms + s.N) * kGradStride);
+    static_assert(kGradStride % 2 == 0, "the extra row must be 8-byte aligned");
+    if (r.live != nullptr) {
+        int group = 1;                                      // census blocks per scan entry, <= kRangeMaxEntries entries
+        while ((long long)s.N * ((census_blocks(tiles_per_inst) + group - 1) / group) > kRangeMaxEntries) group *= 2;
+        backward_ranges_kernel<<<1, kRangeThreads, 0, st>>>(r.live, s.N, tiles_per_inst, group, grid, range_starts);
+    } else {
+        range_starts = nullptr;                             // even split, computed by the kernels themselves
+    }
+    VSRD_CHECK_LAUNCH();
     field_backward_mma_kernel<MT, PAIR><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(
-        s, r, (const float4*)adjoint, partials, tiles_per_inst);
+        s, r, (const float4*)adjoint, partials, range_starts, tiles_per_inst);
     VSRD_CHECK_LAUNCH();
     const dim3 rgrid((kGradStride + 127) / 128, (unsigned)s.N);
-    reduce_segment_rows_kernel<<<rgrid, 128, 0, st>>>(partials, grid, tiles_per_inst, all_tiles, gloc, grot, gdim, gW);
+    reduce_segment_rows_kernel<<<rgrid, 128, 0, st>>>(partials, range_starts, grid, tiles_per_inst, gloc, grot, gdim, gW);
     VSRD_CHECK_LAUNCH();
     return 0;
 }
@@ -731,7 +814,7 @@ int backward_mma_tile_rows() {
 
 int backward_mma_partial_rows(int num_instances) {
     if (bwd5::setup()) return -1;
-    return bwd5::g_sms + num_instances;
+    return bwd5::g_sms + num_instances + 1;      // + one row for the CTA ranges (launch())
 }
 
 int launch_field_backward_mma(const SceneDev& s, const RaysDev& r, const float* adjoint, float* partials,

@@ -133,6 +133,12 @@ __global__ void __launch_bounds__(kGroups * kGroupThreads, 1) field_forward_umma
     long long all_tiles = 0;
     if constexpr (kCull) {
         for (int i = 0; i < scene.N; ++i) all_tiles += live_tiles(i);
+        if (blockIdx.x == 0 && tid == 0 && rays.cull_stats != nullptr) {     // {.., .., forward pairs skipped, visited}
+            long long kept = 0;
+            for (int i = 0; i < scene.N; ++i) kept += __ldg(counts + i * VSRD_CULL_COUNT_STRIDE);
+            atomicAdd(rays.cull_stats + 2, (unsigned long long)((long long)scene.N * total - kept));
+            atomicAdd(rays.cull_stats + 3, (unsigned long long)((long long)scene.N * total));
+        }
     } else {
         all_tiles = (long long)scene.N * tiles_per_inst;
     }

@@ -428,9 +428,15 @@ __global__ void __launch_bounds__(VSRD_MAX_INTERVALS, NMAX <= 8 ? 2 : 1) composi
         const int tile = valid ? (int)(idx >> tile_shift) : -1 - lane;
         const unsigned peers = __match_any_sync(kFull, tile);
         const bool leader = valid && lane == __ffs(peers) - 1;
+        // ... and count the live samples per block of tiles (census_offset()), the weights backward_ranges_kernel balances
+        // the field kernel's CTAs with; a warp's samples are attributed to the block of its first one
+        int* census = reinterpret_cast<int*>(rays.live + census_offset(N, tiles_per_inst));
+        const int nb = census_blocks(tiles_per_inst);
+        const int blk = (int)(((size_t)r * M + 32 * warp) >> tile_shift) / VSRD_CENSUS_BLOCK_TILES;
         for (int i = 0; i < N; ++i) {
             const unsigned votes = __ballot_sync(kFull, (live_mask >> i) & 1u);
             if (leader && (votes & peers)) rays.live[(size_t)i * tiles_per_inst + tile] = 1;
+            if (lane == 0 && votes) atomicAdd(census + i * nb + blk, __popc(votes));
         }
     }
 }

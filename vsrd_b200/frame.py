@@ -185,7 +185,7 @@ class FrameLabeler:
             with torch.cuda.stream(self.stream):
                 self._draw_ahead(self.state)          # batch of step 0
                 self.state_ahead.set_step(1)
-        # phases: 0 = warm-up (box only), 1 = residual field, 2 = residual field + forward culling pre-pass (late schedule)
+        # phases: 0 = warm-up (box only), 1 = residual field, 2 = residual field with instance culling (late schedule)
         self._graphs: Dict[int, torch.cuda.CUDAGraph] = {}
         self._eager_done: Dict[int, int] = {0: 0, 1: 0, 2: 0}
 
@@ -296,15 +296,15 @@ class FrameLabeler:
         self.step_index = int(step)
 
     def phase_of(self, step: int) -> int:
-        """0 = warm-up (box only, main.py:582-618), 1 = residual field, 2 = residual field with the forward culling
-        pre-pass: worth its launch once the temperature has dropped to ops.FORWARD_CULL_MAX_TEMPERATURE."""
+        """0 = warm-up (box only, main.py:582-618), 1 = residual field, 2 = residual field with instance culling: worth
+        its launches once the temperature has dropped to ops.CULL_MAX_TEMPERATURE."""
         if step < self.warmup_steps:
             return 0
-        late = self.state.temperature_at(step) <= ops.FORWARD_CULL_MAX_TEMPERATURE
+        late = self.state.temperature_at(step) <= ops.CULL_MAX_TEMPERATURE
         return 2 if late and ops.culling_enabled() and self.inputs.num_instances > 1 else 1
 
     def _run_phase(self, phase: int) -> None:
-        self.state.forward_cull = phase == 2
+        self.state.cull = phase == 2
         self._step_body(phase >= 1)
 
     def _capture(self, phase: int) -> None:

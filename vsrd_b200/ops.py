@@ -89,12 +89,10 @@ class RayArgs:
         still carry one; vsrd_field_backward visits the marked tiles only.  No extra launch."""
         if self.num_rays == 0 or self.live_tiles is not None:
             return
-        bwd_rows = _lib.load().vsrd_backward_tile_rows()
-        if bwd_rows < 1:
+        size = _lib.load().vsrd_live_tiles_bytes(scene.num_instances, self.num_rays, self.num_intervals)
+        if size < 1:
             _lib.check(1)
-        samples = self.num_rays * self.num_intervals
-        self.live_tiles = torch.zeros(scene.num_instances, (samples + bwd_rows - 1) // bwd_rows,
-                                      device=self.directions.device, dtype=torch.uint8)
+        self.live_tiles = torch.zeros(size, device=self.directions.device, dtype=torch.uint8)
         self.struct.live_tiles = _ptr(self.live_tiles)
         self.struct.cull_stats = _ptr(_cull_stats(self.directions.device))
 
@@ -127,15 +125,19 @@ class RayArgs:
 # ---- instance culling -----------------------------------------------------------------
 _culling = os.environ.get("VSRD_CULL", "1") != "0"
 _cull_counters = {}
-# The forward pre-pass costs ~35 us per two-pass step at R = 1000 (profiles/r02_forward_culling.txt) and culls nothing
-# while 1 + 20 T exceeds the distances between the boxes of a street scene: it runs once the temperature is at most
-FORWARD_CULL_MAX_TEMPERATURE = 0.5
+# Culling costs ~25 us (backward: marks, census, tile lists) + ~35 us (forward pre-passes) per two-pass step at R = 1000
+# (profiles/r02_culling_sweep.txt) and culls nothing while 1 + 20 T exceeds the distances between the boxes of a street
+# scene (break-even at T ~ 0.5 on the synthetic KITTI-360 frames): it is active once the temperature is at most
+CULL_MAX_TEMPERATURE = 0.5
 
 
-def set_culling(enabled: bool) -> None:
-    """Instance culling in the residual field kernels (on by default; VSRD_CULL=0 turns it off at import)."""
-    global _culling
+def set_culling(enabled: bool, max_temperature: Optional[float] = None) -> None:
+    """Instance culling in the residual field kernels (on by default; VSRD_CULL=0 turns it off at import);
+    `max_temperature` replaces CULL_MAX_TEMPERATURE (tests pass inf to cull at every temperature)."""
+    global _culling, CULL_MAX_TEMPERATURE
     _culling = bool(enabled)
+    if max_temperature is not None:
+        CULL_MAX_TEMPERATURE = float(max_temperature)
 
 
 def culling_enabled() -> bool:
@@ -232,18 +234,18 @@ def place_fine(coarse_distances, coarse_weights, sorted_uniforms: Optional[torch
 
 def field_forward(scene: SceneArgs, rays: RayArgs, cull: Optional[bool] = None, backward: bool = True,
                   forward_cull: Optional[bool] = None) -> torch.Tensor:
-    """`cull`: instance culling for this pass (None = the module default, see set_culling); `backward`: the pass will
-    be differentiated (attach the backward kernels' tile marks); `forward_cull`: run the forward culling pre-pass
-    (None = by temperature: the scene's own, or the decision its StepState carries, see FORWARD_CULL_MAX_TEMPERATURE)."""
+    """`cull`: instance culling for this pass: True / False, or None = the module default (see set_culling) AND a low
+    enough temperature -- the scene's own, or the decision its StepState carries (CULL_MAX_TEMPERATURE); `backward`: the
+    pass will be differentiated (attach the backward kernels' tile marks); `forward_cull`: run the forward culling
+    pre-pass (None = whenever culling is on)."""
     field = torch.empty(scene.num_instances, rays.num_rays * rays.num_intervals, 4,
                         device=rays.directions.device, dtype=torch.float32)
-    if (_culling if cull is None else cull) and scene.mlp_weights is not None and scene.num_instances > 1:
+    if cull is None:
+        cull = _culling and (scene.temperature <= CULL_MAX_TEMPERATURE if scene.step_state is None else scene.step_state.cull)
+    if cull and scene.mlp_weights is not None and scene.num_instances > 1:
         if backward:
             rays.enable_backward_culling(scene)
-        if forward_cull is None:
-            forward_cull = (scene.temperature <= FORWARD_CULL_MAX_TEMPERATURE if scene.step_state is None
-                            else scene.step_state.forward_cull)
-        if forward_cull:
+        if forward_cull is None or forward_cull:
             rays.cull_forward(scene, field)
     _lib.check(_lib.load().vsrd_field_forward(ctypes.byref(scene.struct), ctypes.byref(rays.struct), _ptr(field), _stream()))
     return field
@@ -330,7 +332,7 @@ class StepState:
                                      float(std_deviation[0]), float(std_deviation[1]), float(eikonal_weight), 0.0,
                                      int(seed) & (2 ** 64 - 1))
         self.buffer = torch.zeros(ctypes.sizeof(VsrdStepState), dtype=torch.uint8, device=device)
-        self.forward_cull = False     # host-side: whether field_forward runs the culling pre-pass (the owner decides per phase)
+        self.cull = False             # host-side: whether the field kernels cull (the owner decides per phase, CULL_MAX_TEMPERATURE)
         self.set_step(0)
 
     def temperature_at(self, step: int) -> float:
