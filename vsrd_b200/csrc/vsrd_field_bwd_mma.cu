@@ -58,13 +58,10 @@ using frag::fma2;
 using frag::hsum;
 
 // LayerNorm (no affine, eps 1e-5) of one row and of its tangent, on channel pairs.  In: p = h, d = hd
-// (this lane's 2 x 2 of the 16 channels).  Out: p = z, d = zd, rs = 1/sigma, mz = mean(z * centred tangent).
+// (this lane's 2 x 2 of the 16 channels), both CENTRED already: the weights that produced them were centred when they
+// were staged (frag::stage_weight_fragments).  Out: p = z, d = zd, rs = 1/sigma, mz = mean(z * centred tangent).
 __device__ __forceinline__ void ln_dual2(f2& p0, f2& p1, f2& d0, f2& d1, float& rs, float& mz) {
     constexpr float inv = 1.0f / kHid;
-    const f2 m = frag::quad_sum2(make_float2(hsum(add2(p0, p1)), hsum(add2(d0, d1))));
-    const float nmean = m.x * -inv, nmt = m.y * -inv;
-    p0 = add2(p0, bc(nmean)); p1 = add2(p1, bc(nmean));
-    d0 = add2(d0, bc(nmt)); d1 = add2(d1, bc(nmt));
     // (16 var, sum v d) in one packed reduction; z = v rs, so mean(z d) = rs * sum(v d) / 16
     const f2 q = frag::quad_sum2(make_float2(hsum(fma2(p0, p0, mul2(p1, p1))), hsum(fma2(p0, d0, mul2(p1, d1)))));
     rs = rsqrtf(fmaf(q.x, inv, kLnEps));
@@ -84,8 +81,10 @@ __device__ __forceinline__ void gelu_pair(f2 z, f2 zd, f2& g, f2& gd, f2& g1, f2
     gd = mul2(g1, zd);
 }
 
-// Adjoint of (LayerNorm -> GELU) and of its tangent for one row (vsrd_math.cuh::ln_gelu_reverse).
-// gb / gdb: adjoints of gelu(z) and of its tangent; out hb / hdb: adjoints of the LayerNorm input and
+// Adjoint of (LayerNorm -> GELU) and of its tangent for one row (vsrd_math.cuh::ln_gelu_reverse) w.r.t. the CENTRED
+// LayerNorm input: the terms - mean(zb), - mean(zdb) of the full adjoint are applied by the centred transposed weights
+// the result is multiplied with next (P W)^T hb = W^T (P hb), and cancel in the gradient of the centred weights.
+// gb / gdb: adjoints of gelu(z) and of its tangent; out hb / hdb: adjoints of the (centred) LayerNorm input and
 // of its tangent.  [0] / [1]: the lane's two channel pairs.
 __device__ __forceinline__ void ln_gelu_reverse_row2(const f2 (&z)[2], const f2 (&zd)[2], const f2 (&g1)[2],
                                                      const f2 (&g2)[2], float rs, float m, const f2 (&gb)[2],
@@ -97,14 +96,15 @@ __device__ __forceinline__ void ln_gelu_reverse_row2(const f2 (&z)[2], const f2 
         zdb[k] = mul2(gdb[k], g1[k]);
         zb[k] = fma2(gb[k], g1[k], mul2(mul2(gdb[k], g2[k]), zd[k]));
     }
-    const f2 sa = frag::quad_sum2(make_float2(hsum(add2(zb[0], zb[1])), hsum(fma2(z[0], zb[0], mul2(z[1], zb[1])))));
-    const f2 sb = frag::quad_sum2(make_float2(hsum(add2(zdb[0], zdb[1])), hsum(fma2(z[0], zdb[0], mul2(z[1], zdb[1])))));
-    const float sc = frag::quad_sum(hsum(fma2(zd[0], zdb[0], mul2(zd[1], zdb[1]))));
-    const float n_zb = sa.x * -inv, n_zz = (sa.y + sc) * -inv, n_zdb = sb.x * -inv, n_zzdb = sb.y * -inv;
+    // sum(z zb) + sum(zd zdb) and sum(z zdb) in one packed quad reduction
+    const f2 s = frag::quad_sum2(make_float2(
+        hsum(fma2(z[0], zb[0], fma2(z[1], zb[1], fma2(zd[0], zdb[0], mul2(zd[1], zdb[1]))))),
+        hsum(fma2(z[0], zdb[0], mul2(z[1], zdb[1])))));
+    const float n_zz = s.x * -inv, n_zzdb = s.y * -inv;
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
-        hdb[k] = mul2(bc(rs), fma2(z[k], bc(n_zzdb), add2(zdb[k], bc(n_zdb))));
-        hb[k] = mul2(bc(rs), fma2(zd[k], bc(n_zzdb), fma2(hdb[k], bc(-m), fma2(z[k], bc(n_zz), add2(zb[k], bc(n_zb))))));
+        hdb[k] = mul2(bc(rs), fma2(z[k], bc(n_zzdb), zdb[k]));
+        hb[k] = mul2(bc(rs), fma2(zd[k], bc(n_zzdb), fma2(hdb[k], bc(-m), fma2(z[k], bc(n_zz), zb[k]))));
     }
 }
 
@@ -234,13 +234,14 @@ __global__ void __launch_bounds__(BwdCfg<MT>::kThreads, 1) field_backward_mma_ke
     unsigned tiles_visited = 0, tiles_culled = 0;          // per warp; two atomics per warp at the end
     constexpr int kChunkTiles = 2048;
     __shared__ unsigned short s_list[kChunkTiles];
+    __shared__ float s_mean[frag::kNumMeans];
     __shared__ int s_live;
 
     for (long long seg = begin; seg < end;) {
         const int inst = (int)(seg / tiles_per_inst);
         const long long seg_end = min(end, (long long)(inst + 1) * tiles_per_inst);
         __syncthreads();                                    // previous segment fully flushed
-        frag::stage_weight_fragments(scene.W + (size_t)inst * kNumW, sF, sTail);
+        frag::stage_weight_fragments(scene.W + (size_t)inst * kNumW, sF, sTail, s_mean);
 #pragma unroll
         for (int f = 0; f < kAccFrags; ++f) accL[f * 32] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         __syncthreads();
@@ -732,12 +733,16 @@ __global__ void __launch_bounds__(BwdCfg<MT>::kThreads, 1) field_backward_mma_ke
 }
 
 // Sum the partial rows of every instance: CTA b wrote row b + inst for every instance whose tiles intersect its range
-// [range_starts[b], range_starts[b + 1]).
-__global__ void reduce_segment_rows_kernel(const float* __restrict__ partials, const long long* __restrict__ range_starts,
-                                           int grid, int tiles_per_inst, float* __restrict__ gloc, float* __restrict__ grot,
-                                           float* __restrict__ gdim, float* __restrict__ gW) {
+// [range_starts[b], range_starts[b + 1]).  The kernel accumulated the gradient w.r.t. the CENTRED weights P W_l, P b_l of
+// layers 0..3 (frag::stage_weight_fragments); dW = P dW' subtracts, per input column, the mean over the 16 outputs.
+// grid (5, N): blockIdx.x = layer 0 | hidden layer 1..3 | last layer + pose.
+constexpr int kReduceThreads = 256;
+__global__ void __launch_bounds__(kReduceThreads) reduce_segment_rows_kernel(
+        const float* __restrict__ partials, const long long* __restrict__ range_starts, int grid, int tiles_per_inst,
+        float* __restrict__ gloc, float* __restrict__ grot, float* __restrict__ gdim, float* __restrict__ gW) {
     __shared__ int s_first, s_last;
-    const int inst = blockIdx.y;
+    __shared__ float s_sum[kW1];                            // the largest section: layer 0, 16 x 49
+    const int inst = blockIdx.y, section = blockIdx.x;
     const long long first = (long long)inst * tiles_per_inst, last = first + tiles_per_inst;     // [first, last)
     if (threadIdx.x == 0) { s_first = grid; s_last = -1; }
     __syncthreads();
@@ -748,14 +753,30 @@ __global__ void reduce_segment_rows_kernel(const float* __restrict__ partials, c
         if (lo < hi && lo < last && hi > first) { atomicMin(&s_first, b); atomicMax(&s_last, b); }
     }
     __syncthreads();
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= kNumW + kNumPose) return;
-    float s = 0.0f;
-    for (int b = s_first; b <= s_last; ++b) s += partials[((size_t)b + inst) * kGradStride + f];
-    if (f < kNumW) gW[(size_t)inst * kNumW + f] = s;
-    else if (f < kNumW + 3) gloc[3 * inst + (f - kNumW)] = s;
-    else if (f < kNumW + 6) gdim[3 * inst + (f - kNumW - 3)] = s;
-    else grot[9 * inst + (f - kNumW - 6)] = s;
+    const int base = section == 0 ? 0 : (section <= 3 ? kW1 + (section - 1) * kWStride : kW4);
+    const int count = section == 0 ? kW1 : (section <= 3 ? kWStride : kGradStride - kW4);
+    const int fan = section == 0 ? kEnc + 1 : kHid + 1;     // row length [inputs + bias] of the section's layer
+    for (int k = threadIdx.x; k < count; k += blockDim.x) {
+        float s = 0.0f;
+        for (int b = s_first; b <= s_last; ++b) s += partials[((size_t)b + inst) * kGradStride + base + k];
+        s_sum[k] = s;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < count; k += blockDim.x) {
+        float s = s_sum[k];
+        const int f = base + k;
+        if (section <= 3) {                                 // P along the output index: same input column, all 16 outputs
+            const int col = k % fan;
+            float mean = 0.0f;
+#pragma unroll
+            for (int o = 0; o < kHid; ++o) mean += s_sum[o * fan + col];
+            s -= mean * (1.0f / kHid);
+        }
+        if (f < kNumW) gW[(size_t)inst * kNumW + f] = s;
+        else if (f < kNumW + 3) gloc[3 * inst + (f - kNumW)] = s;
+        else if (f < kNumW + 6) gdim[3 * inst + (f - kNumW - 3)] = s;
+        else grot[9 * inst + (f - kNumW - 6)] = s;
+    }
 }
 
 static int g_sms = 0;
@@ -799,8 +820,8 @@ static int launch(const SceneDev& s, const RaysDev& r, const float* adjoint, flo
     field_backward_mma_kernel<MT, PAIR><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(
         s, r, (const float4*)adjoint, partials, range_starts, tiles_per_inst);
     VSRD_CHECK_LAUNCH();
-    const dim3 rgrid((kGradStride + 127) / 128, (unsigned)s.N);
-    reduce_segment_rows_kernel<<<rgrid, 128, 0, st>>>(partials, range_starts, grid, tiles_per_inst, gloc, grot, gdim, gW);
+    const dim3 rgrid(5, (unsigned)s.N);
+    reduce_segment_rows_kernel<<<rgrid, kReduceThreads, 0, st>>>(partials, range_starts, grid, tiles_per_inst, gloc, grot, gdim, gW);
     VSRD_CHECK_LAUNCH();
     return 0;
 }

@@ -47,10 +47,30 @@ constexpr int kStashFloats = 3 * 32;                      // per thread: layers 
 constexpr size_t smem_bytes(int groups) { return 1024 + (size_t)kWeightFloats * 4 + (size_t)groups * kGroupThreads * kStashFloats * 4; }
 
 // Global (reference layout: per layer [out][in + 1], bias last) -> the B operand blocks above.
-__device__ void stage_weights_umma(const float* __restrict__ W, float* sW) {
+//
+// LayerNorm centring folded into the weights: every layer's output feeds a LayerNorm (no affine), whose first step
+// subtracts the mean over the 16 channels.  h - mean(h) = (P W) a + P b with P = I - 11^T / 16, so the operands staged
+// here are the CENTRED weights P W_l, P b_l (l = 0..3; column means over the output index), the contractions deliver
+// centred pre-activations, and norm_gelu() / norm_gelu_adjoint() skip the mean and its adjoint (the adjoint w.r.t. the
+// centred h times (P W)^T equals the full adjoint times W^T).  Saves 17 + 18 of ~260 instructions per (sample, layer).
+constexpr int kNumMeans = (kEnc + 1) + 3 * (kHid + 1);       // column means: layer 0 (48 inputs + bias), layers 1..3 (16 + bias)
+__device__ void stage_weights_umma(const float* __restrict__ W, float* sW, float* s_mean) {
+    for (int i = threadIdx.x; i < kNumMeans; i += blockDim.x) {
+        const bool first = i <= kEnc;
+        const int l = first ? 0 : (i - (kEnc + 1)) / (kHid + 1), j = first ? i : (i - (kEnc + 1)) % (kHid + 1);
+        const float* col = first ? W + kW0 + j : W + kW1 + l * kWStride + j;
+        const int stride = first ? kEnc + 1 : kHid + 1;
+        float sum = 0.0f;
+#pragma unroll
+        for (int o = 0; o < kHid; ++o) sum += __ldg(col + o * stride);
+        s_mean[i] = sum * (1.0f / kHid);
+    }
+    __syncthreads();
+    const float* mean0 = s_mean;                                                          // [kEnc + 1]
+    const float* meanl = s_mean + (kEnc + 1);                                             // [3][kHid + 1]
     for (int i = threadIdx.x; i < kHid * kEnc; i += blockDim.x) {                         // layer 0
         const int o = i / kEnc, j = i % kEnc, c = j / 16, jj = j % 16, k = jj >> 1;
-        const float w = __ldg(W + kW0 + o * (kEnc + 1) + j);
+        const float w = __ldg(W + kW0 + o * (kEnc + 1) + j) - mean0[j];
         put_split(sW + kOffW0 + c * 2 * kBlk, o, jj, w);
         // e = (cos(2^k a), sin(2^k a)):  d/da of  w_cos cos + w_sin sin  =  2^k (w_sin cos - w_cos sin)
         const float f = (float)(1 << k);
@@ -59,11 +79,12 @@ __device__ void stage_weights_umma(const float* __restrict__ W, float* sW) {
     }
     for (int i = threadIdx.x; i < 4 * kHid; i += blockDim.x) {                            // biases of layers 0..3
         const int l = i / kHid, o = i % kHid;
-        sW[kOffBias + i] = l == 0 ? __ldg(W + kW0 + o * (kEnc + 1) + kEnc) : __ldg(W + kW1 + (l - 1) * kWStride + o * (kHid + 1) + kHid);
+        sW[kOffBias + i] = l == 0 ? __ldg(W + kW0 + o * (kEnc + 1) + kEnc) - mean0[kEnc]
+                                  : __ldg(W + kW1 + (l - 1) * kWStride + o * (kHid + 1) + kHid) - meanl[(l - 1) * (kHid + 1) + kHid];
     }
     for (int i = threadIdx.x; i < 3 * kHid * kHid; i += blockDim.x) {                     // hidden layers and transposes
         const int l = i / (kHid * kHid), o = (i / kHid) % kHid, in = i % kHid;
-        const float w = __ldg(W + kW1 + l * kWStride + o * (kHid + 1) + in);
+        const float w = __ldg(W + kW1 + l * kWStride + o * (kHid + 1) + in) - meanl[l * (kHid + 1) + in];
         put_split(sW + kOffWl + l * 2 * kBlk, o, in, w);
         put_split(sW + kOffWt + l * 2 * kBlk, in, o, w);
     }
@@ -97,6 +118,7 @@ __global__ void __launch_bounds__(kGroups * kGroupThreads, 1) field_forward_umma
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ uint64_t s_mbar[kMaxGroups];
     __shared__ uint32_t s_tmem_base;
+    __shared__ float s_mean[kNumMeans];
     float* sW = reinterpret_cast<float*>(smem_raw);
     float* sStash = sW + kWeightFloats;
 
@@ -161,7 +183,7 @@ __global__ void __launch_bounds__(kGroups * kGroupThreads, 1) field_forward_umma
         const long long seg_end = min(end, inst_first + inst_tiles);
         fence_before_sync();
         __syncthreads();                                   // every group is done with the previous instance's weights
-        stage_weights_umma(scene.W + (size_t)inst * kNumW, sW);
+        stage_weights_umma(scene.W + (size_t)inst * kNumW, sW, s_mean);
         fence_proxy_async_smem();
         __syncthreads();
         fence_after_sync();

@@ -247,7 +247,30 @@ __device__ __forceinline__ void wgrad_bias(f2 (&D)[2], const uint32_t (&ah)[4], 
 }
 
 // Reference weight layout (hyper_distance_field.py:57-73): layer l rows [out][fan_in + 1], bias last.
-__device__ __forceinline__ void stage_weight_fragments(const float* __restrict__ W, float4* sF, float* sTail) {
+//
+// LayerNorm centring folded into the weights (as in vsrd_field_umma.cu::stage_weights_umma): the fragments hold the CENTRED
+// weights P W_l and biases P b_l of layers 0..3 (P = I - 11^T / 16 over the output index), so every contraction delivers
+// centred pre-activations (and tangents), the transposed contractions apply P to the adjoints for free, and the
+// LayerNorm code skips its mean reductions.  The weight gradient the kernel accumulates is then the one w.r.t. P W; the
+// row reduction maps it back (dW = P dW', reduce_segment_rows_kernel).
+constexpr int kNumMeans = (kEnc + 1) + 3 * (kHid + 1);
+__device__ __forceinline__ float centred_weight(const float* __restrict__ W, int i, const float* s_mean) {
+    if (i < kW1) return __ldg(W + i) - s_mean[i % (kEnc + 1)];
+    const int q = i - kW1, l = q / kWStride, j = (q - l * kWStride) % (kHid + 1);
+    return __ldg(W + i) - s_mean[(kEnc + 1) + l * (kHid + 1) + j];
+}
+__device__ __forceinline__ void stage_weight_fragments(const float* __restrict__ W, float4* sF, float* sTail, float* s_mean) {
+    for (int i = threadIdx.x; i < kNumMeans; i += blockDim.x) {                     // column means over the 16 outputs
+        const bool first = i <= kEnc;
+        const int l = first ? 0 : (i - (kEnc + 1)) / (kHid + 1), j = first ? i : (i - (kEnc + 1)) % (kHid + 1);
+        const float* col = first ? W + j : W + kW1 + l * kWStride + j;
+        const int stride = first ? kEnc + 1 : kHid + 1;
+        float sum = 0.0f;
+#pragma unroll
+        for (int o = 0; o < kHid; ++o) sum += __ldg(col + o * stride);
+        s_mean[i] = sum * (1.0f / kHid);
+    }
+    __syncthreads();
     for (int f = threadIdx.x; f < kFragFloat4; f += blockDim.x) {
         const int lane = f & 31, frag = f >> 5;
         const int g = lane >> 2, t = lane & 3;
@@ -270,14 +293,14 @@ __device__ __forceinline__ void stage_weight_fragments(const float* __restrict__
             i1 = i0 + (kEnc + 1);
         }
         uint32_t h0, l0, h1, l1;
-        split(__ldg(W + i0), h0, l0);
-        split(__ldg(W + i1), h1, l1);
+        split(centred_weight(W, i0, s_mean), h0, l0);
+        split(centred_weight(W, i1, s_mean), h1, l1);
         sF[f] = make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(l0), __uint_as_float(l1));
     }
     for (int f = threadIdx.x; f < kTailFloats; f += blockDim.x) {
         float v = 0.0f;
-        if (f < 16) v = __ldg(W + f * (kEnc + 1) + kEnc);
-        else if (f < 64) v = __ldg(W + kW1 + ((f >> 4) - 1) * kWStride + (f & 15) * (kHid + 1) + kHid);
+        if (f < 16) v = centred_weight(W, f * (kEnc + 1) + kEnc, s_mean);
+        else if (f < 64) v = centred_weight(W, kW1 + ((f >> 4) - 1) * kWStride + (f & 15) * (kHid + 1) + kHid, s_mean);
         else if (f <= kTailB4) v = __ldg(W + kW4 + (f - 64));
         sTail[f] = v;
     }

@@ -92,20 +92,18 @@ __device__ __forceinline__ void gelu_terms2(f2 z, f2& Phi, f2& phi) {
     phi = mul2(E, bc(kInvSqrt2Pi));
 }
 
-// h -> z = LayerNorm(h) (no affine, eps 1e-5), a = gelu(z), g = gelu'(z) / sigma; channel pairs (2i, 2i + 1)
+// h -> z = LayerNorm(h) (no affine, eps 1e-5), a = gelu(z), g = gelu'(z) / sigma; channel pairs (2i, 2i + 1).
+// h arrives CENTRED (mean over the 16 channels == 0 up to rounding): the producing layer's weights and bias were
+// centred when they were staged (vsrd_field_umma.cu::stage_weights_umma).
 __device__ __forceinline__ void norm_gelu(const f2 (&h)[8], f2 (&z)[8], f2 (&a)[8], f2 (&g)[8]) {
-    f2 acc = h[0];
-#pragma unroll
-    for (int i = 1; i < 8; ++i) acc = add2(acc, h[i]);
-    const f2 mean = bc((acc.x + acc.y) * (-1.0f / 16.0f));
     f2 var = bc(0.0f);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { z[i] = add2(h[i], mean); var = fma2(z[i], z[i], var); }
+    for (int i = 0; i < 8; ++i) var = fma2(h[i], h[i], var);
     const float rs1 = rsqrtf((var.x + var.y) * (1.0f / 16.0f) + kLnEps);
     const f2 rs = bc(rs1);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        z[i] = mul2(z[i], rs);
+        z[i] = mul2(h[i], rs);
         f2 Phi, phi;
         gelu_terms2(z[i], Phi, phi);
         a[i] = mul2(z[i], Phi);
@@ -113,18 +111,19 @@ __device__ __forceinline__ void norm_gelu(const f2 (&h)[8], f2 (&z)[8], f2 (&a)[
     }
 }
 
-// adjoint of a = gelu(LayerNorm(h)) w.r.t. h:  zb = abar * gelu'(z) / sigma;  hbar = zb - mean(zb) - z mean(z zb)
+// adjoint of a = gelu(LayerNorm(h)) w.r.t. the CENTRED h:  zb = abar * gelu'(z) / sigma;  hbar = zb - z mean(z zb).
+// (The full adjoint also subtracts mean(zb); that projection lives in the centred transposed weights the result is
+// multiplied with next -- or, at layer 0, in the centred derivative weights behind g_c.)
 __device__ __forceinline__ void norm_gelu_adjoint(const f2 (&abar)[8], const f2 (&z)[8], const f2 (&g)[8], f2 (&hbar)[8]) {
-    f2 m1 = bc(0.0f), m2 = bc(0.0f);
+    f2 m2 = bc(0.0f);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         hbar[i] = mul2(abar[i], g[i]);
-        m1 = add2(m1, hbar[i]);
         m2 = fma2(z[i], hbar[i], m2);
     }
-    const f2 s1 = bc((m1.x + m1.y) * (-1.0f / 16.0f)), s2 = bc((m2.x + m2.y) * (-1.0f / 16.0f));
+    const f2 s2 = bc((m2.x + m2.y) * (-1.0f / 16.0f));
 #pragma unroll
-    for (int i = 0; i < 8; ++i) hbar[i] = fma2(z[i], s2, add2(hbar[i], s1));
+    for (int i = 0; i < 8; ++i) hbar[i] = fma2(z[i], s2, hbar[i]);
 }
 
 // v (8 channel pairs) -> hi / lo columns of the group's A operand
