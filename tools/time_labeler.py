@@ -32,8 +32,9 @@ frame, lab = make(0)
 torch.cuda.synchronize(); t2 = time.perf_counter()
 marks = {}
 w = a.warmup_steps
+p2 = next((k for k in range(w, a.steps) if lab.phase_of(k) == 2), a.steps)       # first step with instance culling
 for k in range(a.steps):
-    if k in (10, w, w + 10):
+    if k in (10, w, w + 10, p2, p2 + 10):
         torch.cuda.synchronize(); marks[k] = time.perf_counter()
     lab.step()
 torch.cuda.synchronize(); t3 = time.perf_counter()
@@ -45,6 +46,9 @@ culled, visited = _ops.culling_counters(dev, reset=True)
 res = dict(culled_tile_fraction_first_frame=(culled / visited) if visited else 0.0, first_frame_setup_s=t2 - t0, first_frame_steps_s=t3 - t2,
            warmup_ms_per_step=(marks[w] - marks[10]) / (w - 10) * 1e3,
            main_ms_per_step=(t3 - marks[w + 10]) / (a.steps - w - 10) * 1e3,
+           residual_no_culling_ms_per_step=(marks[p2] - marks[w + 10]) / max(p2 - w - 10, 1) * 1e3 if p2 in marks else None,
+           residual_culling_ms_per_step=(t3 - marks[p2 + 10]) / max(a.steps - p2 - 10, 1) * 1e3 if p2 + 10 in marks else None,
+           first_culling_step=p2,
            centre_error_m=err, losses=lab.losses.tolist(), draw_failures=int(lab.draw_failures))
 if a.frames > 1:
     del lab

@@ -41,7 +41,7 @@ struct BwdCfg {
     static constexpr int kWarps = MT == 2 ? 8 : 12;
     static constexpr int kThreads = kWarps * 32;
     static constexpr int kRows = 16 * MT;
-    static constexpr bool kPoseInRegs = MT == 1;
+    static constexpr bool kPoseInRegs = false;             // bf16 weight fragments (12 KB instead of 24 KB) leave room for the pose accumulators in shared memory
     static constexpr int kAccFrags = kPoseInRegs ? 17 : 21;
     static constexpr int kAccFloat4 = kAccFrags * 32;
     static constexpr int kLayerPairs = 4 * MT;                      // pair rows (float2 x 32 lanes) of z per layer; as many of zd
@@ -352,29 +352,26 @@ __global__ void __launch_bounds__(BwdCfg<MT>::kThreads, 1) field_backward_mma_ke
                 for (int mt = 0; mt < MT; ++mt) { h[mt][nt][0] = bias; h[mt][nt][1] = bias; }
             }
 #pragma unroll
-            for (int c = 0; c < 3; ++c)
+            for (int c = 0; c < 3; ++c) {       // one k-step per coordinate: frequencies t (a0, a1) and t + 4 (a2, a3), (cos, sin) pairs
+                const float4 w0 = fragL[(frag::kB0 + 2 * c) * 32], w1 = fragL[(frag::kB0 + 2 * c + 1) * 32];
 #pragma unroll
-                for (int f = 0; f < 2; ++f) {
-                    const int ks = 2 * c + f;
-                    const float fk = f ? f1 : f0;
-                    const float4 w0 = fragL[(frag::kF0 + 2 * ks) * 32], w1 = fragL[(frag::kF0 + 2 * ks + 1) * 32];
+                for (int mt = 0; mt < MT; ++mt) {
+                    uint32_t ah[4], al[4], adh[4], adl[4];
 #pragma unroll
-                    for (int mt = 0; mt < MT; ++mt) {
-                        const f2 cs = e.cs[mt][c][f], sn = e.sn[mt][c][f];
-                        uint32_t ah[4], al[4], adh[4], adl[4];
-                        frag::a_from_row_pairs(cs, sn, ah, al);
-                        const f2 da = mul2(adrow[mt][c], bc(fk));
-                        frag::a_from_row_pairs(mul2(mul2(da, bc(-1.0f)), sn), mul2(da, cs), adh, adl);
-                        if (ks == 0) {       // the value accumulators start from the bias, the tangent ones from zero
-                            frag::mma3(h[mt][0], ah, al, w0);
-                            frag::mma3_zero(hd[mt][0], adh, adl, w0);
-                            frag::mma3(h[mt][1], ah, al, w1);
-                            frag::mma3_zero(hd[mt][1], adh, adl, w1);
-                        } else {
-                            frag::mma3_quad<false>(h[mt][0], h[mt][1], hd[mt][0], hd[mt][1], ah, al, adh, adl, w0, w1);
-                        }
+                    for (int f = 0; f < 2; ++f) {
+                        const f2 cs = e.cs[mt][c][f], sn = e.sn[mt][c][f];             // pairs over rows (g, g + 8)
+                        const f2 da = mul2(adrow[mt][c], bc(f ? f1 : f0));
+                        const f2 dcs = mul2(mul2(da, bc(-1.0f)), sn), dsn = mul2(da, cs);   // tangents of (cos, sin)
+                        frag::pack_bf16_split_scalar(cs.x, sn.x, ah[2 * f], al[2 * f]);
+                        frag::pack_bf16_split_scalar(cs.y, sn.y, ah[2 * f + 1], al[2 * f + 1]);
+                        frag::pack_bf16_split_scalar(dcs.x, dsn.x, adh[2 * f], adl[2 * f]);
+                        frag::pack_bf16_split_scalar(dcs.y, dsn.y, adh[2 * f + 1], adl[2 * f + 1]);
                     }
+                    // the value accumulators start from the bias, the tangent ones from zero
+                    if (c == 0) frag::mma3b_quad<false, true>(h[mt][0], h[mt][1], hd[mt][0], hd[mt][1], ah, al, adh, adl, w0, w1);
+                    else frag::mma3b_quad<false, false>(h[mt][0], h[mt][1], hd[mt][0], hd[mt][1], ah, al, adh, adl, w0, w1);
                 }
+            }
             // layers 1..3: LayerNorm -> GELU -> linear; lane t keeps 1/sigma and mz of layer t + 1
             float rreg[kSlots], mreg[kSlots];
 #pragma unroll
@@ -406,22 +403,15 @@ __global__ void __launch_bounds__(BwdCfg<MT>::kThreads, 1) field_backward_mma_ke
                 for (int nt = 0; nt < 2; ++nt) {
                     const f2 bias = make_float2(sTail[16 * l + 8 * nt + 2 * t], sTail[16 * l + 8 * nt + 2 * t + 1]);
 #pragma unroll
-                    for (int mt = 0; mt < MT; ++mt) {
-                        hn[mt][nt][0] = bias; hn[mt][nt][1] = bias;
-                        hdn[mt][nt][0] = bc(0.0f); hdn[mt][nt][1] = bc(0.0f);
-                    }
+                    for (int mt = 0; mt < MT; ++mt) { hn[mt][nt][0] = bias; hn[mt][nt][1] = bias; }
                 }
-                const float4* fl = fragL + (frag::kF1 + 4 * (l - 1)) * 32;
+                const float4 w0 = fragL[(frag::kB1 + 2 * (l - 1)) * 32], w1 = fragL[(frag::kB1 + 2 * (l - 1) + 1) * 32];
 #pragma unroll
-                for (int ks = 0; ks < 2; ++ks) {
-                    const float4 w0 = fl[(2 * ks) * 32], w1 = fl[(2 * ks + 1) * 32];
-#pragma unroll
-                    for (int mt = 0; mt < MT; ++mt) {
-                        uint32_t ah[4], al[4], adh[4], adl[4];
-                        frag::a_from_c(h[mt][ks], ah, al);
-                        frag::a_from_c(hd[mt][ks], adh, adl);
-                        frag::mma3_quad<false>(hn[mt][0], hn[mt][1], hdn[mt][0], hdn[mt][1], ah, al, adh, adl, w0, w1);
-                    }
+                for (int mt = 0; mt < MT; ++mt) {
+                    uint32_t ah[4], al[4], adh[4], adl[4];
+                    frag::a_bf16_from_c(h[mt], ah, al);
+                    frag::a_bf16_from_c(hd[mt], adh, adl);
+                    frag::mma3b_quad<false, true>(hn[mt][0], hn[mt][1], hdn[mt][0], hdn[mt][1], ah, al, adh, adl, w0, w1);
                 }
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt)
@@ -478,18 +468,13 @@ __global__ void __launch_bounds__(BwdCfg<MT>::kThreads, 1) field_backward_mma_ke
                 // adjoints of gelu(z_l) and its tangent: W_l^T hb, W_l^T hdb
                 f2 gb[MT][2][2], gdb[MT][2][2];
                 {
-                    const float4* fl = fragL + (frag::kR1 + 4 * (l - 1)) * 32;
+                    const float4 w0 = fragL[(frag::kBR1 + 2 * (l - 1)) * 32], w1 = fragL[(frag::kBR1 + 2 * (l - 1) + 1) * 32];
 #pragma unroll
-                    for (int ks = 0; ks < 2; ++ks) {
-                        const float4 w0 = fl[(2 * ks) * 32], w1 = fl[(2 * ks + 1) * 32];
-#pragma unroll
-                        for (int mt = 0; mt < MT; ++mt) {
-                            uint32_t ah[4], al[4], adh[4], adl[4];
-                            frag::a_from_c(hb[mt][ks], ah, al);
-                            frag::a_from_c(hdb[mt][ks], adh, adl);
-                            if (ks == 0) frag::mma3_quad<true>(gb[mt][0], gb[mt][1], gdb[mt][0], gdb[mt][1], ah, al, adh, adl, w0, w1);
-                            else frag::mma3_quad<false>(gb[mt][0], gb[mt][1], gdb[mt][0], gdb[mt][1], ah, al, adh, adl, w0, w1);
-                        }
+                    for (int mt = 0; mt < MT; ++mt) {
+                        uint32_t ah[4], al[4], adh[4], adl[4];
+                        frag::a_bf16_from_c(hb[mt], ah, al);
+                        frag::a_bf16_from_c(hdb[mt], adh, adl);
+                        frag::mma3b_quad<true, true>(gb[mt][0], gb[mt][1], gdb[mt][0], gdb[mt][1], ah, al, adh, adl, w0, w1);
                     }
                 }
                 float4* accW = accL + (kAccHidden + 3 * (l - 1)) * 32;
@@ -570,20 +555,15 @@ __global__ void __launch_bounds__(BwdCfg<MT>::kThreads, 1) field_backward_mma_ke
                                 frag::wgrad_tile_scalar(D0[2 * c + f], adh, adl, dcs.x, dsn.x, dcs.y, dsn.y);
                             }
                     }
-                    uint32_t ah[2][4], al[2][4], adh[2][4], adl[2][4];
-#pragma unroll
-                    for (int ks = 0; ks < 2; ++ks) {
-                        frag::a_from_c(hb[mt][ks], ah[ks], al[ks]);
-                        frag::a_from_c(hdb[mt][ks], adh[ks], adl[ks]);
-                    }
+                    uint32_t ah[4], al[4], adh[4], adl[4];
+                    frag::a_bf16_from_c(hb[mt], ah, al);
+                    frag::a_bf16_from_c(hdb[mt], adh, adl);
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
                         float acc0 = 0.0f, acc1 = 0.0f, accd0 = 0.0f, accd1 = 0.0f;
                         f2 eb[2][2], edb[2][2];                 // [octave half f]: (cos, sin) adjoints of rows g, g + 8
-                        frag::mma3_quad<true>(eb[0], eb[1], edb[0], edb[1], ah[0], al[0], adh[0], adl[0],
-                                              fragL[(frag::kR0 + 2 * c) * 32], fragL[(frag::kR0 + 2 * c + 1) * 32]);
-                        frag::mma3_quad<false>(eb[0], eb[1], edb[0], edb[1], ah[1], al[1], adh[1], adl[1],
-                                               fragL[(frag::kR0 + 6 + 2 * c) * 32], fragL[(frag::kR0 + 6 + 2 * c + 1) * 32]);
+                        frag::mma3b_quad<true, true>(eb[0], eb[1], edb[0], edb[1], ah, al, adh, adl,
+                                                     fragL[(frag::kBR0 + 2 * c) * 32], fragL[(frag::kBR0 + 2 * c + 1) * 32]);
 #pragma unroll
                         for (int f = 0; f < 2; ++f) {
                             const float fk = f ? f1 : f0;

@@ -42,12 +42,19 @@ __device__ __forceinline__ f2 sub2(f2 a, f2 b) { return __ffma2_rn(b, bc(-1.0f),
 __device__ __forceinline__ float hsum(f2 a) { return a.x + a.y; }
 
 // ---- shared-memory image of one instance's weights -------------------------------------------
-// float4 {b0_hi, b1_hi, b0_lo, b1_lo} per (fragment, lane); fragment order:
-constexpr int kF0 = 0;              // layer 0 forward:   [ks 0..5][nt 0..1]     b0 = W0[8nt+g][8ks+2t], b1 = W0[8nt+g][8ks+2t+1]
-constexpr int kF1 = kF0 + 12;       // hidden forward:    [l-1][ks 0..1][nt 0..1] b0 = Wl[8nt+g][8ks+2t]
-constexpr int kR1 = kF1 + 12;       // hidden transposed: [l-1][ks 0..1][nt 0..1] b0 = Wl[8ks+2t][8nt+g], b1 = Wl[8ks+2t+1][8nt+g]
-constexpr int kR0 = kR1 + 12;       // layer 0 transposed:[ks 0..1][nt 0..5]     b0 = W0[8ks+2t][8nt+g]
-constexpr int kNumFrag = kR0 + 12;  // 48 fragments x 32 lanes x 16 B = 24 KB
+// Contractions run on mma.sync m16n8k16 with bf16 hi + bf16 lo operands (products hi*hi + hi*lo + lo*hi, fp32
+// accumulation: ~2^-16 per operand, two orders below the 1e-3 gradient tolerance; the forward kernel, which has to meet
+// the 1e-4 silhouette bar, keeps 3xTF32 on tcgen05).  One k-step covers a whole 16-channel layer, so a layer costs
+// 3 MMAs per 8 outputs instead of the 6 of 3xTF32 on m16n8k8 -- measured on B200: both shapes issue at the same rate
+// (profiles/r01_pipe_rates_b200.txt), and the tensor pipe's issue slots were 25 % of this kernel's stall samples.
+// The C fragment of n-tiles (0, 1) IS the A fragment of the next layer's k-step (a0 = pack(c0, c1) of n-tile 0 ...), so
+// activations chain in registers exactly as before.
+// uint4 {b0_hi, b1_hi, b0_lo, b1_lo} per (fragment, lane), b0 = B[k = 2t, 2t+1][n = g], b1 = B[k = 2t+8, 2t+9][n = g]:
+constexpr int kB0 = 0;              // layer 0 forward:    [c 0..2][nt 0..1]   B[k][n] = W0[8nt+n][16c+k]
+constexpr int kB1 = kB0 + 6;        // hidden forward:     [l-1][nt 0..1]      B[k][n] = Wl[8nt+n][k]
+constexpr int kBR1 = kB1 + 6;       // hidden transposed:  [l-1][nt 0..1]      B[k][n] = Wl[k][8nt+n]
+constexpr int kBR0 = kBR1 + 6;      // layer 0 transposed: [nt 0..5]           B[k][n] = W0[k][8nt+n]
+constexpr int kNumFrag = kBR0 + 6;  // 24 fragments x 32 lanes x 16 B = 12 KB
 constexpr int kFragFloat4 = kNumFrag * 32;
 // followed by the biases in fp32: b0[16] b1[16] b2[16] b3[16] w4[16] b4
 constexpr int kBias = 0;            // offsets into the float tail
@@ -205,6 +212,43 @@ __device__ __forceinline__ void mma_bf16(f2 (&d)[2], const uint32_t (&a)[4], uin
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+__device__ __forceinline__ void mma_bf16_zero(f2 (&d)[2], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+                 : "=f"(d[0].x), "=f"(d[0].y), "=f"(d[1].x), "=f"(d[1].y)
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(0.0f));
+}
+
+// ---- layer contractions: one k-step (16 channels) of FOUR accumulator tiles ------------------------------------------
+// x0, x1 share the A operand X (n-tiles w0, w1), y0, y1 share Y.  The three passes (lo*hi, hi*lo, hi*hi) are issued
+// pass-major, so two MMAs into the same accumulator are always three independent MMAs apart: a back-to-back chain stalls
+// on the tensor pipe's result latency.  kZeroX / kZeroY: the accumulators start from zero (the C operand is the zero
+// register, no clearing is issued) instead of their current contents (bias).
+template <bool kZeroX, bool kZeroY>
+__device__ __forceinline__ void mma3b_quad(f2 (&x0)[2], f2 (&x1)[2], f2 (&y0)[2], f2 (&y1)[2],
+                                           const uint32_t (&xh)[4], const uint32_t (&xl)[4],
+                                           const uint32_t (&yh)[4], const uint32_t (&yl)[4],
+                                           const float4& w0, const float4& w1) {
+    const uint32_t w0h0 = __float_as_uint(w0.x), w0h1 = __float_as_uint(w0.y), w0l0 = __float_as_uint(w0.z), w0l1 = __float_as_uint(w0.w);
+    const uint32_t w1h0 = __float_as_uint(w1.x), w1h1 = __float_as_uint(w1.y), w1l0 = __float_as_uint(w1.z), w1l1 = __float_as_uint(w1.w);
+    if (kZeroX) { mma_bf16_zero(x0, xl, w0h0, w0h1); mma_bf16_zero(x1, xl, w1h0, w1h1); }
+    else { mma_bf16(x0, xl, w0h0, w0h1); mma_bf16(x1, xl, w1h0, w1h1); }
+    if (kZeroY) { mma_bf16_zero(y0, yl, w0h0, w0h1); mma_bf16_zero(y1, yl, w1h0, w1h1); }
+    else { mma_bf16(y0, yl, w0h0, w0h1); mma_bf16(y1, yl, w1h0, w1h1); }
+    mma_bf16(x0, xh, w0l0, w0l1); mma_bf16(x1, xh, w1l0, w1l1);
+    mma_bf16(y0, yh, w0l0, w0l1); mma_bf16(y1, yh, w1l0, w1l1);
+    mma_bf16(x0, xh, w0h0, w0h1); mma_bf16(x1, xh, w1h0, w1h1);
+    mma_bf16(y0, yh, w0h0, w0h1); mma_bf16(y1, yh, w1h0, w1h1);
+}
+
+// A fragment (hi, lo) of the k-step from an activation held as two C tiles c[nt][q] (q: row g | row g + 8):
+// a0 = channels (2t, 2t+1) of row g, a1 = of row g + 8, a2 / a3 = channels (2t+8, 2t+9).
+__device__ __forceinline__ void a_bf16_from_c(const f2 (&c)[2][2], uint32_t (&ah)[4], uint32_t (&al)[4]) {
+    pack_bf16_split(c[0][0].x, c[0][0].y, ah[0], al[0]);
+    pack_bf16_split(c[0][1].x, c[0][1].y, ah[1], al[1]);
+    pack_bf16_split(c[1][0].x, c[1][0].y, ah[2], al[2]);
+    pack_bf16_split(c[1][1].x, c[1][1].y, ah[3], al[3]);
+}
+
 // A operand (16 outputs x 16 samples of one m-tile) of the weight-gradient product from the adjoint's
 // two C tiles c[nt][q] (nt = output half): rows = outputs, k = samples.
 __device__ __forceinline__ void wgrad_a_operand(const f2 (&c)[2][2], uint32_t (&ah)[4], uint32_t (&al)[4]) {
@@ -274,27 +318,27 @@ __device__ __forceinline__ void stage_weight_fragments(const float* __restrict__
     for (int f = threadIdx.x; f < kFragFloat4; f += blockDim.x) {
         const int lane = f & 31, frag = f >> 5;
         const int g = lane >> 2, t = lane & 3;
-        int i0, i1;
-        if (frag < kF1) {                       // layer 0 forward
-            const int ks = frag >> 1, nt = frag & 1;
-            i0 = (8 * nt + g) * (kEnc + 1) + 8 * ks + 2 * t;
-            i1 = i0 + 1;
-        } else if (frag < kR1) {                // hidden forward
-            const int q = frag - kF1, l = q >> 2, ks = (q >> 1) & 1, nt = q & 1;
-            i0 = kW1 + l * kWStride + (8 * nt + g) * (kHid + 1) + 8 * ks + 2 * t;
-            i1 = i0 + 1;
-        } else if (frag < kR0) {                // hidden transposed
-            const int q = frag - kR1, l = q >> 2, ks = (q >> 1) & 1, nt = q & 1;
-            i0 = kW1 + l * kWStride + (8 * ks + 2 * t) * (kHid + 1) + 8 * nt + g;
-            i1 = i0 + (kHid + 1);
-        } else {                                // layer 0 transposed
-            const int q = frag - kR0, ks = q / 6, nt = q % 6;
-            i0 = (8 * ks + 2 * t) * (kEnc + 1) + 8 * nt + g;
-            i1 = i0 + (kEnc + 1);
+        int idx[4];                             // the four elements k = 2t, 2t+1, 2t+8, 2t+9 of column n = g
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int k = 2 * t + (e & 1) + 8 * (e >> 1);
+            if (frag < kB1) {                   // layer 0 forward
+                const int c = frag >> 1, nt = frag & 1;
+                idx[e] = (8 * nt + g) * (kEnc + 1) + 16 * c + k;
+            } else if (frag < kBR1) {           // hidden forward
+                const int q = frag - kB1, l = q >> 1, nt = q & 1;
+                idx[e] = kW1 + l * kWStride + (8 * nt + g) * (kHid + 1) + k;
+            } else if (frag < kBR0) {           // hidden transposed
+                const int q = frag - kBR1, l = q >> 1, nt = q & 1;
+                idx[e] = kW1 + l * kWStride + k * (kHid + 1) + 8 * nt + g;
+            } else {                            // layer 0 transposed
+                const int nt = frag - kBR0;
+                idx[e] = k * (kEnc + 1) + 8 * nt + g;
+            }
         }
         uint32_t h0, l0, h1, l1;
-        split(centred_weight(W, i0, s_mean), h0, l0);
-        split(centred_weight(W, i1, s_mean), h1, l1);
+        pack_bf16_split_scalar(centred_weight(W, idx[0], s_mean), centred_weight(W, idx[1], s_mean), h0, l0);
+        pack_bf16_split_scalar(centred_weight(W, idx[2], s_mean), centred_weight(W, idx[3], s_mean), h1, l1);
         sF[f] = make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(l0), __uint_as_float(l1));
     }
     for (int f = threadIdx.x; f < kTailFloats; f += blockDim.x) {
