@@ -467,14 +467,16 @@ __global__ void __launch_bounds__(BwdCfg<MT>::kThreads, 1) field_backward_mma_ke
             for (int l = 3; l >= 1; --l) {
                 // adjoints of gelu(z_l) and its tangent: W_l^T hb, W_l^T hdb
                 f2 gb[MT][2][2], gdb[MT][2][2];
+                uint32_t th[MT][4], tl[MT][4], tdh[MT][4], tdl[MT][4];     // hb / hdb as bf16 (hi, lo) packs: A operand here, transposed below
                 {
                     const float4 w0 = fragL[(frag::kBR1 + 2 * (l - 1)) * 32], w1 = fragL[(frag::kBR1 + 2 * (l - 1) + 1) * 32];
 #pragma unroll
                     for (int mt = 0; mt < MT; ++mt) {
-                        uint32_t ah[4], al[4], adh[4], adl[4];
-                        frag::a_bf16_from_c(hb[mt], ah, al);
-                        frag::a_bf16_from_c(hdb[mt], adh, adl);
-                        frag::mma3b_quad<true, true>(gb[mt][0], gb[mt][1], gdb[mt][0], gdb[mt][1], ah, al, adh, adl, w0, w1);
+                        frag::a_bf16_from_c(hb[mt], th[mt], tl[mt]);
+                        frag::a_bf16_from_c(hdb[mt], tdh[mt], tdl[mt]);
+                        frag::mma3b_quad<true, true>(gb[mt][0], gb[mt][1], gdb[mt][0], gdb[mt][1], th[mt], tl[mt], tdh[mt], tdl[mt], w0, w1);
+                        frag::wgrad_a_from_packs(th[mt], tl[mt]);         // the weight gradient's A operand: outputs x samples
+                        frag::wgrad_a_from_packs(tdh[mt], tdl[mt]);
                     }
                 }
                 float4* accW = accL + (kAccHidden + 3 * (l - 1)) * 32;
@@ -497,16 +499,11 @@ __global__ void __launch_bounds__(BwdCfg<MT>::kThreads, 1) field_backward_mma_ke
                         gelu_pair(z[hf][1], zd[hf][1], g[hf][1], gd[hf][1], g1[hf][1], g2[hf][1]);
                     }
                     // weight gradient of linear layer l over the 16 samples of this m-tile
-                    {
-                        uint32_t ah[4], al[4];
-                        frag::wgrad_a_operand(hb[mt], ah, al);
-                        frag::wgrad_tile(D[0], ah, al, g[0][0], g[1][0]);
-                        frag::wgrad_tile(D[1], ah, al, g[0][1], g[1][1]);
-                        frag::wgrad_bias(D[2], ah, al);
-                        frag::wgrad_a_operand(hdb[mt], ah, al);
-                        frag::wgrad_tile(D[0], ah, al, gd[0][0], gd[1][0]);
-                        frag::wgrad_tile(D[1], ah, al, gd[0][1], gd[1][1]);
-                    }
+                    frag::wgrad_tile(D[0], th[mt], tl[mt], g[0][0], g[1][0]);
+                    frag::wgrad_tile(D[1], th[mt], tl[mt], g[0][1], g[1][1]);
+                    frag::wgrad_bias(D[2], th[mt], tl[mt]);
+                    frag::wgrad_tile(D[0], tdh[mt], tdl[mt], gd[0][0], gd[1][0]);
+                    frag::wgrad_tile(D[1], tdh[mt], tdl[mt], gd[0][1], gd[1][1]);
                     // LayerNorm / GELU adjoint: hb, hdb <- adjoints of the output of linear layer l - 1
 #pragma unroll
                     for (int hf = 0; hf < 2; ++hf) {
@@ -538,23 +535,6 @@ __global__ void __launch_bounds__(BwdCfg<MT>::kThreads, 1) field_backward_mma_ke
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt) {
                     const int s0 = 2 * mt, s1 = 2 * mt + 1;
-                    {
-                        uint32_t ah[4], al[4], adh[4], adl[4];
-                        frag::wgrad_a_operand(hb[mt], ah, al);
-                        frag::wgrad_a_operand(hdb[mt], adh, adl);
-                        frag::wgrad_bias(D0[6], ah, al);
-#pragma unroll
-                        for (int c = 0; c < 3; ++c)
-#pragma unroll
-                            for (int f = 0; f < 2; ++f) {
-                                const float fk = f ? f1 : f0;
-                                const f2 cs = e.cs[mt][c][f], sn = e.sn[mt][c][f];
-                                const f2 da = mul2(adrow[mt][c], bc(fk));
-                                const f2 dcs = mul2(mul2(da, bc(-1.0f)), sn), dsn = mul2(da, cs);   // tangents of (cos, sin)
-                                frag::wgrad_tile_scalar(D0[2 * c + f], ah, al, cs.x, sn.x, cs.y, sn.y);
-                                frag::wgrad_tile_scalar(D0[2 * c + f], adh, adl, dcs.x, dsn.x, dcs.y, dsn.y);
-                            }
-                    }
                     uint32_t ah[4], al[4], adh[4], adl[4];
                     frag::a_bf16_from_c(hb[mt], ah, al);
                     frag::a_bf16_from_c(hdb[mt], adh, adl);
@@ -579,6 +559,21 @@ __global__ void __launch_bounds__(BwdCfg<MT>::kThreads, 1) field_backward_mma_ke
                         abar[s0][c] = qa.x; abar[s1][c] = qa.y;
                         adbar[s0][c] = qd.x; adbar[s1][c] = qd.y;
                     }
+                    // weight gradient against the encoding and its tangent: the same packs, transposed
+                    frag::wgrad_a_from_packs(ah, al);
+                    frag::wgrad_a_from_packs(adh, adl);
+                    frag::wgrad_bias(D0[6], ah, al);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+#pragma unroll
+                        for (int f = 0; f < 2; ++f) {
+                            const float fk = f ? f1 : f0;
+                            const f2 cs = e.cs[mt][c][f], sn = e.sn[mt][c][f];
+                            const f2 da = mul2(adrow[mt][c], bc(fk));
+                            const f2 dcs = mul2(mul2(da, bc(-1.0f)), sn), dsn = mul2(da, cs);   // tangents of (cos, sin)
+                            frag::wgrad_tile_scalar(D0[2 * c + f], ah, al, cs.x, sn.x, cs.y, sn.y);
+                            frag::wgrad_tile_scalar(D0[2 * c + f], adh, adl, dcs.x, dsn.x, dcs.y, dsn.y);
+                        }
                 }
 #pragma unroll
                 for (int n = 0; n < 7; ++n)

@@ -258,6 +258,17 @@ __device__ __forceinline__ void wgrad_a_operand(const f2 (&c)[2][2], uint32_t (&
     pack_transposed(c[1][1], ah[3], al[3]);   // outputs 8-15, samples 8-15
 }
 
+// The same operand from the packs a_bf16_from_c() made of the adjoint for its transposed contraction (the packing, 5
+// instructions per register, is shared): in place, (p0, p1, p2, p3) = (nt0 g | nt0 g+8 | nt1 g | nt1 g+8) ->
+// (T p0, T p2, T p1, T p3).
+__device__ __forceinline__ void wgrad_a_from_packs(uint32_t (&h)[4], uint32_t (&l)[4]) {
+    const uint32_t h1 = h[1], l1 = l[1];
+    h[0] = movmatrix_trans(h[0]); l[0] = movmatrix_trans(l[0]);
+    h[1] = movmatrix_trans(h[2]); l[1] = movmatrix_trans(l[2]);
+    h[2] = movmatrix_trans(h1);   l[2] = movmatrix_trans(l1);
+    h[3] = movmatrix_trans(h[3]); l[3] = movmatrix_trans(l[3]);
+}
+
 // D (16 outputs x 8 inputs) += A (adjoint) x B, B = one C tile (16 samples x 8 input channels).
 // lo = channels (2t, 2t+1) of the samples in rows g, hi = the same channels in rows g + 8.
 __device__ __forceinline__ void wgrad_tile(f2 (&D)[2], const uint32_t (&ah)[4], const uint32_t (&al)[4], f2 lo_rows, f2 hi_rows) {
