@@ -768,10 +768,11 @@ def run_native(args):
                          "traffic": capture.get("traffic_bytes") if same_shape else None,
                          "traffic_unit": f"dram bytes read + written per launch (ncu --set full, {capture.get('source', 'no capture')})",
                          "peak_source": f"{sms} SMs x 128 lanes x 2 x sm_max_mhz {sm_max:.0f} (MEASURED_PEAKS.json clock)",
-                         "bound_note": "issue-bound FP32 work between 3xTF32 mma.sync contractions: DRAM traffic is one pass over "
-                                       "the adjoint buffer (26 MB per launch, 0.5 % of the HBM roofline) and the tensor pipe is "
-                                       "~30 % busy, so the kernel is rated against the FP32 FMA peak (DESIGN.md section 3)",
-                         "forward_fine": {"kernel": "cull_samples_kernel + field_forward_umma_kernel<4, cull> (tcgen05 / TMEM, vsrd_field_umma.cu)",
+                         "bound_note": "issue- / latency-bound FP32 work between mma.sync m16n8k16 (bf16 hi + lo) contractions: DRAM "
+                                       "traffic is one pass over the adjoint buffer (26 MB per launch, 0.6 % of the HBM roofline) and the "
+                                       "tensor pipe is ~28 % busy, so the kernel is rated against the FP32 FMA peak (DESIGN.md section 3)",
+                         "forward_fine": {"kernel": ("cull_samples_kernel + field_forward_umma_kernel<4, true>" if fwd_pairs.get("fine")
+                                                     else "field_forward_umma_kernel<4, false>") + " (tcgen05 / TMEM, vsrd_field_umma.cu)",
                                           "kernel_ms": per_kernel.get("field_forward_fine"),
                                           "executed_fraction": fwd_live["fine"],
                                           "achieved": (2 * F_MLP * args.instances * args.rays * m_fine * fwd_live["fine"]
@@ -780,7 +781,7 @@ def run_native(args):
                                           "frac": (2 * F_MLP * args.instances * args.rays * m_fine * fwd_live["fine"]
                                                    / (per_kernel["field_forward_fine"] * 1e-3) / 1e12 / fma_peak_tflops)
                                           if per_kernel.get("field_forward_fine") else None,
-                                          "note": "2F credited per executed (sample, instance); the time includes the culling pre-pass launch"},
+                                          "note": "2F credited per executed (sample, instance); with culling the time includes the pre-pass launch"},
                          "kernel_ms": bwd_ms, "algorithmic_flops_per_launch": bwd_flops,
                          "algorithmic_hbm_bytes_per_step": hbm_bytes,
                          "hbm_peak_gbs": peaks.get("hbm_gbs")},

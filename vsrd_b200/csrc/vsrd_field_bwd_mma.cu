@@ -1,4 +1,4 @@
-// sm_100a kernels of the VSRD silhouette-renderer hot path, part 3b: tensor-core field backward (v5).
+// sm_100a kernels of the VSRD silhouette-renderer hot path, part 3b: tensor-core field backward (v6).
 //
 // Replaces the autograd double-backward replay of the reference (renderers.py:218-228 create_graph=True,
 // main.py:859) for the residual-MLP instances.  Given the adjoints (dd, dG) of every (sample, instance)
@@ -7,22 +7,29 @@
 // w.r.t. the 1617 MLP weights and the 15 pose parameters of the instance ("one tangent + one reverse
 // sweep"; the scalar restatement is vsrd_math.cuh::field_backward).
 //
-// One warp owns a tile of 16 MT samples of one instance in the mma.sync fragment layout of vsrd_frag.cuh:
+// One warp owns a tile of 16 samples of one instance in the mma.sync fragment layout of vsrd_frag.cuh:
 //   1. lane == sample: position, box SDF, tangent direction v = R^T dG, PE arguments
-//   2. dual forward sweep (value + tangent along v): 3xTF32 mma.sync contractions chained in registers,
-//      LayerNorm statistics by quad reductions; LayerNorm outputs (z, zd) of layers 1..3 go to a
-//      lane-private shared-memory stash, those of layer 4 stay in registers
-//   3. reverse sweep layer by layer: transposed contractions (3xTF32), LayerNorm/GELU second-order
-//      adjoints, and the weight gradient dW_l += hbar^T g + hdbar^T gd as a sample-contracted bf16x2
-//      mma.sync m16n8k16 whose operands are transposed in registers by movmatrix
+//   2. dual forward sweep (value + tangent along v): mma.sync m16n8k16 contractions on bf16 hi + lo operands chained in
+//      registers, weights and biases CENTRED over the output index so that the LayerNorm code needs no mean reductions
+//      (vsrd_frag.cuh::stage_weight_fragments); LayerNorm outputs (z, zd) of layers 1..3 go to a lane-private
+//      shared-memory stash, those of layer 4 stay in registers
+//   3. reverse sweep layer by layer: transposed contractions, LayerNorm/GELU second-order adjoints, and the weight
+//      gradient dW_l += hbar^T g + hdbar^T gd as a sample-contracted m16n8k16 whose operands are transposed in registers
+//      by movmatrix (the adjoints' bf16 packs are shared with the transposed contraction)
 //   4. lane == sample: chain through |p_x|, the box SDF and the pose
-// Weight-gradient accumulators live in per-warp shared memory in fragment layout (plain float4
-// load/add/store, no atomics, deterministic) and are reduced once per (CTA, instance) segment into one
-// partial row; reduce_segment_rows_kernel sums the rows of each instance.
+// Weight-gradient and pose accumulators live in per-warp shared memory (plain float4 load/add/store, no atomics,
+// deterministic) and are reduced once per (CTA, instance) segment into one partial row; reduce_segment_rows_kernel sums
+// the rows of each instance and maps the gradient of the centred weights back.
 //
-// Persistent: gridDim.x CTAs split the N * tiles_per_inst warp tiles evenly (any N fills the SMs); a
-// CTA restages the weight fragments when its range crosses an instance boundary.  Segment (cta b,
-// instance i) writes partial row b + i (strictly increasing along the tile order, hence unique).
+// Persistent: gridDim.x CTAs split the N * tiles_per_inst warp tiles into contiguous ranges -- evenly, or with instance
+// culling by live work (backward_ranges_kernel) -- so any N fills the SMs; a CTA restages the weight fragments when its
+// range crosses an instance boundary.  Segment (cta b, instance i) writes partial row b + i (strictly increasing along
+// the tile order, hence unique).
+//
+// History of the contraction format (cfg2 fine pass, N = 8, R = 1000, M = 199): 3xTF32 on m16n8k8 0.741 ms; + centring
+// folded into the weights 0.695 ms; bf16 hi + lo on m16n8k16 (half the tensor instructions: both shapes issue at the same
+// rate on B200, and the legacy tensor pipe was a quarter of the stall samples) + pose accumulators in the shared memory
+// the smaller weight image frees 0.613 ms.
 #include "vsrd_frag.cuh"
 
 namespace vsrd {
@@ -33,15 +40,15 @@ constexpr int kAccL0 = 9;                     // layer 0: input tiles 0..5, bias
 constexpr int kAccLast = 16;                  // last layer: this lane's 4 channels
 constexpr int kAccPose = 17;                  // (sum obar, pose 0..2) (pose 3..6) (pose 7..10) (pose 11..14), lane == sample
 
-// MT = m-tiles (16 samples) per warp tile.  MT = 2: 8 warps x 255 registers, pose accumulators in shared memory.
-// MT = 1: 12 warps x <= 168 registers (3 warps per scheduler instead of 2), pose accumulators in registers so that
-// 12 warps' weight-gradient accumulators + stashes still fit the 227 KB of shared memory.
+// MT = m-tiles (16 samples) per warp tile.  Shipped: MT = 1, 12 warps x 168 registers (3 warps per scheduler); the 12 KB
+// of bf16 weight fragments leave room for the pose accumulators (4 fragments per warp) next to 12 warps' weight-
+// gradient accumulators and stashes: 217 KB of the 227 KB.  (MT = 2: 8 warps x 255 registers, measured slower.)
 template <int MT>
 struct BwdCfg {
     static constexpr int kWarps = MT == 2 ? 8 : 12;
     static constexpr int kThreads = kWarps * 32;
     static constexpr int kRows = 16 * MT;
-    static constexpr bool kPoseInRegs = false;             // bf16 weight fragments (12 KB instead of 24 KB) leave room for the pose accumulators in shared memory
+    static constexpr bool kPoseInRegs = false;             // true: 16 more registers per thread instead of 24 KB of shared memory
     static constexpr int kAccFrags = kPoseInRegs ? 17 : 21;
     static constexpr int kAccFloat4 = kAccFrags * 32;
     static constexpr int kLayerPairs = 4 * MT;                      // pair rows (float2 x 32 lanes) of z per layer; as many of zd
@@ -711,7 +718,7 @@ __global__ void __launch_bounds__(BwdCfg<MT>::kThreads, 1) field_backward_mma_ke
 // [range_starts[b], range_starts[b + 1]).  The kernel accumulated the gradient w.r.t. the CENTRED weights P W_l, P b_l of
 // layers 0..3 (frag::stage_weight_fragments); dW = P dW' subtracts, per input column, the mean over the 16 outputs.
 // grid (5, N): blockIdx.x = layer 0 | hidden layer 1..3 | last layer + pose.
-constexpr int kReduceThreads = 256;
+constexpr int kReduceThreads = 1024;
 __global__ void __launch_bounds__(kReduceThreads) reduce_segment_rows_kernel(
         const float* __restrict__ partials, const long long* __restrict__ range_starts, int grid, int tiles_per_inst,
         float* __restrict__ gloc, float* __restrict__ grot, float* __restrict__ gdim, float* __restrict__ gW) {
@@ -732,8 +739,15 @@ __global__ void __launch_bounds__(kReduceThreads) reduce_segment_rows_kernel(
     const int count = section == 0 ? kW1 : (section <= 3 ? kWStride : kGradStride - kW4);
     const int fan = section == 0 ? kEnc + 1 : kHid + 1;     // row length [inputs + bias] of the section's layer
     for (int k = threadIdx.x; k < count; k += blockDim.x) {
+        const float* col = partials + (size_t)inst * kGradStride + base + k;
         float s = 0.0f;
-        for (int b = s_first; b <= s_last; ++b) s += partials[((size_t)b + inst) * kGradStride + base + k];
+        for (int b = s_first; b <= s_last; b += 8) {        // eight rows in flight: the loop is pure L2 latency otherwise
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = b + u <= s_last ? __ldg(col + (size_t)(b + u) * kGradStride) : 0.0f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += v[u];
+        }
         s_sum[k] = s;
     }
     __syncthreads();
@@ -767,7 +781,7 @@ static int setup() {
     if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return fail("vsrd_b200: cudaGetDeviceProperties failed%s");
     if (cudaFuncSetAttribute(field_backward_mma_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)BwdCfg<1>::kSmemBytes) != cudaSuccess)
-        return fail("vsrd_b200: cannot reserve %s of shared memory for field_backward_mma_kernel (built for sm_100a)", "206 KB");
+        return fail("vsrd_b200: cannot reserve %s of shared memory for field_backward_mma_kernel (built for sm_100a)", "217 KB");
     g_sms = prop.multiProcessorCount;
     return 0;
 }

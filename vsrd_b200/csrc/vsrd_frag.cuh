@@ -1,27 +1,21 @@
-// Warp-level building blocks of the tensor-core field kernels (v4).
+// Warp-level building blocks of the tensor-core field BACKWARD kernel (vsrd_field_bwd_mma.cu).
 //
-// One warp owns a tile of 32 (sample, instance) pairs of one instance: two 16-row MMA tiles.  All layer
-// activations live in registers in the mma.sync accumulator ("C") layout and are chained into the next
-// contraction as the A operand without leaving the register file:
+// One warp owns a tile of 16 (sample, instance) pairs of one instance.  All layer activations live in registers in the
+// mma.sync accumulator ("C") layout and are chained into the next contraction as the A operand without leaving the
+// register file:
 //
 //   lane = 4 g + t   (g = lane >> 2 in 0..7, t = lane & 3)
-//   C fragment of an m16n8 tile:  c0 (row g, col 2t)  c1 (row g, col 2t+1)  c2 (row g+8, col 2t)  c3 (row g+8, col 2t+1)
-//   A fragment of m16n8k8 (tf32): a0 (row g, k t)     a1 (row g+8, k t)     a2 (row g, k t+4)     a3 (row g+8, k t+4)
-//   B fragment of m16n8k8 (tf32): b0 (k t, n g)       b1 (k t+4, n g)
+//   C fragment of an m16n8 tile:       c0 (row g, col 2t)  c1 (row g, col 2t+1)  c2 (row g+8, col 2t)  c3 (row g+8, col 2t+1)
+//   A fragment of m16n8k16 (bf16 x 2): a0 (row g, k 2t..2t+1)  a1 (row g+8, k 2t..2t+1)  a2 (row g, k 2t+8..)  a3 (row g+8, k 2t+8..)
+//   B fragment of m16n8k16:            b0 (k 2t..2t+1, n g)    b1 (k 2t+8..2t+9, n g)
 //
-// The contraction index k is only summed over, so it can be permuted freely as long as A and B agree.
-// We let k-slot t of k-step j stand for channel 8j+2t and k-slot t+4 for channel 8j+2t+1: then the C
-// fragment of n-tile j IS the A fragment of k-step j (a0=c0, a1=c2, a2=c1, a3=c3) and the weight
-// fragments are staged once per CTA in that permuted order.
+// so the C fragments of n-tiles (0, 1) of a 16-channel layer ARE the A fragment of the next layer's single k-step once
+// each (c0, c1) / (c2, c3) pair is packed to bf16 x 2.  Rows: a lane holds rows g and g + 8 of the tile; activation
+// registers are indexed x[mt][nt][q] with q = 0: (c0, c1) of row g, q = 1: (c2, c3) of row g + 8.
 //
-// Rows: a lane holds 4 rows of the 32-row tile, "slots" s = 0..3 -> row 8 s + g  (m-tile s >> 1, half s & 1).
-// Activation registers are indexed x[mt][nt][q] (q = c0..c3); slot s holds x[s>>1][nt][2*(s&1) + {0,1}].
-//
-// Precision: every contraction runs as 3xTF32 (hi*hi + hi*lo + lo*hi with fp32 accumulation), which
-// keeps ~21 mantissa bits: the silhouette parity bar (1e-4 abs) cannot be met by single-pass TF32
-// (7.3e-5 from the hidden contractions alone).  profiles/r01_pipe_rates_b200.txt:
-// the legacy tensor pipe sustains one m16n8k8 per 5-6 cycles per SM sub-partition and overlaps
-// perfectly with >= 8 FP32 instructions per MMA, which is the ratio these kernels have.
+// Precision: operands are bf16 hi + bf16 lo (16 mantissa bits), products hi*hi + hi*lo + lo*hi with fp32 accumulation:
+// ~1e-5 per contraction, two orders below the 1e-3 gradient tolerance (measured at the BASELINE shapes: the gradients
+// differ from the fp32 reference's by 1e-5 .. 1.5e-4 and track its own error against fp64, tests/test_gpu_fullsize.py).
 #pragma once
 #include "vsrd_common.cuh"
 
@@ -62,110 +56,6 @@ constexpr int kTailW4 = 64;
 constexpr int kTailB4 = 80;
 constexpr int kTailFloats = 96;
 constexpr size_t kWeightBytes = (size_t)kFragFloat4 * 16 + kTailFloats * 4;
-
-// The TF32 mask lives in constant memory on purpose: with an immediate, ptxas proves that the tensor core
-// ignores the low 13 bits, drops the AND and then has to MOV the raw (register-pair allocated) activations
-// into a contiguous A-operand quad before every HMMA (13 % of the executed instructions were such MOVs,
-// profiles/r01_v8_*).  A constant-bank operand keeps the LOP3, which writes the operand quad directly.
-static __constant__ uint32_t kTf32Mask = 0xffffe000u;
-
-__device__ __forceinline__ void split(float x, uint32_t& hi, uint32_t& lo) {
-    hi = __float_as_uint(x) & kTf32Mask;              // exact TF32 (truncated)
-    lo = __float_as_uint(x - __uint_as_float(hi));    // remainder; the MMA reads its top 19 bits
-}
-
-// An accumulator tile is two register pairs: d[0] = (c0, c1) (row g), d[1] = (c2, c3) (row g + 8).
-__device__ __forceinline__ void mma_tf32(f2 (&d)[2], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(d[0].x), "+f"(d[0].y), "+f"(d[1].x), "+f"(d[1].y)
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-
-// d += A * B with A = ah + al, B = bh + bl (the lo*lo term is below fp32 rounding)
-__device__ __forceinline__ void mma3(f2 (&d)[2], const uint32_t (&ah)[4], const uint32_t (&al)[4], const float4& b) {
-    mma_tf32(d, al, __float_as_uint(b.x), __float_as_uint(b.y));
-    mma_tf32(d, ah, __float_as_uint(b.z), __float_as_uint(b.w));
-    mma_tf32(d, ah, __float_as_uint(b.x), __float_as_uint(b.y));
-}
-
-// The same with a zero accumulator on input (first k-step of a product without bias): the C operand is
-// the zero register, so no accumulator clearing is issued.
-__device__ __forceinline__ void mma_tf32_zero(f2 (&d)[2], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
-                 : "=f"(d[0].x), "=f"(d[0].y), "=f"(d[1].x), "=f"(d[1].y)
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(0.0f));
-}
-__device__ __forceinline__ void mma3_zero(f2 (&d)[2], const uint32_t (&ah)[4], const uint32_t (&al)[4], const float4& b) {
-    mma_tf32_zero(d, al, __float_as_uint(b.x), __float_as_uint(b.y));
-    mma_tf32(d, ah, __float_as_uint(b.z), __float_as_uint(b.w));
-    mma_tf32(d, ah, __float_as_uint(b.x), __float_as_uint(b.y));
-}
-
-// One k-step of FOUR accumulator tiles at once: x0, x1 share the A operand X (n-tiles w0, w1), y0, y1
-// share Y.  The three 3xTF32 passes are issued pass-major, so two MMAs into the same accumulator are
-// always three independent MMAs apart: a back-to-back chain stalls on the tensor pipe's result latency
-// (profiles/r01_v5_*: HMMA = 6 % of the instructions but 22 % of the stall samples, "wait").
-template <bool kZero>
-__device__ __forceinline__ void mma3_quad(f2 (&x0)[2], f2 (&x1)[2], f2 (&y0)[2], f2 (&y1)[2],
-                                          const uint32_t (&xh)[4], const uint32_t (&xl)[4],
-                                          const uint32_t (&yh)[4], const uint32_t (&yl)[4],
-                                          const float4& w0, const float4& w1) {
-    const uint32_t w0h0 = __float_as_uint(w0.x), w0h1 = __float_as_uint(w0.y), w0l0 = __float_as_uint(w0.z), w0l1 = __float_as_uint(w0.w);
-    const uint32_t w1h0 = __float_as_uint(w1.x), w1h1 = __float_as_uint(w1.y), w1l0 = __float_as_uint(w1.z), w1l1 = __float_as_uint(w1.w);
-    if (kZero) {
-        mma_tf32_zero(x0, xl, w0h0, w0h1); mma_tf32_zero(x1, xl, w1h0, w1h1);
-        mma_tf32_zero(y0, yl, w0h0, w0h1); mma_tf32_zero(y1, yl, w1h0, w1h1);
-    } else {
-        mma_tf32(x0, xl, w0h0, w0h1); mma_tf32(x1, xl, w1h0, w1h1);
-        mma_tf32(y0, yl, w0h0, w0h1); mma_tf32(y1, yl, w1h0, w1h1);
-    }
-    mma_tf32(x0, xh, w0l0, w0l1); mma_tf32(x1, xh, w1l0, w1l1);
-    mma_tf32(y0, yh, w0l0, w0l1); mma_tf32(y1, yh, w1l0, w1l1);
-    mma_tf32(x0, xh, w0h0, w0h1); mma_tf32(x1, xh, w1h0, w1h1);
-    mma_tf32(y0, yh, w0h0, w0h1); mma_tf32(y1, yh, w1h0, w1h1);
-}
-
-// Two accumulator tiles sharing one A operand (one m-tile per warp), pass-major.
-template <bool kZero>
-__device__ __forceinline__ void mma3_pair(f2 (&x0)[2], f2 (&x1)[2], const uint32_t (&xh)[4], const uint32_t (&xl)[4],
-                                          const float4& w0, const float4& w1) {
-    const uint32_t w0h0 = __float_as_uint(w0.x), w0h1 = __float_as_uint(w0.y), w0l0 = __float_as_uint(w0.z), w0l1 = __float_as_uint(w0.w);
-    const uint32_t w1h0 = __float_as_uint(w1.x), w1h1 = __float_as_uint(w1.y), w1l0 = __float_as_uint(w1.z), w1l1 = __float_as_uint(w1.w);
-    if (kZero) { mma_tf32_zero(x0, xl, w0h0, w0h1); mma_tf32_zero(x1, xl, w1h0, w1h1); }
-    else { mma_tf32(x0, xl, w0h0, w0h1); mma_tf32(x1, xl, w1h0, w1h1); }
-    mma_tf32(x0, xh, w0l0, w0l1); mma_tf32(x1, xh, w1l0, w1l1);
-    mma_tf32(x0, xh, w0h0, w0h1); mma_tf32(x1, xh, w1h0, w1h1);
-}
-
-// All accumulators [MT][2 n-tiles] of one k-step.
-template <bool kZero, int MT>
-__device__ __forceinline__ void mma3_step(f2 (&acc)[MT][2][2], const uint32_t (&ah)[MT][4], const uint32_t (&al)[MT][4],
-                                          const float4& w0, const float4& w1) {
-    if constexpr (MT == 2) mma3_quad<kZero>(acc[0][0], acc[0][1], acc[1][0], acc[1][1], ah[0], al[0], ah[1], al[1], w0, w1);
-    else mma3_pair<kZero>(acc[0][0], acc[0][1], ah[0], al[0], w0, w1);
-}
-
-// A fragment (hi, lo) of k-step `nt` from an activation tile held in C layout.
-__device__ __forceinline__ void a_from_c(const f2 (&c)[2], uint32_t (&ah)[4], uint32_t (&al)[4]) {
-    split(c[0].x, ah[0], al[0]);
-    split(c[1].x, ah[1], al[1]);
-    split(c[0].y, ah[2], al[2]);
-    split(c[1].y, ah[3], al[3]);
-}
-
-// A fragment from two register pairs that already are (row g, row g + 8) pairs: lo = x - hi packed.
-//   p01 -> (a0, a1) = k-slot t of rows g, g + 8;  p23 -> (a2, a3) = k-slot t + 4
-__device__ __forceinline__ void a_from_row_pairs(f2 p01, f2 p23, uint32_t (&ah)[4], uint32_t (&al)[4]) {
-    f2 h01, h23;
-    const uint32_t mask = kTf32Mask;
-    ah[0] = __float_as_uint(p01.x) & mask; ah[1] = __float_as_uint(p01.y) & mask;
-    ah[2] = __float_as_uint(p23.x) & mask; ah[3] = __float_as_uint(p23.y) & mask;
-    h01.x = __uint_as_float(ah[0]); h01.y = __uint_as_float(ah[1]);
-    h23.x = __uint_as_float(ah[2]); h23.y = __uint_as_float(ah[3]);
-    const f2 l01 = sub2(p01, h01), l23 = sub2(p23, h23);
-    al[0] = __float_as_uint(l01.x); al[1] = __float_as_uint(l01.y);
-    al[2] = __float_as_uint(l23.x); al[3] = __float_as_uint(l23.y);
-}
 
 // ---- sample-contracted products (weight gradients) ---------------------------------------------
 // dW[o][i] = sum_samples hbar[s][o] g[s][i] contracts over the SAMPLE index, which the C layout keeps in
@@ -249,17 +139,9 @@ __device__ __forceinline__ void a_bf16_from_c(const f2 (&c)[2][2], uint32_t (&ah
     pack_bf16_split(c[1][1].x, c[1][1].y, ah[3], al[3]);
 }
 
-// A operand (16 outputs x 16 samples of one m-tile) of the weight-gradient product from the adjoint's
-// two C tiles c[nt][q] (nt = output half): rows = outputs, k = samples.
-__device__ __forceinline__ void wgrad_a_operand(const f2 (&c)[2][2], uint32_t (&ah)[4], uint32_t (&al)[4]) {
-    pack_transposed(c[0][0], ah[0], al[0]);   // outputs 0-7,  samples 0-7
-    pack_transposed(c[1][0], ah[1], al[1]);   // outputs 8-15, samples 0-7
-    pack_transposed(c[0][1], ah[2], al[2]);   // outputs 0-7,  samples 8-15
-    pack_transposed(c[1][1], ah[3], al[3]);   // outputs 8-15, samples 8-15
-}
-
-// The same operand from the packs a_bf16_from_c() made of the adjoint for its transposed contraction (the packing, 5
-// instructions per register, is shared): in place, (p0, p1, p2, p3) = (nt0 g | nt0 g+8 | nt1 g | nt1 g+8) ->
+// A operand (16 outputs x 16 samples of one m-tile) of the weight-gradient product, rows = outputs, k = samples: from
+// the packs a_bf16_from_c() made of the adjoint for its transposed contraction (the packing, 5 instructions per
+// register, is shared): in place, (p0, p1, p2, p3) = (nt0 g | nt0 g+8 | nt1 g | nt1 g+8) ->
 // (T p0, T p2, T p1, T p3).
 __device__ __forceinline__ void wgrad_a_from_packs(uint32_t (&h)[4], uint32_t (&l)[4]) {
     const uint32_t h1 = h[1], l1 = l[1];
@@ -362,12 +244,6 @@ __device__ __forceinline__ void stage_weight_fragments(const float* __restrict__
 }
 
 // ---- small helpers ---------------------------------------------------------------------------
-__device__ __forceinline__ float quad_sum(float v) {
-    v += __shfl_xor_sync(kFull, v, 1);
-    v += __shfl_xor_sync(kFull, v, 2);
-    return v;
-}
-
 // two independent quad sums at once: (x, y) -> (sum over the quad of x, of y)
 __device__ __forceinline__ f2 quad_sum2(f2 v) {
     f2 o;
@@ -377,46 +253,9 @@ __device__ __forceinline__ f2 quad_sum2(f2 v) {
     return add2(v, o);
 }
 
-// sin / cos with a three-term Cody-Waite reduction (|x| < ~1e4) and the single-precision minimax
-// polynomials on [-pi/4, pi/4]; absolute error ~1e-7, no slow path, no local memory.
-__host__ __device__ __forceinline__ void sincos_cw(float x, float& s, float& c) {
-    const float kf = rintf(x * 0.63661977236758134308f);
-    float r = fmaf(kf, -1.5707962513e+00f, x);
-    r = fmaf(kf, -7.5497894159e-08f, r);
-    r = fmaf(kf, -5.3903029534e-15f, r);
-    const int q = (int)kf;
-    const float r2 = r * r;
-    float sp = fmaf(r2, -1.9515295891e-4f, 8.3321608736e-3f);
-    sp = fmaf(sp, r2, -1.6666654611e-1f);
-    sp = fmaf(sp * r2, r, r);
-    float cp = fmaf(r2, 2.443315711809948e-5f, -1.388731625493765e-3f);
-    cp = fmaf(cp, r2, 4.166664568298827e-2f);
-    cp = fmaf(cp, r2, -0.5f);
-    cp = fmaf(cp, r2, 1.0f);
-    float ss = (q & 1) ? cp : sp;
-    float cc = (q & 1) ? sp : cp;
-    s = (q & 2) ? -ss : ss;
-    c = ((q + 1) & 2) ? -cc : cc;
-}
-
-// Phi, phi of the exact-erf GELU (see vsrd_math.cuh::gelu_terms) with single-instruction reciprocal.
-__device__ __forceinline__ void gelu_terms_fast(float z, float& Phi, float& phi) {
-    const float az = fabsf(z);
-    float E;                                                          // exp(-z^2/2)
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(E) : "f"(-0.72134752044448170368f * z * z));
-    float t;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f * kInvSqrt2, az, 1.0f)));
-    float poly = fmaf(1.061405429f, t, -1.453152027f);
-    poly = fmaf(poly, t, 1.421413741f);
-    poly = fmaf(poly, t, -0.284496736f);
-    poly = fmaf(poly, t, 0.254829592f);
-    const float tail = 0.5f * poly * t * E;
-    Phi = z >= 0.0f ? 1.0f - tail : tail;
-    phi = kInvSqrt2Pi * E;
-}
-
-// The same for a channel pair.  zz = z^2 is returned for gelu'' = phi (2 - z^2).  The polynomial
-// coefficients carry the factor 1/2 of the tail; Phi = 1/2 + copysign(1/2 - tail, z).
+// Phi, phi of the exact-erf GELU (vsrd_math.cuh::gelu_terms; Abramowitz-Stegun 7.1.26 with ex2 / rcp approximations) for a
+// channel pair.  zz = z^2 is returned for gelu'' = phi (2 - z^2).  The polynomial coefficients carry the factor 1/2 of
+// the tail; Phi = 1/2 + copysign(1/2 - tail, z).
 __device__ __forceinline__ void gelu_terms2(f2 z, f2& Phi, f2& phi, f2& zz) {
     zz = mul2(z, z);
     const f2 arg = mul2(zz, bc(-0.72134752044448170368f));
@@ -437,7 +276,8 @@ __device__ __forceinline__ void gelu_terms2(f2 z, f2& Phi, f2& phi, f2& zz) {
     phi = mul2(E, bc(kInvSqrt2Pi));
 }
 
-// sincos_cw on a pair of arguments.
+// sin / cos of a pair of arguments: three-term Cody-Waite reduction (|x| < ~1e4) and the single-precision minimax
+// polynomials on [-pi/4, pi/4]; absolute error ~1e-7, no slow path, no local memory.
 __device__ __forceinline__ void sincos_cw2(f2 x, f2& s, f2& c) {
     const f2 kx = mul2(x, bc(0.63661977236758134308f));
     f2 kf;
@@ -474,7 +314,6 @@ struct EncodingT {
     f2 cs[MT][3][2];
     f2 sn[MT][3][2];
 };
-using Encoding2 = EncodingT<2>;
 
 // a[mt][c] = PE argument fl(pi * u_c) of rows (g, g + 8) of m-tile mt.
 template <int MT>
@@ -497,41 +336,6 @@ __device__ __forceinline__ void encode2(const f2 (&a)[MT][3], int t, EncodingT<M
         }
 }
 
-// Per-lane view of the positional encoding of its 4 rows: lane t owns the (cos, sin) pairs of
-// frequencies k = t and k = t + 4 of each coordinate (channels 16 c + 2 k + {0, 1}), which are exactly
-// the A-fragment elements of k-steps 2c and 2c+1.
-struct Encoding {
-    float cs[4][3][2];   // [slot][coordinate][k = t, t + 4]
-    float sn[4][3][2];
-};
-
-__device__ __forceinline__ void encode(const float (&a)[4][3], int t, Encoding& e) {
-    const float f = (float)(1 << t);
-#pragma unroll
-    for (int s = 0; s < 4; ++s)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            float sn, cs;
-            sincos_cw(f * a[s][c], sn, cs);        // f * a is exact: matches fl(2^k * fl(pi * u))
-            e.cs[s][c][0] = cs; e.sn[s][c][0] = sn;
-#pragma unroll
-            for (int d = 0; d < 4; ++d) {          // four octaves up by the double-angle recurrence
-                const float s2 = 2.0f * sn * cs;
-                cs = (cs - sn) * (cs + sn);
-                sn = s2;
-            }
-            e.cs[s][c][1] = cs; e.sn[s][c][1] = sn;
-        }
-}
-
-// Row `row` of the 32-row tile lives in quad (row & 7) as slot (row >> 3).  Move one per-row value
-// from the fragment layout (v[slot], identical in the 4 lanes of a quad) to lane == row.
-__device__ __forceinline__ float rows_to_lanes(const float (&v)[4], int lane) {
-    const int t = lane & 3;
-    const float mine = t == 0 ? v[0] : (t == 1 ? v[1] : (t == 2 ? v[2] : v[3]));
-    return __shfl_sync(kFull, mine, 4 * (lane & 7) + (lane >> 3));
-}
-
 // Tiles of 16 * MT rows: row r (= lane, r < 16 MT) lives in quad (r & 7) as slot (r >> 3); pairs are
 // (slot 2 mt, slot 2 mt + 1) = rows (g, g + 8) of m-tile mt.
 template <int MT>
@@ -550,13 +354,6 @@ __device__ __forceinline__ float row_slots_to_lanes(const float (&v)[2 * MT], in
 #pragma unroll
     for (int s = 1; s < 2 * MT; ++s) mine = (t == s) ? v[s] : mine;
     return __shfl_sync(kFull, mine, 4 * (lane & 7) + ((lane >> 3) & (2 * MT - 1)));
-}
-
-// The inverse: lane == row holds x; returns x of the 4 rows this lane owns in the fragment layout.
-__device__ __forceinline__ void lanes_to_rows(float x, int lane, float (&v)[4]) {
-    const int g = lane >> 2;
-#pragma unroll
-    for (int s = 0; s < 4; ++s) v[s] = __shfl_sync(kFull, x, 8 * s + g);
 }
 
 }  // namespace frag
