@@ -11,15 +11,24 @@
 //   1. lane == sample: position, box SDF, tangent direction v = R^T dG, PE arguments
 //   2. dual forward sweep (value + tangent along v): mma.sync m16n8k16 contractions on bf16 hi + lo operands chained in
 //      registers, weights and biases CENTRED over the output index so that the LayerNorm code needs no mean reductions
-//      (vsrd_frag.cuh::stage_weight_fragments); LayerNorm outputs (z, zd) of layers 1..3 go to a lane-private
-//      shared-memory stash, those of layer 4 stay in registers
+//      (vsrd_frag.cuh::stage_weight_fragments); LayerNorm outputs (z, zd) of layers 1..3 and the (Phi, phi) of their
+//      GELUs go to a lane-private stash in TENSOR MEMORY (tcgen05.st), those of layer 4 stay in registers
 //   3. reverse sweep layer by layer: transposed contractions, LayerNorm/GELU second-order adjoints, and the weight
 //      gradient dW_l += hbar^T g + hdbar^T gd as a sample-contracted m16n8k16 whose operands are transposed in registers
-//      by movmatrix (the adjoints' bf16 packs are shared with the transposed contraction)
+//      by movmatrix (the adjoints' bf16 packs are shared with the transposed contraction); the GELU factors come from
+//      the stashed (Phi, phi), no MUFU
 //   4. lane == sample: chain through |p_x|, the box SDF and the pose
-// Weight-gradient and pose accumulators live in per-warp shared memory (plain float4 load/add/store, no atomics,
-// deterministic) and are reduced once per (CTA, instance) segment into one partial row; reduce_segment_rows_kernel sums
-// the rows of each instance and maps the gradient of the centred weights back.
+// The weight-gradient accumulators live in tensor memory too (tcgen05.ld / add in registers by the MMAs / tcgen05.st,
+// lane-private, no atomics, deterministic), the pose accumulators in per-warp shared memory; both are reduced once per
+// (CTA, instance) segment into one partial row; reduce_segment_rows_kernel sums the rows of each instance and maps the
+// gradient of the centred weights back.
+//
+// Tensor memory here is a 256 KB lane-private scratchpad, not an MMA operand space: the kernel has no tcgen05.mma (the
+// tcgen05 backward that was built and measured is slower, vsrd_field_bwd_umma.cu), but every warp owns 164 TMEM columns
+// of its lane quarter (BwdCfg) and moves 4 / 8 / 16 of them per tcgen05.ld / tcgen05.st.  Against the shared-memory
+// stash this removes 16 STS.64 + 16 LDS.64 per layer and tile with their address arithmetic and bank conflicts, the
+// recomputation of the GELU terms in the reverse sweep, and 42 LDS.128 / STS.128 of accumulator traffic per tile, and
+// leaves the shared-memory pipe to the shuffles and movmatrix: 331 M -> 285 M warp instructions.
 //
 // Persistent: gridDim.x CTAs split the N * tiles_per_inst warp tiles into contiguous ranges -- evenly, or with instance
 // culling by live work (backward_ranges_kernel) -- so any N fills the SMs; a CTA restages the weight fragments when its
@@ -29,8 +38,11 @@
 // History of the contraction format (cfg2 fine pass, N = 8, R = 1000, M = 199): 3xTF32 on m16n8k8 0.741 ms; + centring
 // folded into the weights 0.695 ms; bf16 hi + lo on m16n8k16 (half the tensor instructions: both shapes issue at the same
 // rate on B200, and the legacy tensor pipe was a quarter of the stall samples) + pose accumulators in the shared memory
-// the smaller weight image frees 0.613 ms.
+// the smaller weight image frees 0.613 ms; (Phi, phi) stash in tensor memory 0.590 ms; + (z, zd) stash 0.560 ms; +
+// accumulators 0.541 ms; + the encoding parked in shared memory across the hidden layers (spills 240 -> 44 B), sample
+// positions kept for phase 4, pass-major weight-gradient MMAs, unrolled reverse loop 0.533 ms.
 #include "vsrd_frag.cuh"
+#include "vsrd_umma.cuh"
 
 namespace vsrd {
 namespace bwd5 {
@@ -40,21 +52,30 @@ constexpr int kAccL0 = 9;                     // layer 0: input tiles 0..5, bias
 constexpr int kAccLast = 16;                  // last layer: this lane's 4 channels
 constexpr int kAccPose = 17;                  // (sum obar, pose 0..2) (pose 3..6) (pose 7..10) (pose 11..14), lane == sample
 
-// MT = m-tiles (16 samples) per warp tile.  Shipped: MT = 1, 12 warps x 168 registers (3 warps per scheduler); the 12 KB
-// of bf16 weight fragments leave room for the pose accumulators (4 fragments per warp) next to 12 warps' weight-
-// gradient accumulators and stashes: 217 KB of the 227 KB.  (MT = 2: 8 warps x 255 registers, measured slower.)
+// MT = m-tiles (16 samples) per warp tile.  Shipped: MT = 1, 12 warps x 168 registers (3 warps per scheduler).
+// Measured and not kept: MT = 2 (8 warps x 255 registers): slower; 16 warps x 128 registers with the stash in tensor
+// memory (shared memory no longer limits the warp count): 0.556 ms, the same as 12 warps at that point -- the spills
+// cost what the fourth warp per scheduler hides -- and 16 warps leave no TMEM columns for the accumulators; software
+// prefetch of the next tile's adjoints into L1 / L2: +0.5 %.
 template <int MT>
 struct BwdCfg {
-    static constexpr int kWarps = MT == 2 ? 8 : 12;
+    static_assert(MT == 1, "the tensor-memory layout below is the one-m-tile kernel's");
+    static constexpr int kWarps = 12;
     static constexpr int kThreads = kWarps * 32;
     static constexpr int kRows = 16 * MT;
     static constexpr bool kPoseInRegs = false;             // true: 16 more registers per thread instead of 24 KB of shared memory
     static constexpr int kAccFrags = kPoseInRegs ? 17 : 21;
     static constexpr int kAccFloat4 = kAccFrags * 32;
-    static constexpr int kLayerPairs = 4 * MT;                      // pair rows (float2 x 32 lanes) of z per layer; as many of zd
-    static constexpr int kStashFloats = 3 * 2 * kLayerPairs * 32 * 2;   // per warp: layers 1..3 x [z | zd]
+    static constexpr int kEncPairs = 12;                   // per lane: (cos, sin) x 3 coordinates x 2 octave halves, row pairs
+    // shared memory per warp: accumulator slots (pose fragments live here; fragments 0..16 only at the flush), the
+    // flush row, the sample positions and the parked encoding
     static constexpr size_t kSmemBytes = frag::kWeightBytes
-        + (size_t)kWarps * (kAccFloat4 * sizeof(float4) + kStashFloats * sizeof(float) + 32 * sizeof(float));
+        + (size_t)kWarps * (kAccFloat4 * sizeof(float4) + 32 * sizeof(float) + 96 * sizeof(float) + kEncPairs * 32 * sizeof(float2));
+    // tensor memory: every warp owns 164 columns of its lane quarter (3 warps per quarter, 492 of the 512 columns):
+    //   [0, 96)    layers 1..3 x { (z, zd) of the LayerNorm outputs: 16 | (Phi, phi) of their GELU: 16 }
+    //   [96, 164)  weight-gradient accumulator fragments 0..16 (4 columns each)
+    static constexpr uint32_t kTmemWarpCols = 164, kTmemAccCol = 96;
+    static constexpr int kTmemCols = 512;
 };
 
 using frag::f2;
@@ -85,6 +106,14 @@ __device__ __forceinline__ void gelu_pair(f2 z, f2 zd, f2& g, f2& gd, f2& g1, f2
     g = mul2(z, Phi);
     g1 = fma2(z, phi, Phi);
     g2 = mul2(phi, fma2(zz, bc(-1.0f), bc(2.0f)));
+    gd = mul2(g1, zd);
+}
+
+// The same from the (Phi, phi) the forward sweep kept (TMEM stash): no MUFU, bit-identical to gelu_pair.
+__device__ __forceinline__ void gelu_pair_kept(f2 z, f2 zd, f2 Phi, f2 phi, f2& g, f2& gd, f2& g1, f2& g2) {
+    g = mul2(z, Phi);
+    g1 = fma2(z, phi, Phi);
+    g2 = mul2(phi, fma2(mul2(z, z), bc(-1.0f), bc(2.0f)));
     gd = mul2(g1, zd);
 }
 
@@ -216,20 +245,35 @@ __global__ void __launch_bounds__(BwdCfg<MT>::kThreads, 1) field_backward_mma_ke
     static_assert(PAIR == 0 || MT == 1, "tile pairs are a variant of the one-m-tile kernel");
     using Cfg = BwdCfg<MT>;
     constexpr int kWarpsB = Cfg::kWarps, kThreadsB = Cfg::kThreads, kRows = Cfg::kRows, kSlots = 2 * MT;
-    constexpr int kAccFloat4 = Cfg::kAccFloat4, kAccFrags = Cfg::kAccFrags, kLayerPairs = Cfg::kLayerPairs;
-    constexpr int kLayerStride = 2 * kLayerPairs * 32;      // float2 per layer in the stash
+    constexpr int kAccFloat4 = Cfg::kAccFloat4, kAccFrags = Cfg::kAccFrags;
+    constexpr uint32_t kTmemAccCol = Cfg::kTmemAccCol;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4* sF = reinterpret_cast<float4*>(smem_raw);
     float* sTail = reinterpret_cast<float*>(sF + frag::kFragFloat4);
     float4* sAcc = reinterpret_cast<float4*>(sTail + frag::kTailFloats);
-    float* sStash = reinterpret_cast<float*>(sAcc + kWarpsB * kAccFloat4);
-    float* sRed = sStash + kWarpsB * Cfg::kStashFloats;     // [warp][32]: last layer (17) + pose (15)
-
+    float* sRed = reinterpret_cast<float*>(sAcc + kWarpsB * kAccFloat4);   // [warp][32]: last layer (17) + pose (15)
+    float* sPos = sRed + kWarpsB * 32;                      // [warp][3][32]: sample positions, phase 1 -> phase 4
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // [warp][12][32] pairs: the encoding waits here between layer 0 forward and layer 0 reverse (24 registers the
+    // hidden-layer loops can use: register spills 240 -> 44 bytes)
+    float2* sEnc = reinterpret_cast<float2*>(sPos + kWarpsB * 96) + (size_t)warp * Cfg::kEncPairs * 32 + lane;
+    // Tensor memory as the warp's lane-private scratchpad (BwdCfg): this kernel issues no tcgen05.mma, it uses the
+    // 256 KB of TMEM next to the tensor cores for what shared memory served before -- the (z, zd) stash, the GELU terms
+    // (Phi, phi) the reverse sweep would otherwise recompute (2 MUFU + ~14 instructions per channel pair) and the
+    // weight-gradient accumulators -- as x4 / x8 / x16 tcgen05.st / tcgen05.ld of the lane's own row: no bank
+    // conflicts, no address arithmetic, and the shared-memory pipe is left to the shuffles and movmatrix.  Measured
+    // (cfg2 fine pass): 0.613 -> 0.590 ms (Phi, phi) -> 0.560 ms (z, zd) -> 0.541 ms (accumulators).
+    __shared__ uint32_t s_tmem;
+    if (threadIdx.x < 32) umma::tmem_alloc<Cfg::kTmemCols>(&s_tmem);
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    // a warp reaches the 32 lanes of quarter (warp % 4) only
+    const uint32_t tmem_base = s_tmem + ((uint32_t)(warp & 3) << 21) + (uint32_t)(warp >> 2) * Cfg::kTmemWarpCols;
+
     const int t = lane & 3;
     const int quad_base = lane & ~3;
     float4* accL = sAcc + warp * kAccFloat4 + lane;         // accL[fragment * 32]
-    float2* stash = reinterpret_cast<float2*>(sStash + warp * Cfg::kStashFloats) + lane;
     const float4* fragL = sF + lane;
 
     const int total = rays.R * rays.M;
@@ -251,6 +295,11 @@ __global__ void __launch_bounds__(BwdCfg<MT>::kThreads, 1) field_backward_mma_ke
         frag::stage_weight_fragments(scene.W + (size_t)inst * kNumW, sF, sTail, s_mean);
 #pragma unroll
         for (int f = 0; f < kAccFrags; ++f) accL[f * 32] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        {
+            const float zero4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+            for (int f = 0; f < kAccPose; ++f) umma::tmem_st4(tmem_base + kTmemAccCol + 4u * f, zero4);
+        }
         __syncthreads();
         Instance I;
         load_instance(scene, inst, I);
@@ -313,6 +362,8 @@ __global__ void __launch_bounds__(BwdCfg<MT>::kThreads, 1) field_backward_mma_ke
             {
                 float x[3];
                 sample_position(rays, r, j, x);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) sPos[(warp * 3 + c) * 32 + lane] = x[c];      // phase 4 picks it up again
                 BoxEval b;
                 box_eval(x, I, b);
                 const float m[3] = {fabsf(b.p[0]), b.p[1], b.p[2]};
@@ -379,13 +430,16 @@ __global__ void __launch_bounds__(BwdCfg<MT>::kThreads, 1) field_backward_mma_ke
                     else frag::mma3b_quad<false, false>(h[mt][0], h[mt][1], hd[mt][0], hd[mt][1], ah, al, adh, adl, w0, w1);
                 }
             }
+#pragma unroll
+            for (int c = 0; c < 3; ++c)                      // park the encoding until layer 0's reverse step
+#pragma unroll
+                for (int f = 0; f < 2; ++f) { sEnc[(4 * c + 2 * f) * 32] = e.cs[0][c][f]; sEnc[(4 * c + 2 * f + 1) * 32] = e.sn[0][c][f]; }
             // layers 1..3: LayerNorm -> GELU -> linear; lane t keeps 1/sigma and mz of layer t + 1
             float rreg[kSlots], mreg[kSlots];
 #pragma unroll
             for (int s = 0; s < kSlots; ++s) { rreg[s] = 0.0f; mreg[s] = 0.0f; }
 #pragma unroll 1
             for (int l = 1; l <= 3; ++l) {
-                float2* st = stash + (l - 1) * kLayerStride;
 #pragma unroll
                 for (int s = 0; s < kSlots; ++s) {
                     f2& p0 = h[s >> 1][0][s & 1];
@@ -395,15 +449,21 @@ __global__ void __launch_bounds__(BwdCfg<MT>::kThreads, 1) field_backward_mma_ke
                     float rs, mz;
                     ln_dual2(p0, p1, d0, d1, rs, mz);
                     if (t == l - 1) { rreg[s] = rs; mreg[s] = mz; }
-                    st[(2 * s) * 32] = p0; st[(2 * s + 1) * 32] = p1;
-                    st[(kLayerPairs + 2 * s) * 32] = d0; st[(kLayerPairs + 2 * s + 1) * 32] = d1;
+                    {                                       // (z, zd) of the row -> tensor memory
+                        const float zs[8] = {p0.x, p0.y, p1.x, p1.y, d0.x, d0.y, d1.x, d1.y};
+                        umma::tmem_st8(tmem_base + (uint32_t)((l - 1) * 32 + 8 * s), zs);
+                    }
                     f2 Phi, phi, zz;
+                    float keep[8];                          // (Phi, phi) of the row's two channel pairs -> tensor memory
                     frag::gelu_terms2(p0, Phi, phi, zz);
+                    keep[0] = Phi.x; keep[1] = Phi.y; keep[2] = phi.x; keep[3] = phi.y;
                     d0 = mul2(d0, fma2(p0, phi, Phi));
                     p0 = mul2(p0, Phi);
                     frag::gelu_terms2(p1, Phi, phi, zz);
+                    keep[4] = Phi.x; keep[5] = Phi.y; keep[6] = phi.x; keep[7] = phi.y;
                     d1 = mul2(d1, fma2(p1, phi, Phi));
                     p1 = mul2(p1, Phi);
+                    umma::tmem_st8(tmem_base + (uint32_t)((l - 1) * 32 + 16 + 8 * s), keep);
                 }
                 f2 hn[MT][2][2], hdn[MT][2][2];
 #pragma unroll
@@ -431,9 +491,11 @@ __global__ void __launch_bounds__(BwdCfg<MT>::kThreads, 1) field_backward_mma_ke
             // layer 4 (16 -> 1), LayerNorm outputs stay in registers; hb / hdb: adjoints of the output of
             // linear layer 3 and of its tangent (C layout)
             f2 hb[MT][2][2], hdb[MT][2][2];
+            umma::wait_st();                                // this sweep's stash and the previous tile's accumulators have landed
             {
-                const float4 last4 = accL[kAccLast * 32];
-                f2 last0 = make_float2(last4.x, last4.y), last1 = make_float2(last4.z, last4.w);
+                float last4[4];
+                umma::tmem_ld4(tmem_base + kTmemAccCol + 4u * kAccLast, last4); umma::wait_ld();
+                f2 last0 = make_float2(last4[0], last4[1]), last1 = make_float2(last4[2], last4[3]);
                 float obsum = 0.0f;
 #pragma unroll
                 for (int s = 0; s < kSlots; ++s) {
@@ -461,7 +523,10 @@ __global__ void __launch_bounds__(BwdCfg<MT>::kThreads, 1) field_backward_mma_ke
                     hb[s >> 1][0][s & 1] = hbv[0]; hb[s >> 1][1][s & 1] = hbv[1];
                     hdb[s >> 1][0][s & 1] = hdbv[0]; hdb[s >> 1][1][s & 1] = hdbv[1];
                 }
-                accL[kAccLast * 32] = make_float4(last0.x, last0.y, last1.x, last1.y);
+                {
+                    const float v4[4] = {last0.x, last0.y, last1.x, last1.y};
+                    umma::tmem_st4(tmem_base + kTmemAccCol + 4u * kAccLast, v4);
+                }
                 if constexpr (Cfg::kPoseInRegs) {
                     pose_reg[0] += obsum;
                 } else {
@@ -470,7 +535,8 @@ __global__ void __launch_bounds__(BwdCfg<MT>::kThreads, 1) field_backward_mma_ke
                     accL[kAccPose * 32] = p0;
                 }
             }
-#pragma unroll 1
+            // (unrolled: 1 % faster than a rolled loop since the stash left shared memory)
+#pragma unroll
             for (int l = 3; l >= 1; --l) {
                 // adjoints of gelu(z_l) and its tangent: W_l^T hb, W_l^T hdb
                 f2 gb[MT][2][2], gdb[MT][2][2];
@@ -486,31 +552,36 @@ __global__ void __launch_bounds__(BwdCfg<MT>::kThreads, 1) field_backward_mma_ke
                         frag::wgrad_a_from_packs(tdh[mt], tdl[mt]);
                     }
                 }
-                float4* accW = accL + (kAccHidden + 3 * (l - 1)) * 32;
-                f2 D[3][2];
-#pragma unroll
-                for (int n = 0; n < 3; ++n) {
-                    const float4 a = accW[n * 32];
-                    D[n][0] = make_float2(a.x, a.y); D[n][1] = make_float2(a.z, a.w);
+                f2 D[3][2];                                 // this layer's weight-gradient accumulators (12 TMEM columns)
+                const uint32_t tacc = tmem_base + kTmemAccCol + 4u * (kAccHidden + 3 * (l - 1));
+                {
+                    float v8[8], v4[4];
+                    umma::tmem_ld8(tacc, v8); umma::tmem_ld4(tacc + 8u, v4); umma::wait_ld();
+                    D[0][0] = make_float2(v8[0], v8[1]); D[0][1] = make_float2(v8[2], v8[3]);
+                    D[1][0] = make_float2(v8[4], v8[5]); D[1][1] = make_float2(v8[6], v8[7]);
+                    D[2][0] = make_float2(v4[0], v4[1]); D[2][1] = make_float2(v4[2], v4[3]);
                 }
-                const float2* st = stash + (l - 1) * kLayerStride;
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt) {
                     f2 z[2][2], zd[2][2], g[2][2], gd[2][2], g1[2][2], g2[2][2];      // [row half][channel pair]
+                    float keptz[16];                        // (z, zd) of the forward sweep: [row half][z pair 0, z pair 1, zd pair 0, zd pair 1]
+                    float kept[16];                         // (Phi, phi): [row half][pair][Phi.xy phi.xy]
+                    umma::tmem_ld16(tmem_base + (uint32_t)((l - 1) * 32), keptz);
+                    umma::tmem_ld16(tmem_base + (uint32_t)((l - 1) * 32 + 16), kept);
+                    umma::wait_ld();
 #pragma unroll
                     for (int hf = 0; hf < 2; ++hf) {
-                        const int s = 2 * mt + hf;
-                        z[hf][0] = st[(2 * s) * 32]; z[hf][1] = st[(2 * s + 1) * 32];
-                        zd[hf][0] = st[(kLayerPairs + 2 * s) * 32]; zd[hf][1] = st[(kLayerPairs + 2 * s + 1) * 32];
-                        gelu_pair(z[hf][0], zd[hf][0], g[hf][0], gd[hf][0], g1[hf][0], g2[hf][0]);
-                        gelu_pair(z[hf][1], zd[hf][1], g[hf][1], gd[hf][1], g1[hf][1], g2[hf][1]);
+                        z[hf][0] = make_float2(keptz[8 * hf], keptz[8 * hf + 1]); z[hf][1] = make_float2(keptz[8 * hf + 2], keptz[8 * hf + 3]);
+                        zd[hf][0] = make_float2(keptz[8 * hf + 4], keptz[8 * hf + 5]); zd[hf][1] = make_float2(keptz[8 * hf + 6], keptz[8 * hf + 7]);
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            const f2 Phi = make_float2(kept[8 * hf + 4 * q], kept[8 * hf + 4 * q + 1]);
+                            const f2 phi = make_float2(kept[8 * hf + 4 * q + 2], kept[8 * hf + 4 * q + 3]);
+                            gelu_pair_kept(z[hf][q], zd[hf][q], Phi, phi, g[hf][q], gd[hf][q], g1[hf][q], g2[hf][q]);
+                        }
                     }
                     // weight gradient of linear layer l over the 16 samples of this m-tile
-                    frag::wgrad_tile(D[0], th[mt], tl[mt], g[0][0], g[1][0]);
-                    frag::wgrad_tile(D[1], th[mt], tl[mt], g[0][1], g[1][1]);
-                    frag::wgrad_bias(D[2], th[mt], tl[mt]);
-                    frag::wgrad_tile(D[0], tdh[mt], tdl[mt], gd[0][0], gd[1][0]);
-                    frag::wgrad_tile(D[1], tdh[mt], tdl[mt], gd[0][1], gd[1][1]);
+                    frag::wgrad_hidden(D, th[mt], tl[mt], tdh[mt], tdl[mt], g, gd);
                     // LayerNorm / GELU adjoint: hb, hdb <- adjoints of the output of linear layer l - 1
 #pragma unroll
                     for (int hf = 0; hf < 2; ++hf) {
@@ -525,19 +596,31 @@ __global__ void __launch_bounds__(BwdCfg<MT>::kThreads, 1) field_backward_mma_ke
                         hdb[mt][0][hf] = hdbv[0]; hdb[mt][1][hf] = hdbv[1];
                     }
                 }
-#pragma unroll
-                for (int n = 0; n < 3; ++n) accW[n * 32] = make_float4(D[n][0].x, D[n][0].y, D[n][1].x, D[n][1].y);
+                {
+                    const float v8[8] = {D[0][0].x, D[0][0].y, D[0][1].x, D[0][1].y, D[1][0].x, D[1][0].y, D[1][1].x, D[1][1].y};
+                    const float v4[4] = {D[2][0].x, D[2][0].y, D[2][1].x, D[2][1].y};
+                    umma::tmem_st8(tacc, v8); umma::tmem_st4(tacc + 8u, v4);
+                }
             }
             // layer 0: weight gradient against the encoding and its tangent, then the encoding adjoint
             //   abar_c  = sum_k 2^k (ebar_sin cos - ebar_cos sin - da (edbar_cos cos + edbar_sin sin))
             //   adbar_c = sum_k 2^k (edbar_sin cos - edbar_cos sin)
             float abar[kSlots][3], adbar[kSlots][3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c)                      // the encoding comes back from shared memory
+#pragma unroll
+                for (int f = 0; f < 2; ++f) { e.cs[0][c][f] = sEnc[(4 * c + 2 * f) * 32]; e.sn[0][c][f] = sEnc[(4 * c + 2 * f + 1) * 32]; }
             {
                 f2 D0[7][2];
+                const uint32_t tacc0 = tmem_base + kTmemAccCol + 4u * kAccL0;
+                {
+                    float v16[16], v8[8], v4[4];
+                    umma::tmem_ld16(tacc0, v16); umma::tmem_ld8(tacc0 + 16u, v8); umma::tmem_ld4(tacc0 + 24u, v4); umma::wait_ld();
 #pragma unroll
-                for (int n = 0; n < 7; ++n) {
-                    const float4 a = accL[(kAccL0 + n) * 32];
-                    D0[n][0] = make_float2(a.x, a.y); D0[n][1] = make_float2(a.z, a.w);
+                    for (int n = 0; n < 4; ++n) { D0[n][0] = make_float2(v16[4 * n], v16[4 * n + 1]); D0[n][1] = make_float2(v16[4 * n + 2], v16[4 * n + 3]); }
+#pragma unroll
+                    for (int n = 0; n < 2; ++n) { D0[4 + n][0] = make_float2(v8[4 * n], v8[4 * n + 1]); D0[4 + n][1] = make_float2(v8[4 * n + 2], v8[4 * n + 3]); }
+                    D0[6][0] = make_float2(v4[0], v4[1]); D0[6][1] = make_float2(v4[2], v4[3]);
                 }
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt) {
@@ -582,9 +665,15 @@ __global__ void __launch_bounds__(BwdCfg<MT>::kThreads, 1) field_backward_mma_ke
                             frag::wgrad_tile_scalar(D0[2 * c + f], adh, adl, dcs.x, dsn.x, dcs.y, dsn.y);
                         }
                 }
+                {
+                    float v16[16], v8[8];
 #pragma unroll
-                for (int n = 0; n < 7; ++n)
-                    accL[(kAccL0 + n) * 32] = make_float4(D0[n][0].x, D0[n][0].y, D0[n][1].x, D0[n][1].y);
+                    for (int n = 0; n < 4; ++n) { v16[4 * n] = D0[n][0].x; v16[4 * n + 1] = D0[n][0].y; v16[4 * n + 2] = D0[n][1].x; v16[4 * n + 3] = D0[n][1].y; }
+#pragma unroll
+                    for (int n = 0; n < 2; ++n) { v8[4 * n] = D0[4 + n][0].x; v8[4 * n + 1] = D0[4 + n][0].y; v8[4 * n + 2] = D0[4 + n][1].x; v8[4 * n + 3] = D0[4 + n][1].y; }
+                    const float v4[4] = {D0[6][0].x, D0[6][0].y, D0[6][1].x, D0[6][1].y};
+                    umma::tmem_st16(tacc0, v16); umma::tmem_st8(tacc0 + 16u, v8); umma::tmem_st4(tacc0 + 24u, v4);
+                }
             }
             // back to lane == sample: the lanes of this half pick up their rows' encoding adjoints
 #pragma unroll
@@ -599,8 +688,9 @@ __global__ void __launch_bounds__(BwdCfg<MT>::kThreads, 1) field_backward_mma_ke
             }   // halves
             // ------------------------------------------------------------ 4. lane == sample: pose
             {
-                float x[3];
-                sample_position(rays, r, j, x);
+                float x[3];                                 // stashed by phase 1 (reloading the ray costs an L2 round trip here)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) x[c] = sPos[(warp * 3 + c) * 32 + lane];
                 const float dG[3] = {adj.y, adj.z, adj.w};
                 PoseTerms p;
                 pose_terms(x, I, pi_scale, adj.x, dG, p);
@@ -639,6 +729,13 @@ __global__ void __launch_bounds__(BwdCfg<MT>::kThreads, 1) field_backward_mma_ke
         }
         // ---------------------------------------------------------------- flush this segment
         {
+            umma::wait_st();                                // tensor memory -> this warp's shared-memory slots (read across warps below)
+#pragma unroll
+            for (int f = 0; f < kAccPose; ++f) {
+                float v4[4];
+                umma::tmem_ld4(tmem_base + kTmemAccCol + 4u * f, v4); umma::wait_ld();
+                accL[f * 32] = make_float4(v4[0], v4[1], v4[2], v4[3]);
+            }
             // last layer: reduce over the 8 quads (lane bits 2..4); bias / pose: over all 32 lanes
             float4 last = accL[kAccLast * 32];
             float v[16];
@@ -708,6 +805,9 @@ __global__ void __launch_bounds__(BwdCfg<MT>::kThreads, 1) field_backward_mma_ke
         }
         seg = seg_end;
     }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (threadIdx.x < 32) umma::tmem_free<Cfg::kTmemCols>(s_tmem);
     if (lane == 0 && rays.cull_stats != nullptr && tiles_visited) {
         atomicAdd(rays.cull_stats, (unsigned long long)tiles_culled);
         atomicAdd(rays.cull_stats + 1, (unsigned long long)tiles_visited);
@@ -781,7 +881,7 @@ static int setup() {
     if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return fail("vsrd_b200: cudaGetDeviceProperties failed%s");
     if (cudaFuncSetAttribute(field_backward_mma_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)BwdCfg<1>::kSmemBytes) != cudaSuccess)
-        return fail("vsrd_b200: cannot reserve %s of shared memory for field_backward_mma_kernel (built for sm_100a)", "217 KB");
+        return fail("vsrd_b200: cannot reserve %s of shared memory for field_backward_mma_kernel (built for sm_100a)", "166 KB");
     g_sms = prop.multiProcessorCount;
     return 0;
 }
@@ -834,3 +934,4 @@ int launch_field_backward_mma(const SceneDev& s, const RaysDev& r, const float* 
 }
 
 }  // namespace vsrd
+

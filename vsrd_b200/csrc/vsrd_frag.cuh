@@ -183,6 +183,32 @@ __device__ __forceinline__ void wgrad_bias(f2 (&D)[2], const uint32_t (&ah)[4], 
     mma_bf16(D, ah, kOnes, kOnes);
 }
 
+// Weight gradient of one hidden layer over the 16 samples of an m-tile: D[0], D[1] (inputs 0-7, 8-15) += adjoint x
+// activation + tangent adjoint x tangent activation, D[2] += adjoint x ones (bias).  g / gd: [row half][channel pair].
+// The MMAs are issued pass-major over the accumulators: two MMAs into the same accumulator are never back to back
+// (three-pass chains per accumulator wait on the tensor pipe's result latency: 1.3 % of the kernel).  Measured and not
+// kept: separate accumulators for the tangent products (five independent chains + 4 adds): slower.
+__device__ __forceinline__ void wgrad_hidden(f2 (&D)[3][2], const uint32_t (&th)[4], const uint32_t (&tl)[4],
+                                             const uint32_t (&tdh)[4], const uint32_t (&tdl)[4],
+                                             const f2 (&g)[2][2], const f2 (&gd)[2][2]) {
+    constexpr uint32_t kOnes = 0x3f803f80u;
+    uint32_t bh[2][2], bl[2][2];                           // [n-tile][row half]
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) pack_transposed(g[hf][nt], bh[nt][hf], bl[nt][hf]);
+    mma_bf16(D[0], th, bl[0][0], bl[0][1]); mma_bf16(D[1], th, bl[1][0], bl[1][1]); mma_bf16(D[2], tl, kOnes, kOnes);
+    mma_bf16(D[0], tl, bh[0][0], bh[0][1]); mma_bf16(D[1], tl, bh[1][0], bh[1][1]); mma_bf16(D[2], th, kOnes, kOnes);
+    mma_bf16(D[0], th, bh[0][0], bh[0][1]); mma_bf16(D[1], th, bh[1][0], bh[1][1]);
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) pack_transposed(gd[hf][nt], bh[nt][hf], bl[nt][hf]);
+    mma_bf16(D[0], tdh, bl[0][0], bl[0][1]); mma_bf16(D[1], tdh, bl[1][0], bl[1][1]);
+    mma_bf16(D[0], tdl, bh[0][0], bh[0][1]); mma_bf16(D[1], tdl, bh[1][0], bh[1][1]);
+    mma_bf16(D[0], tdh, bh[0][0], bh[0][1]); mma_bf16(D[1], tdh, bh[1][0], bh[1][1]);
+}
+
 // Reference weight layout (hyper_distance_field.py:57-73): layer l rows [out][fan_in + 1], bias last.
 //
 // LayerNorm centring folded into the weights (as in vsrd_field_umma.cu::stage_weights_umma): the fragments hold the CENTRED
