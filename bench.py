@@ -763,14 +763,15 @@ def run_native(args):
                          "peak": fma_peak_tflops, "unit": "TFLOP/s",
                          "frac": (achieved / fma_peak_tflops) if achieved else None,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this exact shape, from the
-                         # `ncu --set full` capture summarised in profiles/r01_v8_ncu_summary.txt (one pass over the
-                         # 25.5 MB adjoint buffer; everything else stays in L2 / shared memory)
+                         # `ncu --set full` capture named in `traffic_unit` (one pass over the 25.5 MB adjoint buffer;
+                         # everything else stays in L2 / shared / tensor memory)
                          "traffic": capture.get("traffic_bytes") if same_shape else None,
                          "traffic_unit": f"dram bytes read + written per launch (ncu --set full, {capture.get('source', 'no capture')})",
                          "peak_source": f"{sms} SMs x 128 lanes x 2 x sm_max_mhz {sm_max:.0f} (MEASURED_PEAKS.json clock)",
-                         "bound_note": "issue- / latency-bound FP32 work between mma.sync m16n8k16 (bf16 hi + lo) contractions: DRAM "
-                                       "traffic is one pass over the adjoint buffer (26 MB per launch, 0.6 % of the HBM roofline) and the "
-                                       "tensor pipe is ~28 % busy, so the kernel is rated against the FP32 FMA peak (DESIGN.md section 3)",
+                         "bound_note": "issue-bound FP32 work between mma.sync m16n8k16 (bf16 hi + lo) contractions, stash and weight-gradient "
+                                       "accumulators in tensor memory (tcgen05.st / tcgen05.ld): DRAM traffic is one pass over the adjoint "
+                                       "buffer (26 MB per launch, 0.7 % of the HBM roofline) and the tensor pipe is ~32 % busy, so the kernel "
+                                       "is rated against the FP32 FMA peak (DESIGN.md section 3)",
                          "forward_fine": {"kernel": ("cull_samples_kernel + field_forward_umma_kernel<4, true>" if fwd_pairs.get("fine")
                                                      else "field_forward_umma_kernel<4, false>") + " (tcgen05 / TMEM, vsrd_field_umma.cu)",
                                           "kernel_ms": per_kernel.get("field_forward_fine"),
