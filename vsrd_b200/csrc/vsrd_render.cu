@@ -190,6 +190,28 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// Warp sums of K values at once (K a power of two <= 32): after each exchange a lane keeps half of its values, so the
+// butterfly costs K - 1 + log2(32 / K) shuffles instead of 5 K.  Lane L ends up with the sum of value L / (32 / K); the
+// additions are those of warp_sum()'s butterfly in the same order (bit-identical results).
+template <int K>
+__device__ __forceinline__ float warp_sum_multi(float (&v)[K], int lane) {
+    static_assert(K >= 1 && K <= 32 && (K & (K - 1)) == 0, "K must be a power of two <= 32");
+    int o = 16;
+#pragma unroll
+    for (int w = K; w > 1; w >>= 1, o >>= 1) {
+        const bool upper = (lane & o) != 0;
+#pragma unroll
+        for (int i = 0; i < w / 2; ++i) {
+            const float send = upper ? v[i] : v[i + w / 2];
+            const float keep = upper ? v[i + w / 2] : v[i];
+            v[i] = keep + __shfl_xor_sync(kFull, send, o);
+        }
+    }
+#pragma unroll
+    for (; o; o >>= 1) v[0] += __shfl_xor_sync(kFull, v[0], o);
+    return v[0];
+}
+
 // inclusive multiplicative scan across the warp
 __device__ __forceinline__ float warp_scan_mul(float v, int lane) {
 #pragma unroll
@@ -268,14 +290,22 @@ __global__ void __launch_bounds__(VSRD_MAX_INTERVALS, NMAX <= 8 ? 2 : 1) composi
         eik = e * e;
     }
     const float k = valid ? omega / u.Z : 0.0f;
+    if constexpr (kRegs) {                                     // all label partials of the warp in one butterfly
+        float part[NMAX];
 #pragma unroll
-    for (int n = 0; n < NMAX; ++n) {
-        if (n < N) {
-            float num = 0.0f;                                  // softmin numerator exp(-d_n/T - mneg)
-            if constexpr (kRegs) { if (valid) num = ur.e[n]; }
-            else if (valid) num = expf(-(load(n).x / T) - u.mneg);
-            const float part = warp_sum(k * num);
-            if (lane == 0) s_lab[warp][n] = part;
+        for (int n = 0; n < NMAX; ++n) part[n] = (valid && n < N) ? k * ur.e[n] : 0.0f;   // softmin numerators exp(-d_n/T - mneg)
+        const float mine = warp_sum_multi<NMAX>(part, lane);
+        constexpr int kLanesPer = 32 / NMAX;
+        if ((lane & (kLanesPer - 1)) == 0 && lane / kLanesPer < N) s_lab[warp][lane / kLanesPer] = mine;
+    } else {
+#pragma unroll
+        for (int n = 0; n < NMAX; ++n) {
+            if (n < N) {
+                float num = 0.0f;                              // softmin numerator exp(-d_n/T - mneg)
+                if (valid) num = expf(-(load(n).x / T) - u.mneg);
+                const float part = warp_sum(k * num);
+                if (lane == 0) s_lab[warp][n] = part;
+            }
         }
     }
     eik = warp_sum(eik);
