@@ -240,8 +240,8 @@ struct LossDev {
 
 constexpr int kRegsMaxInstances = 16;
 
-template <int NMAX>
-__global__ void __launch_bounds__(VSRD_MAX_INTERVALS, NMAX <= 8 ? 2 : 1) composite_forward_kernel(
+template <int NMAX, int TMAX = VSRD_MAX_INTERVALS, int MINB = (NMAX <= 8 ? 2 : 1)>
+__global__ void __launch_bounds__(TMAX, MINB) composite_forward_kernel(
         SceneDev scene, RaysDev rays, float sigma, float rho, float eps, const float4* __restrict__ field,
         float* __restrict__ labels, float* __restrict__ grads, float* __restrict__ weights,
         LossDev loss, float* __restrict__ loss_out) {
@@ -556,11 +556,18 @@ int vsrd_composite_forward(const VsrdScene* scene, const VsrdRays* rays, const V
         VSRD_CHECK_ARG(loss_out != nullptr, "loss_out is NULL while loss targets are given");
         l = LossDev{loss->targets, loss->silhouette_weight, loss->eikonal_weight};
     }
+    if (render_setup()) return 1;
     const int grid = r.R, block = 32 * ((r.M + 31) / 32);
     cudaStream_t st = (cudaStream_t)stream;
 #define VSRD_LAUNCH_CF(NMAX) composite_forward_kernel<NMAX><<<grid, block, 0, st>>>( \
         s, r, params->std_deviation, params->cosine_ratio, params->epsilon, (const float4*)field, labels, gradients, weights, l, loss_out)
-    if (s.N <= 8) VSRD_LAUNCH_CF(8);
+    // Many rays per SM (HBM-bound regime): 48 registers -> 6 CTAs of <= 256 threads per SM instead of 4, 3.24 -> 3.59 TB/s at
+    // R = 64k (55 % of the HBM peak); at R = 1000 (7 CTAs per SM in all) the spills of that variant cost 2 us, so the
+    // 64-register one stays.  (40 registers / 7 CTAs: 3.17 TB/s.)
+    if (s.N <= 8 && block <= 256 && grid >= 32 * g_num_sms_render)
+        composite_forward_kernel<8, 256, 5><<<grid, block, 0, st>>>(
+            s, r, params->std_deviation, params->cosine_ratio, params->epsilon, (const float4*)field, labels, gradients, weights, l, loss_out);
+    else if (s.N <= 8) VSRD_LAUNCH_CF(8);
     else if (s.N <= 16) VSRD_LAUNCH_CF(16);
     else VSRD_LAUNCH_CF(32);
 #undef VSRD_LAUNCH_CF
@@ -595,7 +602,7 @@ int vsrd_composite_backward(const VsrdScene* scene, const VsrdRays* rays, const 
 #define VSRD_LAUNCH_CB(NMAX) composite_backward_kernel<NMAX><<<grid, block, 0, st>>>( \
         s, r, params->std_deviation, params->cosine_ratio, params->epsilon, (const float4*)field, \
         grad_labels, grad_gradients, grad_weights, l, labels, (float4*)adjoint, tile_shift, tiles_per_inst)
-    if (s.N <= 8) VSRD_LAUNCH_CB(8);
+    if (s.N <= 8) VSRD_LAUNCH_CB(8);       // (48 registers / 6 CTAs per SM, as in the forward kernel: 232 B of spills, 3.63 -> 3.46 TB/s)
     else if (s.N <= 16) VSRD_LAUNCH_CB(16);
     else VSRD_LAUNCH_CB(32);
 #undef VSRD_LAUNCH_CB
