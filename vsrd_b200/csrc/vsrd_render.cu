@@ -290,23 +290,16 @@ __global__ void __launch_bounds__(TMAX, MINB) composite_forward_kernel(
         eik = e * e;
     }
     const float k = valid ? omega / u.Z : 0.0f;
-    if constexpr (kRegs) {                                     // all label partials of the warp in one butterfly
+    {                                                          // all label partials of the warp in one butterfly
         float part[NMAX];
 #pragma unroll
-        for (int n = 0; n < NMAX; ++n) part[n] = (valid && n < N) ? k * ur.e[n] : 0.0f;   // softmin numerators exp(-d_n/T - mneg)
+        for (int n = 0; n < NMAX; ++n) {                       // softmin numerators exp(-d_n/T - mneg)
+            if constexpr (kRegs) part[n] = (valid && n < N) ? k * ur.e[n] : 0.0f;
+            else part[n] = (valid && n < N) ? k * expf(-(load(n).x / T) - u.mneg) : 0.0f;
+        }
         const float mine = warp_sum_multi<NMAX>(part, lane);
         constexpr int kLanesPer = 32 / NMAX;
         if ((lane & (kLanesPer - 1)) == 0 && lane / kLanesPer < N) s_lab[warp][lane / kLanesPer] = mine;
-    } else {
-#pragma unroll
-        for (int n = 0; n < NMAX; ++n) {
-            if (n < N) {
-                float num = 0.0f;                              // softmin numerator exp(-d_n/T - mneg)
-                if (valid) num = expf(-(load(n).x / T) - u.mneg);
-                const float part = warp_sum(k * num);
-                if (lane == 0) s_lab[warp][n] = part;
-            }
-        }
     }
     eik = warp_sum(eik);
     if (lane == 0) s_lab[warp][NMAX] = eik;
