@@ -326,6 +326,12 @@ class FrameLabeler:
         if self.inject_samples and (jitter is None or sorted_uniforms is None):
             raise RuntimeError("vsrd_b200: inject_samples=True needs jitter and sorted_uniforms for every step")
         phase = self.phase_of(self.step_index)
+        # Injected DEVICE tensors were produced on the caller's stream and may be freed by the caller as soon as this
+        # call returns: the labeler's stream waits for their producer, and the caching allocator is told that this
+        # stream still reads them (without both, a host that runs ahead of the GPU feeds a step the wrong batch).
+        on_device = [t for t in (pixel_indices, targets, jitter, sorted_uniforms) if t is not None and t.is_cuda]
+        if on_device:
+            self.stream.wait_stream(torch.cuda.current_stream(self.stream.device))
         with torch.cuda.stream(self.stream):
             if self.rays != "draw":
                 self.pixel_indices.copy_(pixel_indices.reshape(-1), non_blocking=True)
@@ -334,6 +340,8 @@ class FrameLabeler:
             if self.inject_samples:
                 self.jitter.copy_(jitter.reshape(self.jitter.shape), non_blocking=True)
                 self.sorted_uniforms.copy_(sorted_uniforms.reshape(self.sorted_uniforms.shape), non_blocking=True)
+            for t in on_device:
+                t.record_stream(self.stream)
             if self.use_graph and phase not in self._graphs and self._eager_done[phase] >= 3:
                 self._capture(phase)
             if self.use_graph and phase in self._graphs:
