@@ -1,5 +1,13 @@
-import os, sys, torch
-sys.path.insert(0, "/root/repo")
+#!/usr/bin/env python
+"""Launches the field forward / backward kernels 40 times on one full-size scene (cfg2, cfg3) and checks that every
+repeat is BIT-identical to the first (accumulation order is a function of the inputs only: no float atomics).
+    python tools/determinism_check.py"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from tests import fullsize_cases as fc
 from vsrd_b200 import ops
 dev = torch.device("cuda", 0)
