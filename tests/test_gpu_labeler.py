@@ -112,6 +112,30 @@ def test_optimised_boxes_match_cpu_oracle(case):
         assert float((got - f32).abs().max()) <= 5.0 * drift + 1e-3, (float((got - f32).abs().max()), drift)
 
 
+def test_injected_device_batches_are_stream_safe_and_runs_bit_reproducible():
+    """Two runs of the same optimisation with the per-step batches passed as device temporaries created on the CALLER's
+    stream (and dropped right after the call) end in bit-identical boxes: FrameLabeler.step() orders its own stream
+    behind the caller's and registers the tensors with the caching allocator.  Without that, a host running ahead of
+    the GPU fed steps the wrong batch and runs ended centimetres apart."""
+    from tests import optim_cases as oc
+    from vsrd_b200.frame import FrameLabeler, synthetic_frame_inputs
+    c = oc.get_case("cfg1")
+    frame, steps, warm, r, s = c["frame"], c["steps"], c["warmup"], c["num_rays"], c["num_samples"]
+    init = dict(locations=c["raw"][0], dimensions=c["raw"][1], orientations=c["raw"][2])
+    finals = []
+    for _ in range(3):
+        inputs = synthetic_frame_inputs(frame, torch.device("cuda", 0))
+        inputs.soft_masks = c["soft"].cuda().contiguous()
+        labeler = FrameLabeler(inputs, initial_parameters={k: v.cuda() for k, v in init.items()}, model_seed=oc.MODEL_SEED,
+                               num_steps=steps, warmup_steps=warm, num_rays=r, num_samples=s, rays="indices",
+                               inject_samples=True, use_graph=True)
+        for step in range(steps):
+            labeler.step(c["pix"][step].cuda(), jitter=c["jitter"][step].cuda(), sorted_uniforms=c["uniforms"][step].cuda())
+        finals.append(labeler.boxes()["boxes_3d"].cpu())
+    assert torch.equal(finals[0], finals[1]) and torch.equal(finals[0], finals[2]), \
+        [float((finals[0] - f).abs().max()) for f in finals[1:]]
+
+
 def test_labeler_moves_boxes_towards_ground_truth():
     """Full-resolution views (the 10 px soft-mask temperature of the reference's SoftRasterizer is tuned to
     376x1408 images): from a 0.5 m / 0.15 rad perturbation the optimisation must pull the boxes onto the
