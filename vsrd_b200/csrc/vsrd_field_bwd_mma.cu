@@ -76,6 +76,8 @@ struct BwdCfg {
     //   [96, 164)  weight-gradient accumulator fragments 0..16 (4 columns each)
     static constexpr uint32_t kTmemWarpCols = 164, kTmemAccCol = 96;
     static constexpr int kTmemCols = 512;
+    static_assert(kWarps % 4 == 0 && (kWarps / 4) * kTmemWarpCols <= kTmemCols, "warps of one lane quarter share its 512 columns");
+    static_assert(kTmemAccCol == 3 * 32 && kTmemAccCol + 4 * 17 == kTmemWarpCols, "stash of 3 layers + 17 accumulator fragments");
 };
 
 using frag::f2;
