@@ -51,6 +51,28 @@ def test_graph_replay_equals_eager_steps():
     assert int(a.state.read()["step"]) == 24
 
 
+def test_multi_step_replay_is_bit_identical_to_single_steps():
+    """advance() replays eight steps of a phase as one CUDA graph; the kernels and their order are those of eight
+    step() calls, so the results are bit-identical -- including across the phase changes, where it falls back to step()."""
+    frame, init = _frame()
+    kw = dict(num_steps=64, warmup_steps=20, num_rays=256, num_samples=24, seed=5)
+    a, _ = _labeler(frame, init, use_graph=True, **kw)
+    b, _ = _labeler(frame, init, use_graph=True, **kw)
+    counts = []
+    while a.step_index < a.num_steps:
+        counts.append(a.advance())
+    while b.step_index < b.num_steps:
+        b.step()
+    assert max(counts) == a.STEPS_PER_REPLAY and sum(counts) == 64, counts
+    assert a._multi_graphs, "no multi-step graph was captured"
+    ra, rb = a.boxes(), b.boxes()
+    assert torch.equal(ra["boxes_3d"], rb["boxes_3d"])
+    a.synchronize(); b.synchronize()
+    # the reported loss scalars are accumulated with float atomics (one per ray): equal up to summation order
+    assert torch.allclose(a.losses, b.losses, rtol=1e-5, atol=1e-7)
+    assert int(a.state.read()["step"]) == 64 and int(b.state.read()["step"]) == 64
+
+
 @pytest.mark.parametrize("case", ["small", "cfg1", "cfg1_full"])
 def test_optimised_boxes_match_cpu_oracle(case):
     """The same optimisation (identical rays, stratified jitter and importance uniforms injected into both) on the CUDA

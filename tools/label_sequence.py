@@ -71,7 +71,7 @@ while queue or active:
         fid = queue.pop(0)
         active.append((fid, make(fid)))
     for _, lab in active:
-        lab.step()
+        lab.advance()
     for fid, lab in [x for x in active if x[1].step_index >= a.steps]:
         out = lab.boxes()
         if int(lab.draw_failures):

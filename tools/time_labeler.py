@@ -14,8 +14,10 @@ ap.add_argument("--instances", type=int, default=8)
 ap.add_argument("--frames", type=int, default=1)
 ap.add_argument("--in-flight", type=int, default=1)
 ap.add_argument("--no-graph", action="store_true")
+ap.add_argument("--single-steps", action="store_true", help="frames in flight: step() per host iteration instead of advance()")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
+ADVANCE = not a.single_steps
 
 
 def make(fid):
@@ -61,7 +63,7 @@ if a.frames > 1:
             active.append(make(next_id)[1]); next_id += 1
             setup_s += time.perf_counter() - ts
         for lab in active:
-            lab.step()
+            lab.advance() if ADVANCE else lab.step()
         for lab in [l for l in active if l.step_index >= a.steps]:
             lab.boxes()["boxes_3d"].cpu()
             active.remove(lab); done += 1

@@ -188,6 +188,9 @@ class FrameLabeler:
         # phases: 0 = warm-up (box only), 1 = residual field, 2 = residual field with instance culling (late schedule)
         self._graphs: Dict[int, torch.cuda.CUDAGraph] = {}
         self._eager_done: Dict[int, int] = {0: 0, 1: 0, 2: 0}
+        # advance(): STEPS_PER_REPLAY consecutive steps of one phase captured as ONE graph (everything a step needs --
+        # schedule, ray draw, learning rates -- is device-resident), so the host issues one launch per 8 steps
+        self._multi_graphs: Dict[int, torch.cuda.CUDAGraph] = {}
 
     # ---- one optimisation step (main.py:328-865), enqueued on the current stream (= self.stream) ----
     def _step_body(self, residual: bool) -> None:
@@ -307,11 +310,33 @@ class FrameLabeler:
         self.state.cull = phase == 2
         self._step_body(phase >= 1)
 
-    def _capture(self, phase: int) -> None:
+    def _capture(self, phase: int, count: int = 1) -> None:
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph, stream=self.stream):
-            self._run_phase(phase)
-        self._graphs[phase] = graph
+            for _ in range(count):
+                self._run_phase(phase)
+        (self._graphs if count == 1 else self._multi_graphs)[phase] = graph
+
+    STEPS_PER_REPLAY = 8
+
+    def advance(self) -> int:
+        """Enqueues the next optimisation step(s) and returns how many: STEPS_PER_REPLAY at once, replayed as one CUDA
+        graph, when the labeler draws its own rays and samples (nothing comes from the host between steps) and those
+        steps lie in one phase of the schedule; a single step() otherwise.  The kernels and their order are exactly
+        those of step() called that many times -- only the number of host launches changes (the frames/hour of several
+        frames in flight is otherwise sensitive to how fast the host thread turns)."""
+        k = self.STEPS_PER_REPLAY
+        phase = self.phase_of(self.step_index)
+        if (self.use_graph and self.rays == "draw" and not self.inject_samples and phase in self._graphs
+                and self.step_index + k <= self.num_steps and self.phase_of(self.step_index + k - 1) == phase):
+            with torch.cuda.stream(self.stream):
+                if phase not in self._multi_graphs:
+                    self._capture(phase, k)
+                self._multi_graphs[phase].replay()
+            self.step_index += k
+            return k
+        self.step()
+        return 1
 
     def step(self, pixel_indices: Optional[torch.Tensor] = None, targets: Optional[torch.Tensor] = None,
              jitter: Optional[torch.Tensor] = None, sorted_uniforms: Optional[torch.Tensor] = None) -> None:
@@ -430,7 +455,7 @@ class FrameLabeler:
         if self.rays != "draw" or self.inject_samples:
             raise RuntimeError("vsrd_b200: run() draws its own rays and samples; drive step(...) yourself when injecting them")
         while self.step_index < self.num_steps:
-            self.step()
+            self.advance()
         out = self.boxes()
         out["losses"] = self.losses.clone()
         failures = int(self.draw_failures)           # the only host sync of the frame

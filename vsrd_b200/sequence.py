@@ -86,7 +86,8 @@ def label_frames_in_flight(frame_ids: Iterable[int], make_labeler: Callable[[int
             fid = queue.pop(0)
             active.append((fid, make_labeler(fid)))
         for _, labeler in active:
-            labeler.step()
+            # FrameLabeler.advance() enqueues several steps per host launch where it can; anything with .step() works
+            (labeler.advance if hasattr(labeler, "advance") else labeler.step)()
         for fid, labeler in [item for item in active if item[1].step_index >= num_steps]:
             results[fid] = dict(boxes_3d=labeler.boxes()["boxes_3d"])
             if on_done is not None:
