@@ -126,3 +126,28 @@ def test_in_flight_scheduler_runs_every_frame_to_completion():
     assert sorted(out) == [2, 4, 5, 7, 9] and FakeLabeler.peak == 2 and FakeLabeler.live == 0
     assert done == [(5, 3), (2, 3), (9, 3), (4, 3), (7, 3)]
     assert all(float(out[f]["boxes_3d"][0, 0, 0]) == f for f in out)
+
+
+def test_in_flight_scheduler_prefers_multi_step_advance():
+    """A labeler that offers advance() (FrameLabeler: several steps per host launch) is driven through it; frames whose
+    step counts differ still finish exactly at num_steps."""
+    class Advancing:
+        def __init__(self, fid):
+            self.fid, self.step_index, self.calls = fid, 0, 0
+
+        def step(self):
+            raise AssertionError("advance() must be preferred")
+
+        def advance(self):
+            self.calls += 1
+            n = min(8, 20 - self.step_index)
+            self.step_index += n
+            return n
+
+        def boxes(self):
+            return dict(boxes_3d=torch.full((2, 8, 3), float(self.fid)))
+
+    seen = []
+    out = sequence.label_frames_in_flight([1, 3, 2], Advancing, num_steps=20, in_flight=2,
+                                          on_done=lambda fid, lab: seen.append((fid, lab.step_index, lab.calls)))
+    assert sorted(out) == [1, 2, 3] and seen == [(1, 20, 3), (3, 20, 3), (2, 20, 3)]
